@@ -1,0 +1,152 @@
+"""Pin the oracle (oracle/numpy_oracle.py and oracle/fdtd_oracle.c) to the golden vectors
+produced by the REAL reference (oracle/make_golden.py -> tests/golden/*.npz), bit for bit.
+CPU only."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, numpy_oracle as npo
+
+DT, DX, FC = 5e-14, 1e-4, 30e9
+SIZES = [(11, 11), (12, 13), (16, 11), (37, 53), (64, 48)]
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def single(golden_dir):
+    return np.load(os.path.join(golden_dir, "single_call.npz"))
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("shape", SIZES)
+def test_single_call_numpy(single, dtype, shape):
+    k = f"{dtype}_{shape[0]}x{shape[1]}"
+    eps, mu = single[k + "_eps"], single[k + "_mu"]
+    Ez, Hx, Hy = single[k + "_Ez0"].copy(), single[k + "_Hx0"].copy(), single[k + "_Hy0"].copy()
+    npo.update_Hx_Hy(Ez, Hx, Hy, mu, eps, DT, DX)
+    assert np.array_equal(Hx, single[k + "_Hx1"]) and np.array_equal(Hy, single[k + "_Hy1"])
+    npo.update_Ez(Ez, Hx, Hy, mu, eps, DT, DX)
+    assert Ez.dtype == np.dtype(dtype)
+    assert np.array_equal(Ez, single[k + "_Ez1"])
+
+
+@pytest.mark.parametrize("omp", [False, True])
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("shape", SIZES)
+def test_single_call_c(single, dtype, shape, omp):
+    k = f"{dtype}_{shape[0]}x{shape[1]}"
+    eps, mu = single[k + "_eps"], single[k + "_mu"]
+    ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(dtype))
+    Ez, Hx, Hy = single[k + "_Ez0"].copy(), single[k + "_Hx0"].copy(), single[k + "_Hy0"].copy()
+    c_oracle.update_h(Ez, Hx, Hy, ch, omp=omp)
+    assert np.array_equal(Hx, single[k + "_Hx1"]) and np.array_equal(Hy, single[k + "_Hy1"])
+    c_oracle.update_e(Ez, Hx, Hy, ce, coef, omp=omp)
+    assert np.array_equal(Ez, single[k + "_Ez1"])
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_demo200_c_oracle(golden_dir, dtype):
+    """fdtd.py defaults, vacuum: 1000 steps, probe trace at every step + final arrays + SHA-256."""
+    g = np.load(os.path.join(golden_dir, f"demo200_vacuum_{dtype}.npz"))
+    dt_ = np.dtype(dtype)
+    Ez, Hx, Hy = npo.grid_init(200, 200, dt_)
+    eps, mu = npo.material_init(None, 200, 200)
+    ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, dt_)
+    amp = npo.source_table("ricker", 1000, DT, FC)
+    probes = [tuple(p) for p in g["probes"]]
+    trace = c_oracle.run(Ez, Hx, Hy, ce, ch, coef, 1000, amp, [(100, 100)], probes)
+    assert np.array_equal(trace, g["trace"])
+    for name, a in (("Ez", Ez), ("Hx", Hx), ("Hy", Hy)):
+        assert np.array_equal(a, g[name])
+        assert _sha(a) == str(g["sha_" + name])
+
+
+def test_appendix_b_known_answers(golden_dir):
+    """SURVEY.md Appendix B values (produced by the reference) against the golden file."""
+    g = np.load(os.path.join(golden_dir, "demo200_vacuum_float64.npz"))
+    tr = g["trace"]  # probes: (100,100), (100,150), (3,3), (0,0), ...
+    assert tr[0, 0] == -0.0009692515861872089
+    assert tr[99, 1] == -2.3958379069786566e-47
+    assert tr[666, 0] == 0.11909875914863788
+    assert tr[999, 0] == 0.036564114544762216 and tr[999, 1] == 0.0334730629924441
+    assert tr[999, 2] == -0.0002744562112140161 and tr[999, 3] == 0.00013691961547454367
+    assert str(g["sha_Ez"]).startswith("19c926b4a21ea56c")
+    assert str(g["sha_Hx"]).startswith("e98b2a4c5c233397")
+    assert str(g["sha_Hy"]).startswith("f1b7155d83734e31")
+    g32 = np.load(os.path.join(golden_dir, "demo200_vacuum_float32.npz"))
+    assert str(g32["sha_Ez"]).startswith("9cc77c8131c0d7d5")
+    assert g32["Ez"].dtype == np.float32
+    # Hx last row / Hy last column are never written (main.py:70,74)
+    assert not g["Hx"][-1].any() and not g["Hy"][:, -1].any()
+    assert g["Hx"][:, 0].any() and g["Hy"][0].any()
+
+
+RUNS = [(37, 53, "ricker"), (96, 130, "sinusoidal"), (11, 11, "ricker")]
+
+
+@pytest.mark.parametrize("impl", ["numpy", "c", "c_omp"])
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("case", RUNS)
+def test_random_runs(golden_dir, case, dtype, impl):
+    g = np.load(os.path.join(golden_dir, "random_runs.npz"))
+    R, C, kind = case
+    k = f"{dtype}_{R}x{C}_{kind}"
+    eps, mu = g[k + "_eps"], g[k + "_mu"]
+    Ez, Hx, Hy = g[k + "_Ez0"].copy(), g[k + "_Hx0"].copy(), g[k + "_Hy0"].copy()
+    n = int(g[k + "_nsteps"])
+    probes = [tuple(p) for p in g[k + "_probes"]]
+    src = tuple(int(v) for v in g[k + "_src"])
+    if impl == "numpy":
+        _, _, _, trace = npo.run(Ez, Hx, Hy, mu, eps, DT, DX, n, source=(src[0], src[1], FC, kind), probes=probes)
+    else:
+        ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(dtype))
+        amp = npo.source_table(kind, n, DT, FC)
+        trace = c_oracle.run(Ez, Hx, Hy, ce, ch, coef, n, amp, [src], probes, omp=(impl == "c_omp"))
+    assert np.array_equal(trace, g[k + "_trace"])
+    assert np.array_equal(Ez, g[k + "_Ez"]) and np.array_equal(Hx, g[k + "_Hx"]) and np.array_equal(Hy, g[k + "_Hy"])
+
+
+def test_material_and_sources(golden_dir):
+    g = np.load(os.path.join(golden_dir, "material_sources.npz"))
+    png = os.path.join(golden_dir, "structure.png")
+    for (R, C, bp) in [(64, 80, 10.0), (200, 200, 10.0), (37, 53, 4.0)]:
+        eps, mu = npo.material_init(png, R, C, bp)
+        assert np.array_equal(eps, g[f"eps_{R}x{C}_bp{bp:g}"]) and np.array_equal(mu, g[f"mu_{R}x{C}_bp{bp:g}"])
+    eps, mu = npo.material_init(None, 23, 17)
+    assert np.array_equal(eps, g["eps_none_23x17"]) and np.array_equal(mu, g["mu_none_23x17"])
+    steps = g["steps"]
+    assert np.array_equal(np.array([npo.ricker_amplitude(int(i) * DT, FC) for i in steps]), g["ricker_amp"])
+    assert np.array_equal(np.array([npo.sinusoidal_amplitude(int(i) * DT, FC) for i in steps]), g["sinus_amp"])
+    assert np.array_equal(npo.ricker(6, 7, 2, 3, 667 * DT, FC), g["ricker_dense_6x7"])
+    assert g["ricker_amp"][0] == -0.0009692515861872089 and g["ricker_amp"][7] == 0.9999925978119194
+    tab = npo.source_table("ricker", 3, DT, FC, step0=666)
+    assert np.array_equal(tab, g["ricker_amp"][6:9])
+
+
+def test_oracle_matches_live_reference_when_present():
+    """If the reference tree is mounted (authoring container), cross-check live on a fresh seed."""
+    from oracle import ref_loader
+
+    if not ref_loader.reference_available():
+        pytest.skip("reference tree not present (expected on the GPU box)")
+    ref = ref_loader.load_reference_main()
+    rng = np.random.default_rng(99)
+    for dtype in (np.float32, np.float64):
+        R, C = 29, 41
+        eps = (npo.EPSILON0 * (1 + 9 * rng.random((R, C)))).astype(dtype)
+        mu = (np.ones((R, C)) * npo.MU0).astype(dtype)
+        a = [rng.standard_normal(s).astype(dtype) for s in ((R, C), (R, C - 1), (R - 1, C))]
+        b = [x.copy() for x in a]
+        for i in range(25):
+            ref.update_Hx_Hy(a[0], a[1], a[2], mu, eps, DT, DX)
+            ref.update_Ez(a[0], a[1], a[2], mu, eps, DT, DX)
+            a[0] += ref.ricker(R, C, R // 2, C // 2, i * DT, FC)
+        ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(dtype))
+        c_oracle.run(b[0], b[1], b[2], ce, ch, coef, 25, npo.source_table("ricker", 25, DT, FC), [(R // 2, C // 2)])
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
