@@ -1,0 +1,746 @@
+// libfdtd2d: C-ABI implementation (include/fdtd2d.h) over the sm_100a kernels.
+// Host-side logic only: handle lifetime, padded device layout, tile planning, launches.
+// There is no CPU compute path in this file or anywhere in the library.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fdtd2d.h"
+#include "common.cuh"
+#include "tile_generic.cuh"
+
+using namespace fdtd2d;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(e_ == cudaErrorMemoryAllocation ? FDTD2D_ENOMEM : FDTD2D_ECUDA,     \
+                        "%s failed: %s", #expr, cudaGetErrorString(e_));                   \
+    } while (0)
+
+#define REQUIRE(cond, ...)                                \
+    do {                                                  \
+        if (!(cond)) return fail(FDTD2D_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// tile geometry of the generic kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int G_TH = 36, G_TW = 128, G_NT = 256;
+constexpr int MIN_LAST = 8;  // smallest core extent allowed for the last tile row/column (ring safety)
+
+struct TilePlan {
+    int k = 0, hx = 0, CH = 0, CW = 0, tiles_y = 0, tiles_x = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct fdtd2d_sim {
+    int dtype = 0, device = 0, batch = 1;
+    int Rg = 0, C = 0, row_begin = 0, row_end = 0, halo = 0, row0 = 0, Rl = 0;
+    bool has_top_nb = false, has_bot_nb = false;
+    size_t esize = 4, pitch = 0, grid_elems = 0;
+    void* field[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    void* ce = nullptr;
+    void* ch = nullptr;
+    void* mur = nullptr;
+    int cur = 0;
+    bool coeffs_set = false, mur_set = false;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // sources
+    int n_src = 0, n_waves = 0, amp_steps = 0;
+    Cell* d_src = nullptr;
+    int* d_src_range = nullptr;
+    double* d_amp = nullptr;
+    // probes
+    int n_probe = 0;
+    Cell* d_probe = nullptr;
+    int* d_probe_range = nullptr;
+    void* d_trace = nullptr;
+    long long trace_cap = 0;
+    std::vector<int> probe_perm;  // sorted position -> caller's index
+    long long step = 0, launches = 0;
+    int variant = 0;
+};
+
+static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+static int plan_axis(int extent, int core_max, int quantum, int* core, int* tiles) {
+    int c = core_max;
+    while (c >= core_max / 2 && c > 0) {
+        int t = (extent + c - 1) / c;
+        int rem = extent - (t - 1) * c;
+        if (t == 1 || rem >= MIN_LAST) {
+            *core = c;
+            *tiles = t;
+            return 0;
+        }
+        c -= quantum;
+    }
+    return -1;
+}
+
+static int plan_tiles(const fdtd2d_sim* s, int k, TilePlan* tp) {
+    const int vn = (int)(16 / s->esize);
+    tp->k = k;
+    tp->hx = (int)round_up((size_t)k, (size_t)vn);
+    if (plan_axis(s->Rl, G_TH - 2 * k, 1, &tp->CH, &tp->tiles_y) != 0 ||
+        plan_axis(s->C, G_TW - 2 * tp->hx, vn, &tp->CW, &tp->tiles_x) != 0)
+        return fail(FDTD2D_EINVAL, "cannot tile a %d x %d grid with k=%d", s->Rl, s->C, k);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels: coefficient maps and synthetic media
+// ------------------------------------------------------------------------------------------------
+// ce <- dt/(ce*dx), ch <- dt/(ch*dx) in place (the buffers hold eps and mu on entry), main.py:27,70,74.
+template <typename T>
+__global__ void coeff_from_materials_kernel(T* ce, T* ch, long long n, T dt, T dx) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const T e = ce[i], m = ch[i];
+        // padding cells hold 0: keep them 0 instead of dt/0 = inf
+        ce[i] = (e == (T)0) ? (T)0 : div_rn(dt, mul_rn(e, dx));
+        ch[i] = (m == (T)0) ? (T)0 : div_rn(dt, mul_rn(m, dx));
+    }
+}
+
+// Mur coefficient from the corner cell's materials, main.py:30-31.
+template <typename T> __device__ __forceinline__ T mur_from(T mu00, T eps00, T dt, T dx) {
+    const T c = div_rn((T)1, sqrt_rn(mul_rn(mu00, eps00)));
+    const T cdt = mul_rn(c, dt);
+    return div_rn(sub_rn(cdt, dx), add_rn(cdt, dx));
+}
+
+// eps/mu of cell (0,0) of every grid are still in ce/ch when this runs (before the in-place transform).
+template <typename T>
+__global__ void mur_from_materials_kernel(const T* eps, const T* mu, long long grid_stride, int batch, T dt, T dx,
+                                          T* mur) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch) mur[b] = mur_from(mu[b * grid_stride], eps[b * grid_stride], dt, dx);
+}
+
+// eps = eps0*(1 + span*u(seed, grid, global row, col)), mu = mu0, then the same transform as above.
+template <typename T>
+__global__ void random_materials_kernel(T* ce, T* ch, T* mur, int Rl, int C, int pitch, int row0, long long grid_stride,
+                                        int batch, uint64_t seed, T span, T eps0, T mu0, T dt, T dx) {
+    const long long per_grid = (long long)Rl * C;
+    const long long n = per_grid * batch;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const T chv = div_rn(dt, mul_rn(mu0, dx));
+    for (; i < n; i += stride) {
+        const int b = (int)(i / per_grid);
+        const long long r = i - (long long)b * per_grid;
+        const int li = (int)(r / C), j = (int)(r - (long long)li * C);
+        const T u = (T)hash_uniform(seed, (uint32_t)b, (uint32_t)(li + row0), (uint32_t)j);
+        const T eps = mul_rn(eps0, add_rn((T)1, mul_rn(span, u)));
+        const long long o = (long long)b * grid_stride + (long long)li * pitch + j;
+        ce[o] = div_rn(dt, mul_rn(eps, dx));
+        ch[o] = chv;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < batch && mur) {
+        // every handle can form the coefficient of global cell (0,0) of its grids
+        for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+            const T u = (T)hash_uniform(seed, (uint32_t)b, 0u, 0u);
+            const T eps = mul_rn(eps0, add_rn((T)1, mul_rn(span, u)));
+            mur[b] = mur_from(mu0, eps, dt, dx);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+static int use_device(const fdtd2d_sim* s) {
+    CUDA_TRY(cudaSetDevice(s->device));
+    return 0;
+}
+
+static int hy_rows(const fdtd2d_sim* s) {
+    // Hy has one row fewer than Ez when the handle holds the global last row (main.py:84)
+    return (s->row0 + s->Rl == s->Rg) ? s->Rl - 1 : s->Rl;
+}
+
+template <typename T> static int set_smem_attr() {
+    static bool done[2] = {false, false};
+    const int idx = sizeof(T) == 4 ? 0 : 1;
+    if (!done[idx]) {
+        CUDA_TRY(cudaFuncSetAttribute(tile_generic_kernel<T, G_TH, G_TW, G_NT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(6 * G_TH * G_TW * sizeof(T))));
+        done[idx] = true;
+    }
+    return 0;
+}
+
+template <typename T> static int launch_pass(fdtd2d_sim* s, int k, int phases) {
+    TilePlan tp;
+    if (int rc = plan_tiles(s, k, &tp)) return rc;
+    PassParams<T> p;
+    memset(&p, 0, sizeof p);
+    for (int f = 0; f < 3; ++f) {
+        p.in[f] = static_cast<const T*>(s->field[s->cur][f]);
+        p.out[f] = static_cast<T*>(s->field[s->cur ^ 1][f]);
+    }
+    p.ce = static_cast<const T*>(s->ce);
+    p.ch = static_cast<const T*>(s->ch);
+    p.mur = static_cast<const T*>(s->mur);
+    p.grid_stride = (long long)s->grid_elems;
+    p.pitch = (int)s->pitch;
+    p.Rg = s->Rg;
+    p.C = s->C;
+    p.row0 = s->row0;
+    p.Rl = s->Rl;
+    p.own_begin = s->row_begin;
+    p.own_end = s->row_end;
+    p.k = k;
+    p.hx = tp.hx;
+    p.phases = phases;
+    p.CH = tp.CH;
+    p.CW = tp.CW;
+    p.tiles_y = tp.tiles_y;
+    p.tiles_x = tp.tiles_x;
+    p.tile_list = nullptr;
+    p.src = s->d_src;
+    p.src_range = s->n_src ? s->d_src_range : nullptr;
+    p.amp = s->d_amp;
+    p.amp_steps = s->amp_steps;
+    p.step0 = s->step;
+    p.probes = s->d_probe;
+    p.probe_range = s->n_probe ? s->d_probe_range : nullptr;
+    p.n_probe = s->n_probe;
+    p.trace = static_cast<T*>(s->d_trace);
+    p.trace_cap = s->trace_cap;
+
+    if (int rc = set_smem_attr<T>()) return rc;
+    const long long n_tiles = (long long)s->batch * tp.tiles_y * tp.tiles_x;
+    if (n_tiles > 0x7fffffffLL) return fail(FDTD2D_EINVAL, "too many tiles");
+    const size_t smem = 6 * G_TH * G_TW * sizeof(T);
+    tile_generic_kernel<T, G_TH, G_TW, G_NT><<<(unsigned)n_tiles, G_NT, smem, s->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    s->launches += 1;
+    return 0;
+}
+
+static int run_pass(fdtd2d_sim* s, int k, int phases) {
+    int rc = s->dtype == FDTD2D_F32 ? launch_pass<float>(s, k, phases) : launch_pass<double>(s, k, phases);
+    if (rc) return rc;
+    s->cur ^= 1;
+    return 0;
+}
+
+// 2-D copy between a dense host array (rows x width elements) and the padded device layout
+static int copy2d(const fdtd2d_sim* s, void* dev, void* host, int rows, int width, bool to_device) {
+    const size_t wbytes = (size_t)width * s->esize;
+    if (to_device)
+        CUDA_TRY(cudaMemcpy2DAsync(dev, s->pitch * s->esize, host, wbytes, wbytes, rows, cudaMemcpyHostToDevice,
+                                   s->stream));
+    else
+        CUDA_TRY(cudaMemcpy2DAsync(host, wbytes, dev, s->pitch * s->esize, wbytes, rows, cudaMemcpyDeviceToHost,
+                                   s->stream));
+    return 0;
+}
+
+static int transfer_field(fdtd2d_sim* s, void* dev, void* host, int rows_host, int width, bool to_device) {
+    // per grid: rows_host x width on the host, Rl x pitch on the device
+    for (int b = 0; b < s->batch; ++b) {
+        char* d = static_cast<char*>(dev) + (size_t)b * s->grid_elems * s->esize;
+        char* h = static_cast<char*>(host) + (size_t)b * rows_host * width * s->esize;
+        if (int rc = copy2d(s, d, h, rows_host, width, to_device)) return rc;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int fdtd2d_abi_version(void) { return FDTD2D_ABI_VERSION; }
+
+const char* fdtd2d_last_error(void) { return g_err.c_str(); }
+
+int fdtd2d_device_count(int* count) {
+    REQUIRE(count, "count is null");
+    *count = 0;
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return 0;
+}
+
+static int create_impl(fdtd2d_sim** out, int Rg, int C, int row_begin, int row_end, int halo, int dtype, int device,
+                       int batch) {
+    REQUIRE(out, "out is null");
+    *out = nullptr;
+    REQUIRE(Rg >= 2 * RING + 1 && C >= 2 * RING + 1, "rows and cols must be >= 11 (got %d x %d)", Rg, C);
+    REQUIRE(dtype == FDTD2D_F32 || dtype == FDTD2D_F64, "dtype must be FDTD2D_F32 or FDTD2D_F64");
+    REQUIRE(batch >= 1, "batch must be >= 1");
+    REQUIRE(0 <= row_begin && row_begin < row_end && row_end <= Rg, "bad slab rows [%d, %d) of %d", row_begin, row_end, Rg);
+    REQUIRE(halo >= 0 && halo <= FDTD2D_MAX_K, "halo must be in [0, %d]", FDTD2D_MAX_K);
+    const bool top_nb = row_begin > 0, bot_nb = row_end < Rg;
+    if (top_nb || bot_nb) {
+        REQUIRE(batch == 1, "slab handles must have batch = 1");
+        REQUIRE(halo >= 1, "a slab with neighbours needs halo >= 1");
+        REQUIRE(row_end - row_begin >= 2 * FDTD2D_MAX_K + 2 * RING, "slab of %d rows is too thin", row_end - row_begin);
+    }
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return fail(FDTD2D_ECUDA, "no CUDA device (libfdtd2d has no CPU fallback)");
+    REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+
+    const int row0_ = row_begin - (top_nb ? halo : 0);
+    const int rl_ = (row_end + (bot_nb ? halo : 0)) - row0_;
+    REQUIRE(row0_ >= 0 && row0_ + rl_ <= Rg, "halo reaches outside the grid");
+
+    fdtd2d_sim* s = new (std::nothrow) fdtd2d_sim();
+    if (!s) return fail(FDTD2D_ENOMEM, "host allocation failed");
+    s->dtype = dtype;
+    s->device = device;
+    s->batch = batch;
+    s->Rg = Rg;
+    s->C = C;
+    s->row_begin = row_begin;
+    s->row_end = row_end;
+    s->halo = halo;
+    s->has_top_nb = top_nb;
+    s->has_bot_nb = bot_nb;
+    s->row0 = row0_;
+    s->Rl = rl_;
+    s->esize = dtype == FDTD2D_F32 ? 4 : 8;
+    s->pitch = round_up((size_t)C, 128 / s->esize);  // rows start on 128-byte lines
+    s->grid_elems = (size_t)s->Rl * s->pitch;
+    const size_t bytes = s->grid_elems * s->esize * (size_t)batch;
+
+    cudaError_t e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(FDTD2D_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
+    s->stream = s->own_stream;
+    void** bufs[9] = {&s->field[0][0], &s->field[0][1], &s->field[0][2], &s->field[1][0], &s->field[1][1],
+                      &s->field[1][2], &s->ce,          &s->ch,          &s->mur};
+    for (int i = 0; i < 9; ++i) {
+        const size_t nb = i == 8 ? (size_t)batch * s->esize : bytes;
+        e = cudaMalloc(bufs[i], nb);
+        if (e == cudaSuccess) e = cudaMemsetAsync(*bufs[i], 0, nb, s->stream);
+        if (e != cudaSuccess) {
+            fdtd2d_destroy(s);
+            return fail(e == cudaErrorMemoryAllocation ? FDTD2D_ENOMEM : FDTD2D_ECUDA,
+                        "device allocation of %zu bytes failed: %s", nb, cudaGetErrorString(e));
+        }
+    }
+    *out = s;
+    return 0;
+}
+
+int fdtd2d_create(fdtd2d_sim** out, int rows, int cols, int dtype, int device, int batch) {
+    return create_impl(out, rows, cols, 0, rows, 0, dtype, device, batch);
+}
+
+int fdtd2d_create_slab(fdtd2d_sim** out, int global_rows, int cols, int row_begin, int row_end, int halo, int dtype,
+                       int device) {
+    return create_impl(out, global_rows, cols, row_begin, row_end, halo, dtype, device, 1);
+}
+
+int fdtd2d_destroy(fdtd2d_sim* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int h = 0; h < 2; ++h)
+        for (int f = 0; f < 3; ++f) cudaFree(s->field[h][f]);
+    cudaFree(s->ce);
+    cudaFree(s->ch);
+    cudaFree(s->mur);
+    cudaFree(s->d_src);
+    cudaFree(s->d_src_range);
+    cudaFree(s->d_amp);
+    cudaFree(s->d_probe);
+    cudaFree(s->d_probe_range);
+    cudaFree(s->d_trace);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+    return 0;
+}
+
+int fdtd2d_set_stream(fdtd2d_sim* s, void* cuda_stream) {
+    REQUIRE(s, "handle is null");
+    if (int rc = use_device(s)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->stream = static_cast<cudaStream_t>(cuda_stream);
+    return 0;
+}
+
+int fdtd2d_reset_stream(fdtd2d_sim* s) {
+    REQUIRE(s, "handle is null");
+    if (int rc = use_device(s)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->stream = s->own_stream;
+    return 0;
+}
+
+int fdtd2d_sync(fdtd2d_sim* s) {
+    REQUIRE(s, "handle is null");
+    if (int rc = use_device(s)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int fdtd2d_geometry(const fdtd2d_sim* s, int* local_rows, int* cols, int* row0, int* global_rows, int* batch,
+                    int* dtype, size_t* pitch_elems) {
+    REQUIRE(s, "handle is null");
+    if (local_rows) *local_rows = s->Rl;
+    if (cols) *cols = s->C;
+    if (row0) *row0 = s->row0;
+    if (global_rows) *global_rows = s->Rg;
+    if (batch) *batch = s->batch;
+    if (dtype) *dtype = s->dtype;
+    if (pitch_elems) *pitch_elems = s->pitch;
+    return 0;
+}
+
+int fdtd2d_upload_state(fdtd2d_sim* s, const void* Ez, const void* Hx, const void* Hy) {
+    REQUIRE(s && Ez && Hx && Hy, "null argument");
+    if (int rc = use_device(s)) return rc;
+    void** f = s->field[s->cur];
+    if (int rc = transfer_field(s, f[0], const_cast<void*>(Ez), s->Rl, s->C, true)) return rc;
+    if (int rc = transfer_field(s, f[1], const_cast<void*>(Hx), s->Rl, s->C - 1, true)) return rc;
+    if (int rc = transfer_field(s, f[2], const_cast<void*>(Hy), hy_rows(s), s->C, true)) return rc;
+    return 0;
+}
+
+int fdtd2d_download_state(fdtd2d_sim* s, void* Ez, void* Hx, void* Hy) {
+    REQUIRE(s, "handle is null");
+    if (int rc = use_device(s)) return rc;
+    void** f = s->field[s->cur];
+    if (Ez)
+        if (int rc = transfer_field(s, f[0], Ez, s->Rl, s->C, false)) return rc;
+    if (Hx)
+        if (int rc = transfer_field(s, f[1], Hx, s->Rl, s->C - 1, false)) return rc;
+    if (Hy)
+        if (int rc = transfer_field(s, f[2], Hy, hy_rows(s), s->C, false)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int fdtd2d_zero_state(fdtd2d_sim* s) {
+    REQUIRE(s, "handle is null");
+    if (int rc = use_device(s)) return rc;
+    const size_t bytes = s->grid_elems * s->esize * (size_t)s->batch;
+    for (int h = 0; h < 2; ++h)
+        for (int f = 0; f < 3; ++f) CUDA_TRY(cudaMemsetAsync(s->field[h][f], 0, bytes, s->stream));
+    s->step = 0;
+    return 0;
+}
+
+int fdtd2d_set_mur_coef(fdtd2d_sim* s, const void* mur_coef) {
+    REQUIRE(s && mur_coef, "null argument");
+    if (int rc = use_device(s)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->mur, mur_coef, (size_t)s->batch * s->esize, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->mur_set = true;
+    return 0;
+}
+
+int fdtd2d_set_coeffs(fdtd2d_sim* s, const void* ce, const void* ch, const void* mur_coef) {
+    REQUIRE(s && ce && ch, "null argument");
+    if (int rc = use_device(s)) return rc;
+    if (int rc = transfer_field(s, s->ce, const_cast<void*>(ce), s->Rl, s->C, true)) return rc;
+    if (int rc = transfer_field(s, s->ch, const_cast<void*>(ch), s->Rl, s->C, true)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->coeffs_set = true;
+    if (mur_coef) return fdtd2d_set_mur_coef(s, mur_coef);
+    return 0;
+}
+
+int fdtd2d_set_materials(fdtd2d_sim* s, const void* eps, const void* mu, double dt, double dx) {
+    REQUIRE(s && eps && mu, "null argument");
+    if (int rc = use_device(s)) return rc;
+    // stage eps in ce and mu in ch, then transform in place on the device
+    if (int rc = transfer_field(s, s->ce, const_cast<void*>(eps), s->Rl, s->C, true)) return rc;
+    if (int rc = transfer_field(s, s->ch, const_cast<void*>(mu), s->Rl, s->C, true)) return rc;
+    const long long n = (long long)s->grid_elems * s->batch;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    const bool has_corner = s->row0 == 0;
+    if (s->dtype == FDTD2D_F32) {
+        if (has_corner)
+            mur_from_materials_kernel<float><<<(s->batch + 127) / 128, 128, 0, s->stream>>>(
+                (const float*)s->ce, (const float*)s->ch, (long long)s->grid_elems, s->batch, (float)dt, (float)dx,
+                (float*)s->mur);
+        coeff_from_materials_kernel<float><<<blocks, 256, 0, s->stream>>>((float*)s->ce, (float*)s->ch, n, (float)dt,
+                                                                         (float)dx);
+    } else {
+        if (has_corner)
+            mur_from_materials_kernel<double><<<(s->batch + 127) / 128, 128, 0, s->stream>>>(
+                (const double*)s->ce, (const double*)s->ch, (long long)s->grid_elems, s->batch, dt, dx, (double*)s->mur);
+        coeff_from_materials_kernel<double><<<blocks, 256, 0, s->stream>>>((double*)s->ce, (double*)s->ch, n, dt, dx);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->launches += has_corner ? 2 : 1;
+    s->coeffs_set = true;
+    if (has_corner) s->mur_set = true;
+    return 0;
+}
+
+double fdtd2d_hash_uniform(uint64_t seed, uint32_t grid, uint32_t row, uint32_t col) {
+    return hash_uniform(seed, grid, row, col);
+}
+
+int fdtd2d_set_materials_random(fdtd2d_sim* s, uint64_t seed, double span, double dt, double dx) {
+    REQUIRE(s, "handle is null");
+    if (int rc = use_device(s)) return rc;
+    const double eps0 = 8.85418e-12, mu0 = 4 * 3.141592653589793 * 1e-7;  // main.py:100-101
+    const long long n = (long long)s->Rl * s->C * s->batch;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    if (s->dtype == FDTD2D_F32)
+        random_materials_kernel<float><<<blocks, 256, 0, s->stream>>>(
+            (float*)s->ce, (float*)s->ch, (float*)s->mur, s->Rl, s->C, (int)s->pitch, s->row0, (long long)s->grid_elems,
+            s->batch, seed, (float)span, (float)eps0, (float)mu0, (float)dt, (float)dx);
+    else
+        random_materials_kernel<double><<<blocks, 256, 0, s->stream>>>(
+            (double*)s->ce, (double*)s->ch, (double*)s->mur, s->Rl, s->C, (int)s->pitch, s->row0,
+            (long long)s->grid_elems, s->batch, seed, span, eps0, mu0, dt, dx);
+    CUDA_TRY(cudaGetLastError());
+    s->launches += 1;
+    s->coeffs_set = true;
+    s->mur_set = true;
+    return 0;
+}
+
+int fdtd2d_download_coeffs(fdtd2d_sim* s, void* ce, void* ch, void* mur_coef) {
+    REQUIRE(s, "handle is null");
+    if (int rc = use_device(s)) return rc;
+    if (ce)
+        if (int rc = transfer_field(s, s->ce, ce, s->Rl, s->C, false)) return rc;
+    if (ch)
+        if (int rc = transfer_field(s, s->ch, ch, s->Rl, s->C, false)) return rc;
+    if (mur_coef)
+        CUDA_TRY(cudaMemcpyAsync(mur_coef, s->mur, (size_t)s->batch * s->esize, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// sort cells by grid; build [batch+1] ranges; reject out-of-range and duplicate cells
+static int build_cells(const fdtd2d_sim* s, int n, const int32_t* grid, const int32_t* row, const int32_t* col,
+                       const int32_t* wave, int n_waves, std::vector<Cell>* cells, std::vector<int>* range,
+                       std::vector<int>* perm) {
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    for (int i = 0; i < n; ++i) {
+        const int g = grid ? grid[i] : 0;
+        REQUIRE(g >= 0 && g < s->batch, "cell %d: grid %d out of range", i, g);
+        REQUIRE(row[i] >= 0 && row[i] < s->Rg && col[i] >= 0 && col[i] < s->C, "cell %d: (%d, %d) outside %d x %d", i,
+                row[i], col[i], s->Rg, s->C);
+        if (wave) REQUIRE(wave[i] >= 0 && wave[i] < n_waves, "cell %d: waveform %d out of range", i, wave[i]);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        const int ga = grid ? grid[a] : 0, gb = grid ? grid[b] : 0;
+        if (ga != gb) return ga < gb;
+        if (row[a] != row[b]) return row[a] < row[b];
+        return col[a] < col[b];
+    });
+    cells->resize(n);
+    range->assign(s->batch + 1, 0);
+    for (int q = 0; q < n; ++q) {
+        const int i = order[q];
+        Cell c;
+        c.grid = grid ? grid[i] : 0;
+        c.row = row[i];
+        c.col = col[i];
+        c.wave = wave ? wave[i] : 0;
+        (*cells)[q] = c;
+        (*range)[c.grid + 1] += 1;
+        if (wave && q > 0) {  // duplicate source cells would make the float64-add order ambiguous
+            const Cell& pc = (*cells)[q - 1];
+            REQUIRE(!(pc.grid == c.grid && pc.row == c.row && pc.col == c.col), "duplicate source cell (%d, %d) in grid %d",
+                    c.row, c.col, c.grid);
+        }
+    }
+    for (int b = 0; b < s->batch; ++b) (*range)[b + 1] += (*range)[b];
+    if (perm) *perm = order;
+    return 0;
+}
+
+int fdtd2d_set_sources(fdtd2d_sim* s, int n_cells, const int32_t* grid, const int32_t* row, const int32_t* col,
+                       const int32_t* wave, int n_waves, int n_steps, const double* tables) {
+    REQUIRE(s, "handle is null");
+    if (int rc = use_device(s)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    cudaFree(s->d_src);
+    cudaFree(s->d_src_range);
+    cudaFree(s->d_amp);
+    s->d_src = nullptr;
+    s->d_src_range = nullptr;
+    s->d_amp = nullptr;
+    s->n_src = s->n_waves = s->amp_steps = 0;
+    if (n_cells == 0) return 0;
+    REQUIRE(n_cells > 0 && row && col && wave && tables && n_waves > 0 && n_steps > 0, "bad source arguments");
+    std::vector<Cell> cells;
+    std::vector<int> range;
+    if (int rc = build_cells(s, n_cells, grid, row, col, wave, n_waves, &cells, &range, nullptr)) return rc;
+    CUDA_TRY(cudaMalloc(&s->d_src, sizeof(Cell) * n_cells));
+    CUDA_TRY(cudaMalloc(&s->d_src_range, sizeof(int) * range.size()));
+    CUDA_TRY(cudaMalloc(&s->d_amp, sizeof(double) * (size_t)n_waves * n_steps));
+    CUDA_TRY(cudaMemcpy(s->d_src, cells.data(), sizeof(Cell) * n_cells, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(s->d_src_range, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(s->d_amp, tables, sizeof(double) * (size_t)n_waves * n_steps, cudaMemcpyHostToDevice));
+    s->n_src = n_cells;
+    s->n_waves = n_waves;
+    s->amp_steps = n_steps;
+    return 0;
+}
+
+int fdtd2d_set_probes(fdtd2d_sim* s, int n_probes, const int32_t* grid, const int32_t* row, const int32_t* col,
+                      int capacity_steps) {
+    REQUIRE(s, "handle is null");
+    if (int rc = use_device(s)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    cudaFree(s->d_probe);
+    cudaFree(s->d_probe_range);
+    cudaFree(s->d_trace);
+    s->d_probe = nullptr;
+    s->d_probe_range = nullptr;
+    s->d_trace = nullptr;
+    s->n_probe = 0;
+    s->trace_cap = 0;
+    s->probe_perm.clear();
+    if (n_probes == 0) return 0;
+    REQUIRE(n_probes > 0 && row && col && capacity_steps > 0, "bad probe arguments");
+    std::vector<Cell> cells;
+    std::vector<int> range;
+    if (int rc = build_cells(s, n_probes, grid, row, col, nullptr, 0, &cells, &range, &s->probe_perm)) return rc;
+    const size_t tbytes = (size_t)capacity_steps * n_probes * s->esize;
+    CUDA_TRY(cudaMalloc(&s->d_probe, sizeof(Cell) * n_probes));
+    CUDA_TRY(cudaMalloc(&s->d_probe_range, sizeof(int) * range.size()));
+    CUDA_TRY(cudaMalloc(&s->d_trace, tbytes));
+    CUDA_TRY(cudaMemcpy(s->d_probe, cells.data(), sizeof(Cell) * n_probes, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(s->d_probe_range, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(s->d_trace, 0, tbytes));
+    s->n_probe = n_probes;
+    s->trace_cap = capacity_steps;
+    return 0;
+}
+
+int fdtd2d_read_probes(fdtd2d_sim* s, void* out, int64_t first_step, int n_steps) {
+    REQUIRE(s && out, "null argument");
+    REQUIRE(s->n_probe > 0, "no probes set");
+    REQUIRE(first_step >= 0 && n_steps >= 0 && first_step + n_steps <= s->trace_cap, "probe rows [%lld, %lld) outside capacity %lld",
+            (long long)first_step, (long long)(first_step + n_steps), s->trace_cap);
+    if (int rc = use_device(s)) return rc;
+    const size_t row_bytes = (size_t)s->n_probe * s->esize;
+    std::vector<char> tmp(row_bytes * (size_t)n_steps);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), static_cast<char*>(s->d_trace) + (size_t)first_step * row_bytes, tmp.size(),
+                             cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    // device columns are in sorted order; give them back in the caller's order
+    char* o = static_cast<char*>(out);
+    for (int t = 0; t < n_steps; ++t)
+        for (int q = 0; q < s->n_probe; ++q)
+            memcpy(o + (size_t)t * row_bytes + (size_t)s->probe_perm[q] * s->esize,
+                   tmp.data() + (size_t)t * row_bytes + (size_t)q * s->esize, s->esize);
+    return 0;
+}
+
+int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
+    REQUIRE(s, "handle is null");
+    REQUIRE(n_steps >= 0, "n_steps must be >= 0");
+    REQUIRE(k_temporal >= 0 && k_temporal <= FDTD2D_MAX_K, "k_temporal must be in [0, %d]", FDTD2D_MAX_K);
+    if (!s->coeffs_set || !s->mur_set) return fail(FDTD2D_ESTATE, "coefficients / Mur coefficient not set");
+    if (int rc = use_device(s)) return rc;
+    int k = k_temporal ? k_temporal : 4;
+    if (s->has_top_nb || s->has_bot_nb) {
+        k = std::min(k, s->halo);
+        REQUIRE(n_steps <= s->halo, "a slab handle can advance at most halo=%d steps between halo exchanges", s->halo);
+    }
+    int left = n_steps;
+    while (left > 0) {
+        const int kk = std::min(k, left);
+        if (int rc = run_pass(s, kk, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC)) return rc;
+        s->step += kk;
+        left -= kk;
+    }
+    return 0;
+}
+
+int fdtd2d_step_phases(fdtd2d_sim* s, int phases) {
+    REQUIRE(s, "handle is null");
+    REQUIRE(phases > 0 && phases < 8, "phases must be a non-empty FDTD2D_PHASE_* mask");
+    if (!s->coeffs_set || !s->mur_set) return fail(FDTD2D_ESTATE, "coefficients / Mur coefficient not set");
+    if (int rc = use_device(s)) return rc;
+    if (int rc = run_pass(s, 1, phases)) return rc;
+    if (phases & FDTD2D_PHASE_SRC) s->step += 1;
+    return 0;
+}
+
+int fdtd2d_get_step_index(const fdtd2d_sim* s, int64_t* step) {
+    REQUIRE(s && step, "null argument");
+    *step = s->step;
+    return 0;
+}
+
+int fdtd2d_set_step_index(fdtd2d_sim* s, int64_t step) {
+    REQUIRE(s && step >= 0, "bad argument");
+    s->step = step;
+    return 0;
+}
+
+int fdtd2d_set_kernel_variant(fdtd2d_sim* s, int variant) {
+    REQUIRE(s && variant >= 0 && variant <= 2, "bad argument");
+    s->variant = variant;
+    return 0;
+}
+
+int fdtd2d_launch_count(const fdtd2d_sim* s, int64_t* launches) {
+    REQUIRE(s && launches, "null argument");
+    *launches = s->launches;
+    return 0;
+}
+
+int fdtd2d_halo_block(fdtd2d_sim* s, int field, int side, void** send_ptr, void** recv_ptr, size_t* nbytes) {
+    REQUIRE(s && field >= 0 && field < 3 && (side == 0 || side == 1), "bad argument");
+    const bool has = side == 0 ? s->has_top_nb : s->has_bot_nb;
+    REQUIRE(has, "no neighbour on that side");
+    char* base = static_cast<char*>(s->field[s->cur][field]);
+    const size_t row_bytes = s->pitch * s->esize;
+    const int h = s->halo;
+    // local rows: [0,h) top ghosts | owned | [Rl-h, Rl) bottom ghosts
+    const int own_first = s->has_top_nb ? h : 0;
+    const int own_last = s->Rl - (s->has_bot_nb ? h : 0);  // one past
+    const int send_row = side == 0 ? own_first : own_last - h;
+    const int recv_row = side == 0 ? 0 : own_last;
+    if (send_ptr) *send_ptr = base + (size_t)send_row * row_bytes;
+    if (recv_ptr) *recv_ptr = base + (size_t)recv_row * row_bytes;
+    if (nbytes) *nbytes = (size_t)h * row_bytes;
+    return 0;
+}
+
+int fdtd2d_device_field(fdtd2d_sim* s, int field, void** ptr) {
+    REQUIRE(s && ptr && field >= 0 && field < 5, "bad argument");
+    *ptr = field < 3 ? s->field[s->cur][field] : (field == 3 ? s->ce : s->ch);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""Device-resident FDTD simulation: the performance surface of the package.
+
+`Simulation` owns a libfdtd2d handle (device buffers + stream) and mirrors the reference driver
+python-src/fdtd.py:14-38: build grid and materials, check Courant, then loop
+H-update -> Ez-update(+Mur+corners) -> source add -> readout.  The loop itself runs on the GPU,
+`k` leapfrog steps per HBM round trip; only setup and readout touch the host.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+_DT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64}
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def ricker_amplitude(t, fc):
+    """Ricker wavelet value at time t, float64 -- the scalar expression of main.py:183-184."""
+    tau = np.pi * fc * (t - 1 / fc)
+    return (1 - 2 * tau**2) * np.exp(-(tau**2))
+
+
+def sinusoidal_amplitude(t, fc):
+    """Ramped sine value at time t, float64 -- the scalar expression of main.py:193-194."""
+    envelope = 1 - np.exp(-((t - 3000 / fc) ** 2) / (2 * (2 / fc) ** 2))
+    return envelope * np.sin(2 * np.pi * fc * t)
+
+
+_WAVEFORMS = {"ricker": ricker_amplitude, "sinusoidal": sinusoidal_amplitude}
+
+
+def source_table(kind: str, nsteps: int, dt: float, fc: float) -> np.ndarray:
+    """amp[i] = waveform(i*dt, fc) for i in 0..nsteps-1, evaluated per step with python scalars exactly
+    as the driver does (fdtd.py:34 passes ``i * dt``), so the table is bit-identical to the reference's
+    per-step values."""
+    fn = _WAVEFORMS[kind]
+    return np.array([fn(i * dt, fc) for i in range(nsteps)], dtype=np.float64)
+
+
+def courant_number(eps, mu, dt, dx):
+    """c_max*dt/dx with c_max = 1/sqrt(eps.min()*mu.min()) (fdtd.py:25-26)."""
+    c = 1 / np.sqrt(eps.min() * mu.min())
+    return (c * dt) / dx
+
+
+class Simulation:
+    """`batch` independent rows x cols TM-mode Yee grids resident on one GPU.
+
+    dtype follows the reference convention: float64 is what `grid_init` returns (main.py:79-85);
+    float32 is the reference run with all five arrays cast to float32.
+    """
+
+    def __init__(self, rows: int, cols: int, dtype=np.float32, *, dt: float, dx: float, device: int = 0,
+                 batch: int = 1, slab: tuple[int, int, int, int] | None = None):
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in _DT:
+            raise TypeError("dtype must be float32 or float64")
+        self.dt, self.dx = float(dt), float(dx)
+        self.batch = int(batch)
+        self._h = ctypes.c_void_p()
+        if slab is None:
+            check(lib().fdtd2d_create(ctypes.byref(self._h), rows, cols, _DT[self.dtype], device, batch))
+        else:
+            global_rows, row_begin, row_end, halo = slab
+            check(lib().fdtd2d_create_slab(ctypes.byref(self._h), global_rows, cols, row_begin, row_end, halo,
+                                           _DT[self.dtype], device))
+        lr, c, r0, gr, b, dtc = (ctypes.c_int() for _ in range(6))
+        pitch = ctypes.c_size_t()
+        check(lib().fdtd2d_geometry(self._h, lr, c, r0, gr, b, dtc, pitch))
+        self.local_rows, self.cols, self.row0, self.global_rows = lr.value, c.value, r0.value, gr.value
+        self.pitch = pitch.value
+        self.rows = self.global_rows
+        self.device = device
+        self._hy_rows = self.local_rows - 1 if self.row0 + self.local_rows == self.global_rows else self.local_rows
+        self._n_probes = 0
+        self._keep = []  # host arrays that must outlive async copies
+
+    # ---- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().fdtd2d_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- helpers ----------------------------------------------------------------------------
+    def _shape(self, rows, cols):
+        return (rows, cols) if self.batch == 1 else (self.batch, rows, cols)
+
+    def _as(self, a, rows, cols, name):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        if a.shape != self._shape(rows, cols) and a.shape != (self.batch, rows, cols):
+            raise ValueError(f"{name} has shape {a.shape}, expected {self._shape(rows, cols)}")
+        return a
+
+    def set_stream(self, cuda_stream: int | None):
+        """Order all work of this simulation on an external CUDA stream handle (e.g.
+        ``torch.cuda.current_stream().cuda_stream``; 0 is the legacy default stream).
+        None goes back to the simulation's own stream."""
+        if cuda_stream is None:
+            check(lib().fdtd2d_reset_stream(self._h))
+        else:
+            check(lib().fdtd2d_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        check(lib().fdtd2d_sync(self._h))
+
+    # ---- state ------------------------------------------------------------------------------
+    def set_state(self, Ez, Hx, Hy):
+        """Upload Ez (R,C), Hx (R,C-1), Hy (R-1,C) -- the shapes grid_init returns (main.py:79-85)."""
+        Ez = self._as(Ez, self.local_rows, self.cols, "Ez")
+        Hx = self._as(Hx, self.local_rows, self.cols - 1, "Hx")
+        Hy = self._as(Hy, self._hy_rows, self.cols, "Hy")
+        check(lib().fdtd2d_upload_state(self._h, _p(Ez), _p(Hx), _p(Hy)))
+        self.synchronize()
+
+    def state(self, out=None):
+        """Download (Ez, Hx, Hy) in the reference's shapes."""
+        if out is None:
+            out = (np.empty(self._shape(self.local_rows, self.cols), self.dtype),
+                   np.empty(self._shape(self.local_rows, self.cols - 1), self.dtype),
+                   np.empty(self._shape(self._hy_rows, self.cols), self.dtype))
+        Ez, Hx, Hy = out
+        check(lib().fdtd2d_download_state(self._h, _p(Ez), _p(Hx), _p(Hy)))
+        return Ez, Hx, Hy
+
+    def read_Ez(self, out=None):
+        if out is None:
+            out = np.empty(self._shape(self.local_rows, self.cols), self.dtype)
+        check(lib().fdtd2d_download_state(self._h, _p(out), None, None))
+        return out
+
+    def zero_state(self):
+        check(lib().fdtd2d_zero_state(self._h))
+
+    # ---- materials --------------------------------------------------------------------------
+    def set_materials(self, eps, mu):
+        """eps, mu maps as `material_init` returns them (main.py:88-123), cast to the run dtype.  The
+        device forms dt/(eps*dx), dt/(mu*dx) and the Mur coefficient with the reference's op order."""
+        eps = self._as(eps, self.local_rows, self.cols, "eps")
+        mu = self._as(mu, self.local_rows, self.cols, "mu")
+        check(lib().fdtd2d_set_materials(self._h, _p(eps), _p(mu), self.dt, self.dx))
+
+    def set_coefficients(self, ce, ch, mur_coef):
+        """Host-precomputed maps ce = dt/(eps*dx), ch = dt/(mu*dx) and Mur coefficient(s)."""
+        ce = self._as(ce, self.local_rows, self.cols, "ce")
+        ch = self._as(ch, self.local_rows, self.cols, "ch")
+        mc = np.ascontiguousarray(np.broadcast_to(np.asarray(mur_coef, dtype=self.dtype), (self.batch,)))
+        check(lib().fdtd2d_set_coeffs(self._h, _p(ce), _p(ch), _p(mc)))
+
+    def set_mur_coef(self, mur_coef):
+        mc = np.ascontiguousarray(np.broadcast_to(np.asarray(mur_coef, dtype=self.dtype), (self.batch,)))
+        check(lib().fdtd2d_set_mur_coef(self._h, _p(mc)))
+
+    def set_materials_random(self, seed: int, span: float = 9.0):
+        """Synthetic medium generated on the device: eps = eps0*(1 + span*u), mu = mu0."""
+        check(lib().fdtd2d_set_materials_random(self._h, seed, span, self.dt, self.dx))
+
+    def coefficients(self):
+        ce = np.empty(self._shape(self.local_rows, self.cols), self.dtype)
+        ch = np.empty_like(ce)
+        mur = np.empty((self.batch,), self.dtype)
+        check(lib().fdtd2d_download_coeffs(self._h, _p(ce), _p(ch), _p(mur)))
+        return ce, ch, mur
+
+    # ---- sources and probes -----------------------------------------------------------------
+    def set_sources(self, cells: Sequence[tuple], tables: np.ndarray):
+        """cells: (grid, row, col, wave) tuples (global rows); tables: float64 [n_waves][n_steps]."""
+        tables = np.ascontiguousarray(np.atleast_2d(tables), dtype=np.float64)
+        if len(cells) == 0:
+            check(lib().fdtd2d_set_sources(self._h, 0, None, None, None, None, 0, 0, None))
+            return
+        arr = np.ascontiguousarray(np.asarray(cells, dtype=np.int32).reshape(-1, 4))
+        g, r, c, w = (np.ascontiguousarray(arr[:, i]) for i in range(4))
+        check(lib().fdtd2d_set_sources(self._h, len(arr), _p(g), _p(r), _p(c), _p(w), tables.shape[0],
+                                       tables.shape[1], _p(tables)))
+
+    def set_point_source(self, row: int, col: int, nsteps: int, fc: float = 30e9, kind: str = "ricker", grid: int = 0):
+        """The driver's source: ``Ez += ricker(rows, cols, row, col, i*dt, fc)`` (fdtd.py:34)."""
+        self.set_sources([(grid, row, col, 0)], source_table(kind, nsteps, self.dt, fc)[None, :])
+
+    def set_probes(self, cells: Iterable[tuple], capacity_steps: int):
+        """cells: (row, col) or (grid, row, col); Ez there is recorded after every step."""
+        cells = [(0, *c) if len(c) == 2 else tuple(c) for c in cells]
+        self._n_probes = len(cells)
+        if not cells:
+            check(lib().fdtd2d_set_probes(self._h, 0, None, None, None, 0))
+            return
+        arr = np.ascontiguousarray(np.asarray(cells, dtype=np.int32).reshape(-1, 3))
+        g, r, c = (np.ascontiguousarray(arr[:, i]) for i in range(3))
+        check(lib().fdtd2d_set_probes(self._h, len(arr), _p(g), _p(r), _p(c), capacity_steps))
+
+    def read_probes(self, first_step: int = 0, n_steps: int | None = None):
+        if n_steps is None:
+            n_steps = self.step_index - first_step
+        out = np.empty((n_steps, self._n_probes), self.dtype)
+        check(lib().fdtd2d_read_probes(self._h, _p(out), first_step, n_steps))
+        return out
+
+    # ---- time stepping ----------------------------------------------------------------------
+    def step(self, n_steps: int = 1, k: int = 0):
+        """Advance n_steps leapfrog steps (asynchronous), k steps per HBM round trip (0 = default)."""
+        check(lib().fdtd2d_step(self._h, n_steps, k))
+
+    run = step
+
+    def step_phases(self, phases: int):
+        check(lib().fdtd2d_step_phases(self._h, phases))
+
+    @property
+    def step_index(self) -> int:
+        v = ctypes.c_int64()
+        check(lib().fdtd2d_get_step_index(self._h, ctypes.byref(v)))
+        return v.value
+
+    @step_index.setter
+    def step_index(self, v: int):
+        check(lib().fdtd2d_set_step_index(self._h, v))
+
+    def set_kernel_variant(self, variant: int):
+        check(lib().fdtd2d_set_kernel_variant(self._h, variant))
+
+    @property
+    def launch_count(self) -> int:
+        v = ctypes.c_int64()
+        check(lib().fdtd2d_launch_count(self._h, ctypes.byref(v)))
+        return v.value
+
+    # ---- multi-GPU plumbing -----------------------------------------------------------------
+    def halo_block(self, field: int, side: int):
+        """(send_ptr, recv_ptr, nbytes) of the current state's halo block (see fdtd2d_halo_block)."""
+        sp, rp, nb = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t()
+        check(lib().fdtd2d_halo_block(self._h, field, side, ctypes.byref(sp), ctypes.byref(rp), ctypes.byref(nb)))
+        return sp.value, rp.value, nb.value
+
+    def device_field(self, field: int) -> int:
+        p = ctypes.c_void_p()
+        check(lib().fdtd2d_device_field(self._h, field, ctypes.byref(p)))
+        return p.value

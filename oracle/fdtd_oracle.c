@@ -20,7 +20,7 @@
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math [-fopenmp]  (see c_oracle.py).
  * -ffp-contract=off is mandatory: a fused multiply-add changes the bits.
  *
- * Parity pin: checked bit-for-bit against tests/golden/*.npz (outputs of the real
+ * Parity pin: checked bit-for-bit against the .npz files under tests/golden (outputs of the real
  * reference) by tests/test_oracle_golden.py.
  */
 #include <stddef.h>

@@ -1,0 +1,306 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI / ctypes) against
+  (a) the golden vectors produced by the real reference (tests/golden/), and
+  (b) the CPU oracle (oracle/) on the same seeded inputs.
+The bar is BIT-EXACT for fp32 and fp64 (which implies the north-star tolerances: rel-L2 <= 1e-5 in
+fp32, <= 1e-12 in fp64, at the final fields and at every probe); rel-L2 is reported on failure."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+DT, DX, FC = 5e-14, 1e-4, 30e9
+TOL = {"float32": 1e-5, "float64": 1e-12}  # north-star tolerances (BASELINE.json); we demand 0.0
+
+
+def rel_l2(a, b):
+    d = np.linalg.norm(a.astype(np.float64) - b.astype(np.float64))
+    n = np.linalg.norm(b.astype(np.float64))
+    return d / n if n else d
+
+
+def assert_bits(a, b, what):
+    assert a.dtype == b.dtype and a.shape == b.shape, what
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        raise AssertionError(f"{what}: {len(bad)} cells differ, first at {bad[0]}, rel-L2 = {rel_l2(a, b):.3e} "
+                             f"(north-star tolerance {TOL[a.dtype.name]})")
+
+
+@pytest.fixture(scope="module")
+def fd():
+    import fdtd2d_b200
+
+    return fdtd2d_b200
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import c_oracle, numpy_oracle
+
+    c_oracle.build()
+    return c_oracle, numpy_oracle
+
+
+# --------------------------------------------------------------------------------------------
+# per-function parity against the reference's own outputs
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("shape", [(11, 11), (12, 13), (16, 11), (37, 53), (64, 48)])
+def test_update_functions_vs_reference_golden(fd, golden_dir, dtype, shape):
+    g = np.load(os.path.join(golden_dir, "single_call.npz"))
+    k = f"{dtype}_{shape[0]}x{shape[1]}"
+    eps, mu = g[k + "_eps"], g[k + "_mu"]
+    Ez, Hx, Hy = g[k + "_Ez0"].copy(), g[k + "_Hx0"].copy(), g[k + "_Hy0"].copy()
+    rHx, rHy = fd.update_Hx_Hy(Ez, Hx, Hy, mu, eps, DT, DX)
+    assert rHx is Hx and rHy is Hy  # in place + returned, like main.py:76
+    assert_bits(Hx, g[k + "_Hx1"], "Hx after update_Hx_Hy")
+    assert_bits(Hy, g[k + "_Hy1"], "Hy after update_Hx_Hy")
+    assert_bits(Ez, g[k + "_Ez0"], "Ez untouched by update_Hx_Hy")
+    rEz = fd.update_Ez(Ez, Hx, Hy, mu, eps, DT, DX)
+    assert rEz is Ez
+    assert_bits(Ez, g[k + "_Ez1"], "Ez after update_Ez")
+
+
+# --------------------------------------------------------------------------------------------
+# the reference demo (fdtd.py defaults), every k
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 8])
+def test_demo200_vs_reference_golden(fd, golden_dir, dtype, k):
+    g = np.load(os.path.join(golden_dir, f"demo200_vacuum_{dtype}.npz"))
+    eps, mu = fd.material_init(None, 200, 200)
+    with fd.Simulation(200, 200, dtype, dt=DT, dx=DX) as sim:
+        sim.set_materials(eps, mu)
+        sim.set_point_source(100, 100, 1000, FC)
+        sim.set_probes([tuple(p) for p in g["probes"]], 1000)
+        sim.step(1000, k)
+        Ez, Hx, Hy = sim.state()
+        trace = sim.read_probes()
+    assert_bits(trace, g["trace"], "probe trace (every step)")
+    assert_bits(Ez, g["Ez"], "Ez")
+    assert_bits(Hx, g["Hx"], "Hx")
+    assert_bits(Hy, g["Hy"], "Hy")
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("case", [(37, 53, "ricker"), (96, 130, "sinusoidal"), (11, 11, "ricker")])
+@pytest.mark.parametrize("k", [1, 4, 7])
+def test_random_runs_vs_reference_golden(fd, golden_dir, dtype, case, k):
+    """Random eps AND mu, non-zero initial state (incl. the never-updated Hx last row / Hy last
+    column), ragged sizes, both waveforms."""
+    g = np.load(os.path.join(golden_dir, "random_runs.npz"))
+    R, C, kind = case
+    key = f"{dtype}_{R}x{C}_{kind}"
+    n = int(g[key + "_nsteps"])
+    src = tuple(int(v) for v in g[key + "_src"])
+    with fd.Simulation(R, C, dtype, dt=DT, dx=DX) as sim:
+        sim.set_materials(g[key + "_eps"], g[key + "_mu"])
+        sim.set_state(g[key + "_Ez0"], g[key + "_Hx0"], g[key + "_Hy0"])
+        sim.set_point_source(src[0], src[1], n, FC, kind)
+        sim.set_probes([tuple(p) for p in g[key + "_probes"]], n)
+        sim.step(n, k)
+        Ez, Hx, Hy = sim.state()
+        trace = sim.read_probes()
+    assert_bits(trace, g[key + "_trace"], "probe trace")
+    assert_bits(Ez, g[key + "_Ez"], "Ez")
+    assert_bits(Hx, g[key + "_Hx"], "Hx")
+    assert_bits(Hy, g[key + "_Hy"], "Hy")
+
+
+# --------------------------------------------------------------------------------------------
+# seeded inputs against the CPU oracle at sizes it finishes in seconds
+# --------------------------------------------------------------------------------------------
+def _random_problem(rng, R, C, dtype, scale=1e-3):
+    eps = (8.85418e-12 * (1 + 9 * rng.random((R, C)))).astype(dtype)
+    mu = (4 * np.pi * 1e-7 * (1 + 0.5 * rng.random((R, C)))).astype(dtype)
+    Ez = (scale * rng.standard_normal((R, C))).astype(dtype)
+    Hx = (scale * 1e-3 * rng.standard_normal((R, C - 1))).astype(dtype)
+    Hy = (scale * 1e-3 * rng.standard_normal((R - 1, C))).astype(dtype)
+    return eps, mu, Ez, Hx, Hy
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("shape,nsteps,k", [
+    ((300, 517), 64, 4), ((300, 517), 33, 8), ((129, 1000), 50, 5), ((1000, 131), 50, 3),
+    ((28, 120), 40, 4), ((29, 121), 40, 4), ((57, 241), 40, 4), ((64, 256), 24, 6),
+    ((1024, 1024), 40, 4), ((1024, 1024), 17, 1), ((203, 215), 30, 2),
+])
+def test_seeded_runs_vs_oracle(fd, oracle, dtype, shape, nsteps, k):
+    c_oracle, npo = oracle
+    R, C = shape
+    rng = np.random.default_rng(R * 100003 + C * 17 + nsteps + k)
+    eps, mu, Ez, Hx, Hy = _random_problem(rng, R, C, dtype)
+    ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(dtype))
+    cells = [(R // 2, C // 2), (7, 9), (R - 3, C - 2), (0, 0)]
+    amp = npo.source_table("ricker", nsteps, DT, FC)
+    probes = [(R // 2, C // 2), (0, 0), (R - 1, C - 1), (4, C - 5), (R - 5, 4), (R // 3, C // 5), (5, 5), (R - 6, C - 6)]
+    oEz, oHx, oHy = Ez.copy(), Hx.copy(), Hy.copy()
+    otrace = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, nsteps, amp, cells, probes, omp=True)
+    with fd.Simulation(R, C, dtype, dt=DT, dx=DX) as sim:
+        sim.set_materials(eps, mu)
+        gce, gch, gmur = sim.coefficients()
+        assert_bits(gce, ce, "ce = dt/(eps*dx) formed on the device")
+        assert_bits(gch, ch, "ch = dt/(mu*dx) formed on the device")
+        assert gmur[0] == coef and gmur.dtype == np.dtype(dtype)
+        sim.set_state(Ez, Hx, Hy)
+        sim.set_sources([(0, r, c, 0) for r, c in cells], amp[None, :])
+        sim.set_probes(probes, nsteps)
+        sim.step(nsteps, k)
+        gEz, gHx, gHy = sim.state()
+        gtrace = sim.read_probes()
+    assert_bits(gtrace, otrace, "probe trace")
+    assert_bits(gEz, oEz, "Ez")
+    assert_bits(gHx, oHx, "Hx")
+    assert_bits(gHy, oHy, "Hy")
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_batched_grids_vs_oracle(fd, oracle, dtype):
+    """Batched mode: independent grids, per-grid media, Mur coefficient, sources (point and line)."""
+    c_oracle, npo = oracle
+    B, R, C, nsteps = 6, 72, 100, 48
+    rng = np.random.default_rng(5)
+    probs = [_random_problem(rng, R, C, dtype, scale=0.0) for _ in range(B)]
+    eps = np.stack([p[0] for p in probs])
+    mu = np.stack([p[1] for p in probs])
+    fcs = [18e9 + 2e9 * b for b in range(B)]
+    tables = np.stack([npo.source_table("ricker" if b % 2 == 0 else "sinusoidal", nsteps, DT, fcs[b]) for b in range(B)])
+    cells, per_grid = [], []
+    for b in range(B):
+        if b % 3 == 0:
+            mine = [(20 + b, 30 + j) for j in range(7)]  # horizontal line source
+        elif b % 3 == 1:
+            mine = [(10 + i, 50 + b) for i in range(5)]  # vertical line source
+        else:
+            mine = [(R // 2, C // 2)]
+        per_grid.append(mine)
+        cells += [(b, r, c, b) for r, c in mine]
+    probes = [(b, R // 2, C // 2 + 3) for b in range(B)] + [(b, 1, 1) for b in range(B)]
+    with fd.Simulation(R, C, dtype, dt=DT, dx=DX, batch=B) as sim:
+        sim.set_materials(eps, mu)
+        sim.set_sources(cells, tables)
+        sim.set_probes(probes, nsteps)
+        sim.step(nsteps, 4)
+        gEz, gHx, gHy = sim.state()
+        gtrace = sim.read_probes()
+    for b in range(B):
+        ce, ch, coef = c_oracle.coefficients(eps[b], mu[b], DT, DX, np.dtype(dtype))
+        oEz, oHx, oHy = npo.grid_init(R, C, np.dtype(dtype))
+        otr = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, nsteps, tables[b], per_grid[b], [(R // 2, C // 2 + 3), (1, 1)])
+        assert_bits(gEz[b], oEz, f"Ez grid {b}")
+        assert_bits(gHx[b], oHx, f"Hx grid {b}")
+        assert_bits(gHy[b], oHy, f"Hy grid {b}")
+        assert_bits(gtrace[:, b], otr[:, 0], f"probe A grid {b}")
+        assert_bits(gtrace[:, B + b], otr[:, 1], f"probe B grid {b}")
+
+
+def test_step_in_pieces_equals_one_call(fd):
+    """Stepping 1000 = 1+2+...: the step index (source phase) carries across calls and mixed k."""
+    eps, mu = fd.material_init(None, 200, 200)
+    outs = []
+    for plan in ([(1000, 4)], [(1, 1), (2, 2), (333, 4), (64, 8), (600, 5)]):
+        with fd.Simulation(200, 200, np.float32, dt=DT, dx=DX) as sim:
+            sim.set_materials(eps, mu)
+            sim.set_point_source(100, 100, 1000, FC)
+            for n, k in plan:
+                sim.step(n, k)
+            assert sim.step_index == 1000
+            outs.append(sim.state())
+    for a, b in zip(*outs):
+        assert_bits(a, b, "piecewise stepping")
+
+
+# --------------------------------------------------------------------------------------------
+# size-independent properties at sizes the oracle cannot reach
+# --------------------------------------------------------------------------------------------
+def test_temporal_blocking_invariance_large(fd):
+    """k steps per HBM round trip must not change a single bit: 3000 x 4100 fp32, device-generated
+    random medium, k in {1, 3, 4, 8}."""
+    R, C, n = 3000, 4100, 24
+    ref = None
+    for k in (1, 3, 4, 8):
+        with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
+            sim.set_materials_random(seed=11, span=9.0)
+            sim.set_point_source(R // 2, C // 2, 700, FC)
+            sim.step_index = 640  # near the Ricker peak so the field is far from zero
+            sim.step(n, k)
+            Ez, Hx, Hy = sim.state()
+        if ref is None:
+            ref = (Ez, Hx, Hy)
+            assert np.abs(Ez).max() > 0.1
+        else:
+            for a, b in zip((Ez, Hx, Hy), ref):
+                assert_bits(a, b, f"k={k} vs k=1")
+
+
+def test_window_locality_vs_oracle_large(fd, oracle):
+    """Full-size check through locality: after n steps a window of a 4096 x 4096 fp32 run equals the
+    oracle run on the window grown by n+8 cells (interior dependency radius is 1 cell per step)."""
+    c_oracle, npo = oracle
+    R = C = 4096
+    n, m = 20, 28
+    rng = np.random.default_rng(3)
+    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
+        sim.set_materials_random(seed=2026, span=9.0)
+        Ez0 = (1e-3 * rng.standard_normal((R, C))).astype(np.float32)
+        Hx0 = (1e-6 * rng.standard_normal((R, C - 1))).astype(np.float32)
+        Hy0 = (1e-6 * rng.standard_normal((R - 1, C))).astype(np.float32)
+        sim.set_state(Ez0, Hx0, Hy0)
+        ce, ch, _ = sim.coefficients()
+        sim.step(n, 4)
+        Ez, Hx, Hy = sim.state()
+    for (r0, c0, h, w) in [(1000, 2000, 96, 160), (3000, 100, 64, 64), (2040, 2040, 40, 40)]:
+        a, b_, c_, d = r0 - m, r0 + h + m, c0 - m, c0 + w + m
+        wEz = Ez0[a:b_, c_:d].copy()
+        wHx = Hx0[a:b_, c_:d - 1].copy()
+        wHy = Hy0[a:b_ - 1, c_:d].copy()
+        c_oracle.run(wEz, wHx, wHy, ce[a:b_, c_:d].copy(), ch[a:b_, c_:d].copy(), np.float32(0), n)
+        assert_bits(Ez[r0:r0 + h, c0:c0 + w], wEz[m:m + h, m:m + w], "Ez window")
+        assert_bits(Hx[r0:r0 + h, c0:c0 + w], wHx[m:m + h, m:m + w], "Hx window")
+        assert_bits(Hy[r0:r0 + h, c0:c0 + w], wHy[m:m + h, m:m + w], "Hy window")
+
+
+def test_random_medium_matches_host_definition(fd):
+    """The device-generated medium is reproducible on the host (fdtd2d_hash_uniform)."""
+    from fdtd2d_b200 import _lib
+
+    R, C = 40, 70
+    for dtype in (np.float32, np.float64):
+        with fd.Simulation(R, C, dtype, dt=DT, dx=DX, batch=2) as sim:
+            sim.set_materials_random(seed=77, span=9.0)
+            ce, ch, mur = sim.coefficients()
+        T = np.dtype(dtype).type
+        for b in range(2):
+            u = np.array([[_lib.lib().fdtd2d_hash_uniform(77, b, i, j) for j in range(C)] for i in range(R)]).astype(dtype)
+            eps = T(8.85418e-12) * (T(1) + T(9.0) * u)
+            mu = np.full((R, C), T(4 * np.pi * 1e-7))
+            assert_bits(ce[b], DT / (eps * DX), "ce of the synthetic medium")
+            assert_bits(ch[b], DT / (mu * DX), "ch of the synthetic medium")
+            c = 1 / np.sqrt(mu[0, 0] * eps[0, 0])
+            assert mur[b] == (c * DT - DX) / (c * DT + DX)
+
+
+# --------------------------------------------------------------------------------------------
+# error behaviour at the boundary
+# --------------------------------------------------------------------------------------------
+def test_errors(fd):
+    with pytest.raises(fd.Fdtd2dError) as e:
+        fd.Simulation(10, 200, np.float32, dt=DT, dx=DX)
+    assert e.value.code == -1
+    with fd.Simulation(32, 32, np.float32, dt=DT, dx=DX) as sim:
+        with pytest.raises(fd.Fdtd2dError) as e:
+            sim.step(1)
+        assert e.value.code == -4  # materials not set
+        sim.set_materials(*fd.material_init(None, 32, 32))
+        with pytest.raises(fd.Fdtd2dError):
+            sim.step(1, 9)  # k > FDTD2D_MAX_K
+        with pytest.raises(fd.Fdtd2dError):
+            sim.set_sources([(0, 40, 3, 0)], np.zeros((1, 4)))  # outside the grid
+        with pytest.raises(fd.Fdtd2dError):
+            sim.set_sources([(0, 4, 3, 0), (0, 4, 3, 0)], np.zeros((1, 4)))  # duplicate cell
+        with pytest.raises(ValueError):
+            sim.set_state(np.zeros((32, 32), np.float32), np.zeros((32, 32), np.float32), np.zeros((31, 32), np.float32))
+    with pytest.raises(ValueError):
+        fd.update_Hx_Hy(np.zeros((20, 20)), np.zeros((20, 20)), np.zeros((19, 20)), np.ones((20, 20)), np.ones((20, 20)), DT, DX)
