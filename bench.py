@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- Gcell-updates/s of the 2D FDTD leapfrog path (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU)
+
+A bench "step" is ONE call of the hot path over the workload grid: `inner` leapfrog steps
+(H -> Ez+Mur+corners -> source -> probes; fdtd.py:31-34) advanced `k` steps per HBM round trip.
+One cell-update = Hx, Hy and Ez of one cell advanced one leapfrog step.
+
+  value   device-resident throughput: inputs already in HBM, CUDA-event timed, max over ranks.
+  e2e     the same call through the public API with HOST (pinned) inputs: every step uploads
+          eps, mu, Ez, Hx, Hy, forms the coefficient maps on the device, runs `inner` leapfrog steps and
+          reads Ez and the probe traces back.
+  roofline  HBM roofline of the tile kernel at the algorithmic 32 B per fp32 cell-update
+          (SURVEY 8d); temporal blocking may legitimately exceed 1.0 -- `traffic` is the DRAM bytes ncu
+          saw per launch (profiles/), which is what actually bounds the kernel.
+  cpu_baseline  the oracle's numpy restatement of the reference (1 core: numpy elementwise) on a bounded
+          sample of the same workload, timed on this box's host.
+
+`--impl reference` times the reference's own CPU implementation of the path.  The reference is plain
+numpy and `/root/reference` does not travel to the GPU box, so this is the oracle's numpy port
+(oracle/numpy_oracle.py, bit-identical to the reference -- tests/test_oracle_golden.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT, DX, FC = 5e-14, 1e-4, 30e9  # fdtd.py:16-17,34
+BYTES_PER_UPDATE_F32 = 32  # read Ez,Hx,Hy,ce,ch + write Ez,Hx,Hy
+
+WORKLOADS = {
+    # name: rows-per-GPU, cols, inner leapfrog steps per bench step, description
+    "cfg2": dict(rows=4096, cols=4096, inner=500, desc="4096x4096 fp32, random permittivity (BASELINE configs[1])"),
+    "cfg3": dict(rows=16384, cols=16384, inner=200,
+                 desc="16384x16384 fp32, random permittivity, temporal-blocked kernel (BASELINE configs[2]; the "
+                      "grid the >=70%-of-roofline target is quoted on)"),
+    "cfg4": dict(rows=65536, cols=65536, inner=16, desc="65536x65536 fp32 y-slab sharded (BASELINE configs[3]), strong scaling"),
+    "small": dict(rows=1024, cols=1024, inner=64, desc="1024x1024 fp32 (debug)"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_eps(rows, cols, seed, row0=0):
+    """eps = eps0*(1+9*U[0,1)) (SURVEY 8d cfg2/cfg3 recipe), float32, generated band-wise."""
+    rng = np.random.default_rng(seed + row0)
+    out = np.empty((rows, cols), np.float32)
+    band = 2048
+    for a in range(0, rows, band):
+        b = min(rows, a + band)
+        out[a:b] = 8.85418e-12 * (1 + 9 * rng.random((b - a, cols), dtype=np.float32))
+    return out
+
+
+def cpu_reference_rate(rows, cols, nsteps, seed=7):
+    """Time the oracle's numpy restatement of the reference loop (fdtd.py:30-34) on rows x cols fp32."""
+    from oracle import numpy_oracle as npo
+
+    eps = synthetic_eps(rows, cols, seed)
+    mu = np.full((rows, cols), np.float32(4 * np.pi * 1e-7))
+    Ez, Hx, Hy = npo.grid_init(rows, cols, np.float32)
+    npo.run(Ez, Hx, Hy, mu, eps, DT, DX, 1, source=(rows // 2, cols // 2, FC, "ricker"))  # touch pages
+    t0 = time.perf_counter()
+    npo.run(Ez, Hx, Hy, mu, eps, DT, DX, nsteps, source=(rows // 2, cols // 2, FC, "ricker"), step0=1)
+    dt = time.perf_counter() - t0
+    return rows * cols * nsteps / dt / 1e9, dt
+
+
+def run_reference_arm(args, wl):
+    """--impl reference: the reference's CPU path (numpy port), rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    rows, cols = min(wl["rows"], 2048), wl["cols"]
+    sample = f"1 leapfrog step per bench step on a {rows}x{cols} fp32 band of the workload grid (numpy, 1 core)"
+    from oracle import numpy_oracle as npo
+
+    eps = synthetic_eps(rows, cols, 7)
+    mu = np.full((rows, cols), np.float32(4 * np.pi * 1e-7))
+    Ez, Hx, Hy = npo.grid_init(rows, cols, np.float32)
+    src = (rows // 2, cols // 2, FC, "ricker")
+    for w in range(args.warmup):
+        npo.run(Ez, Hx, Hy, mu, eps, DT, DX, 1, source=src, step0=w)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        npo.run(Ez, Hx, Hy, mu, eps, DT, DX, 1, source=src, step0=args.warmup + s)
+    el = time.perf_counter() - t0
+    val = rows * cols * args.steps / el / 1e9
+    line = {
+        "impl": "reference", "metric": "Gcell-updates/s (fp32 E+H step)", "value": val, "unit": "Gcell-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Gcell-updates/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": val, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--inner", type=int, default=0, help="leapfrog steps per bench step (0 = workload default)")
+    ap.add_argument("--k", type=int, default=0, help="leapfrog steps per HBM round trip (0 = library default)")
+    ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 auto, 1 generic, 2 fast+generic)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.inner:
+        wl["inner"] = args.inner
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import fdtd2d_b200 as fd
+    from fdtd2d_b200.distributed import SlabSimulation
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+
+    strong = args.workload == "cfg4"
+    cols = wl["cols"]
+    grows = wl["rows"] if strong else wl["rows"] * world  # weak scaling: fixed rows per GPU
+    inner = wl["inner"]
+    k = args.k or fd.DEFAULT_K
+    stream = torch.cuda.current_stream().cuda_stream
+
+    sim = SlabSimulation(grows, cols, np.float32, dt=DT, dx=DX, rank=rank, world=world, device=local_rank, halo=k)
+    sim.set_stream(stream)
+    if args.variant:
+        sim.set_kernel_variant(args.variant)
+    sim.set_materials_random(seed=2026, span=9.0)
+    total_steps = (args.warmup + args.steps + 2) * inner
+    sim.set_point_source(grows // 2, cols // 2, total_steps, FC)
+    probes = [(grows // 2, cols // 2 + 16), (grows // 4, cols // 4), (3 * grows // 4, cols // 3), (grows // 2, 8),
+              (8, cols // 2), (grows - 9, cols // 2), (grows // 3, cols - 9), (grows // 2 + 100, cols // 2 + 100)]
+    sim.set_probes(probes, total_steps)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sim.step(inner, k)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = sim.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        sim.step(inner, k)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sim.launch_count - l0
+    tile_launches = sim.tile_launch_count
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    cells = grows * cols
+    value = cells * inner * args.steps / (ms * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    n_pass = -(-inner // k) * args.steps  # tile-kernel launches per rank in the timed region
+    alg_bytes_per_launch = BYTES_PER_UPDATE_F32 * (cells / world) * inner * args.steps / n_pass
+    achieved = alg_bytes_per_launch / (ms * 1e-3 / n_pass) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(args.workload)
+
+    # ---- e2e: host (pinned) inputs, H2D + coefficient formation + inner steps + D2H, every step ----
+    e2e = None
+    if not args.no_e2e:
+        sim.close()
+        e2e = run_e2e(args, wl, fd, torch, dist, rank, world, local_rank, grows, cols, inner, k, barrier)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        crow = min(4096, wl["rows"])
+        n = 2
+        v, el = cpu_reference_rate(crow, cols, n)
+        cpu = {"value": v, "unit": "Gcell-updates/s", "cores": 1, "kind": "port", "host_cpus": os.cpu_count(),
+               "sample": f"{n} leapfrog steps on a {crow}x{cols} fp32 band of the workload grid, numpy port of the "
+                         f"reference loop ({el:.1f} s)"}
+    if rank == 0:
+        line = {
+            "metric": "Gcell-updates/s (fp32 E+H step)", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "global_rows": grows, "cols": cols,
+                       "inner_leapfrog_steps_per_step": inner, "k_temporal": k,
+                       "parallelism": f"y-slabs x{world}" if world > 1 else "single GPU",
+                       "l2": "state is larger than L2 (inputs larger than L2; no flush needed)",
+                       "seed": 2026, "source": "ricker fc=30e9 at centre", "probes": len(probes)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "note": "achieved = 32 B x cell-updates per tile-kernel launch / mean launch time; k-step "
+                                 "temporal blocking moves fewer DRAM bytes than the algorithmic count"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "tile_kernel_launches": int(tile_launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, wl, fd, torch, dist, rank, world, local_rank, grows, cols, inner, k, barrier):
+    """Public-API path with host buffers: per bench step upload eps, mu, Ez, Hx, Hy from pinned memory,
+    form coefficients on the device, run `inner` leapfrog steps, read back Ez and the probe traces."""
+    from fdtd2d_b200.distributed import SlabSimulation, slab_rows
+
+    steps = max(2, min(args.steps, 4))
+    sim = SlabSimulation(grows, cols, np.float32, dt=DT, dx=DX, rank=rank, world=world, device=local_rank, halo=k)
+    sim.set_stream(torch.cuda.current_stream().cuda_stream)
+    lr, hyr = sim.local_rows, sim.hy_rows
+
+    def pinned(shape):
+        return torch.zeros(shape, dtype=torch.float32, pin_memory=True).numpy()
+
+    eps, mu = pinned((lr, cols)), pinned((lr, cols))
+    eps[...] = synthetic_eps(lr, cols, 2026, sim.row0)
+    mu[...] = np.float32(4 * np.pi * 1e-7)
+    Ez, Hx, Hy = pinned((lr, cols)), pinned((lr, cols - 1)), pinned((hyr, cols))
+    out = pinned((lr, cols))
+    mur = fd_mur_coef(eps if sim.row0 == 0 else None, mu, dist, world, torch)
+    sim.set_point_source(grows // 2, cols // 2, inner, FC)
+    sim.set_probes([(grows // 2, cols // 2 + 16), (grows // 4, cols // 4)], inner)
+    h2d = (eps.nbytes + mu.nbytes + Ez.nbytes + Hx.nbytes + Hy.nbytes) * world
+    d2h = (out.nbytes + inner * 2 * 4) * world
+
+    def one():
+        sim.step_index = 0
+        sim.set_materials(eps, mu, mur)
+        sim.set_state(Ez, Hx, Hy)
+        sim.step(inner, k)
+        sim.read_Ez(out)
+        return sim.read_probes(0, inner)
+
+    one()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    # the API's copies block the host, so the wall clock (>= the device time) is the honest figure
+    ms = max(e0.elapsed_time(e1), wall_ms)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sim.close()
+    return {"value": grows * cols * inner * steps / (ms * 1e-3) / 1e9, "unit": "Gcell-updates/s",
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": steps,
+            "ms_per_step": ms / steps,
+            "what": "Simulation API with pinned host arrays: set_materials(eps, mu) + set_state + step(inner) + "
+                    "read_Ez + read_probes, every step"}
+
+
+def fd_mur_coef(eps_rank0, mu, dist, world, torch):
+    """Mur coefficient from global cell (0,0) (main.py:30-31), shared with every slab."""
+    if eps_rank0 is not None:
+        c = 1 / np.sqrt(mu[0, 0] * eps_rank0[0, 0])
+        coef = np.float32((c * DT - DX) / (c * DT + DX))
+    else:
+        coef = np.float32(0)
+    if world > 1:
+        t = torch.tensor([float(coef)], device="cuda", dtype=torch.float32)
+        dist.broadcast(t, src=0)
+        coef = np.float32(t.item())
+    return coef
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,189 @@
+"""y-slab domain decomposition over the GPUs of one box.
+
+The reference is single-process; this is the new multi-GPU capability named by BASELINE.json
+(configs[3]).  One process per GPU (torchrun), rank r owns a contiguous band of rows of all five arrays
+(rows are the reference's axis 0: `Ez[1:, :] - Ez[:-1, :]`, main.py:69) plus `halo` ghost rows on each
+side that has a neighbour.  A pass advances k <= halo leapfrog steps on chip; ghost rows go stale one row
+per step (the same argument as for tile halos), so after each pass the `halo` owned rows next to each
+internal boundary are sent to the neighbour's ghost rows, for Ez, Hx and Hy.  There is no reduction
+anywhere, so the result is bit-identical to the single-GPU run.
+
+The exchange is one batched group of NCCL send/recv over NVLink (torch.distributed P2P ops on tensors
+that alias the library's device buffers -- no staging copy).  The exchange plumbing (`HaloExchange`) is
+independent of CUDA so that it is covered by world_size-2 gloo tests on CPU.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+
+from .simulation import Simulation
+
+TOP, BOTTOM = 0, 1
+FIELDS = (0, 1, 2)  # Ez, Hx, Hy
+
+
+def slab_rows(global_rows: int, world: int, rank: int) -> tuple[int, int]:
+    """Balanced contiguous partition of rows: [begin, end) owned by `rank`."""
+    base, extra = divmod(global_rows, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+class HaloExchange:
+    """Send/recv of halo blocks with the two neighbours of `rank` in a 1-D chain of `world` ranks.
+
+    blocks(field, side) must return (send_tensor, recv_tensor): the `halo` owned rows next to `side` and
+    the ghost rows on that side, as torch tensors on the communication device."""
+
+    def __init__(self, rank: int, world: int, blocks: Callable, group=None):
+        self.rank, self.world, self.blocks, self.group = rank, world, blocks, group
+
+    def neighbours(self):
+        out = []
+        if self.rank > 0:
+            out.append((TOP, self.rank - 1))
+        if self.rank < self.world - 1:
+            out.append((BOTTOM, self.rank + 1))
+        return out
+
+    def exchange(self):
+        import torch.distributed as dist
+
+        ops = []
+        for side, peer in self.neighbours():
+            for f in FIELDS:
+                send, recv = self.blocks(f, side)
+                ops.append(dist.P2POp(dist.isend, send, peer, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, recv, peer, group=self.group))
+        if not ops:
+            return
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class _DeviceBlock:
+    """A device memory range exposed through __cuda_array_interface__ so torch can alias it."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class SlabSimulation:
+    """A global_rows x cols simulation sharded into y-slabs, one per rank.  With world == 1 it is a thin
+    wrapper over `Simulation`.  Mirrors `Simulation`'s interface with GLOBAL row indices."""
+
+    def __init__(self, global_rows: int, cols: int, dtype=np.float32, *, dt: float, dx: float, rank: int = 0,
+                 world: int = 1, device: int = 0, halo: int = 4, group=None):
+        self.rank, self.world, self.halo = rank, world, halo
+        self.global_rows, self.cols = global_rows, cols
+        self.row_begin, self.row_end = slab_rows(global_rows, world, rank)
+        slab = None if world == 1 else (global_rows, self.row_begin, self.row_end, halo)
+        self.sim = Simulation(global_rows, cols, dtype, dt=dt, dx=dx, device=device, slab=slab)
+        self.dtype = self.sim.dtype
+        self.row0, self.local_rows, self.hy_rows = self.sim.row0, self.sim.local_rows, self.sim._hy_rows
+        self.tile_launch_count = 0
+        self._tensors = {}
+        self._xchg = HaloExchange(rank, world, self._blocks, group) if world > 1 else None
+
+    # -- halo plumbing ------------------------------------------------------------------------
+    def _blocks(self, field, side):
+        import torch
+
+        sp, rp, nb = self.sim.halo_block(field, side)
+        out = []
+        for ptr in (sp, rp):
+            t = self._tensors.get(ptr)
+            if t is None:
+                t = torch.as_tensor(_DeviceBlock(ptr, nb), device=torch.device("cuda", self.sim.device))
+                self._tensors[ptr] = t
+            out.append(t)
+        return out
+
+    def exchange_halos(self):
+        if self._xchg is not None:
+            self._xchg.exchange()
+
+    # -- forwarding ---------------------------------------------------------------------------
+    def set_stream(self, s):
+        self.sim.set_stream(s)
+
+    def set_kernel_variant(self, v):
+        self.sim.set_kernel_variant(v)
+
+    def set_materials_random(self, seed, span=9.0):
+        self.sim.set_materials_random(seed, span)
+
+    def set_materials(self, eps_local, mu_local, mur_coef=None):
+        """eps/mu for the LOCAL rows (ghost rows included).  Slabs that do not hold global cell (0,0)
+        need `mur_coef` (main.py:30-31 uses that cell's materials only)."""
+        self.sim.set_materials(eps_local, mu_local)
+        if mur_coef is not None:
+            self.sim.set_mur_coef(mur_coef)
+
+    def set_state(self, Ez, Hx, Hy):
+        self.sim.set_state(Ez, Hx, Hy)
+
+    def set_point_source(self, row, col, nsteps, fc=30e9, kind="ricker"):
+        self.sim.set_point_source(row, col, nsteps, fc, kind)
+
+    def set_sources(self, cells, tables):
+        self.sim.set_sources(cells, tables)
+
+    def set_probes(self, cells, capacity_steps):
+        self.sim.set_probes(cells, capacity_steps)
+
+    def read_probes(self, first_step=0, n_steps=None):
+        """Traces of the probes this rank owns; columns of probes owned elsewhere are zero."""
+        return self.sim.read_probes(first_step, n_steps)
+
+    def read_Ez(self, out=None):
+        return self.sim.read_Ez(out)
+
+    def state(self):
+        return self.sim.state()
+
+    def owned(self, a):
+        """Slice the owned rows out of a local (ghost-including) array."""
+        lo = self.row_begin - self.row0
+        return a[..., lo:lo + (self.row_end - self.row_begin), :]
+
+    @property
+    def step_index(self):
+        return self.sim.step_index
+
+    @step_index.setter
+    def step_index(self, v):
+        self.sim.step_index = v
+
+    @property
+    def launch_count(self):
+        return self.sim.launch_count
+
+    def synchronize(self):
+        self.sim.synchronize()
+
+    def close(self):
+        self._tensors.clear()
+        self.sim.close()
+
+    # -- time stepping ------------------------------------------------------------------------
+    def step(self, n_steps: int, k: int = 0):
+        """n_steps leapfrog steps; with several slabs, halos are exchanged after every pass of k steps."""
+        from . import DEFAULT_K
+
+        k = k or DEFAULT_K
+        if self.world == 1:
+            self.sim.step(n_steps, k)
+            self.tile_launch_count += -(-n_steps // k)
+            return
+        k = min(k, self.halo)
+        left = n_steps
+        while left > 0:
+            kk = min(k, left)
+            self.sim.step(kk, kk)
+            self.tile_launch_count += 1
+            self.exchange_halos()
+            left -= kk

@@ -1,0 +1,119 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/fdtd2d.h declares, host
+logic of the Python surface, and hygiene rules (no oracle / CPU fallback in the product)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fdtd2d_b200 as fd
+from fdtd2d_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DT, DX, FC = 5e-14, 1e-4, 30e9
+
+
+@pytest.fixture(scope="module")
+def lib():
+    fd.build()
+    return _lib.lib()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "fdtd2d.h")).read()
+    declared = set(re.findall(r"^(?:int|double|const char\*)\s+(fdtd2d_\w+)\s*\(", hdr, flags=re.M))
+    assert len(declared) >= 28
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    raw = ctypes.CDLL(fd.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in include/fdtd2d.h but not exported"
+    assert lib.fdtd2d_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    n = ctypes.c_int(-1)
+    rc = lib.fdtd2d_device_count(ctypes.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(fd.Fdtd2dError) as e:
+        fd.Simulation(64, 64, np.float32, dt=DT, dx=DX)
+    assert e.value.code == -2  # FDTD2D_ECUDA: fails loudly, nothing is computed on the CPU
+    Ez, Hx, Hy = fd.grid_init(20, 20)
+    eps, mu = fd.material_init(None, 20, 20)
+    with pytest.raises(fd.Fdtd2dError):
+        fd.update_Hx_Hy(Ez, Hx, Hy, mu, eps, DT, DX)
+    with pytest.raises(fd.Fdtd2dError):
+        fd.update_Ez(Ez, Hx, Hy, mu, eps, DT, DX)
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    h = ctypes.c_void_p()
+    assert lib.fdtd2d_create(ctypes.byref(h), 10, 64, 0, 0, 1) == -1  # rows < 11
+    assert b"11" in lib.fdtd2d_last_error()
+    assert lib.fdtd2d_create(ctypes.byref(h), 64, 64, 7, 0, 1) == -1  # bad dtype
+    assert lib.fdtd2d_create_slab(ctypes.byref(h), 64, 64, 10, 5, 4, 0, 0) == -1  # empty slab
+    assert lib.fdtd2d_step(None, 1, 1) == -1 and lib.fdtd2d_sync(None) == -1
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "fdtd-2d_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+    assert "oracle" not in open(os.path.join(ROOT, "fdtd2d_b200.py")).read()
+
+
+def test_call_surface_matches_reference_names():
+    # fdtd.py:1-9 imports these from `main`
+    for name in ("grid_init", "material_init", "update_Hx_Hy", "update_Ez", "ricker", "sinusoidal"):
+        assert callable(getattr(fd, name))
+    Ez, Hx, Hy = fd.grid_init(7, 9)
+    assert Ez.shape == (7, 9) and Hx.shape == (7, 8) and Hy.shape == (6, 9) and Ez.dtype == np.float64
+
+
+def test_material_init_and_sources_vs_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "material_sources.npz"))
+    png = os.path.join(golden_dir, "structure.png")
+    for (R, C, bp) in [(64, 80, 10.0), (200, 200, 10.0), (37, 53, 4.0)]:
+        eps, mu = fd.material_init(png, R, C, bp)
+        assert np.array_equal(eps, g[f"eps_{R}x{C}_bp{bp:g}"]) and np.array_equal(mu, g[f"mu_{R}x{C}_bp{bp:g}"])
+    eps, mu = fd.material_init(None, 23, 17)
+    assert np.array_equal(eps, g["eps_none_23x17"]) and np.array_equal(mu, g["mu_none_23x17"])
+    steps = [int(i) for i in g["steps"]]
+    assert np.array_equal(np.array([fd.ricker_amplitude(i * DT, FC) for i in steps]), g["ricker_amp"])
+    assert np.array_equal(np.array([fd.sinusoidal_amplitude(i * DT, FC) for i in steps]), g["sinus_amp"])
+    assert np.array_equal(fd.ricker(6, 7, 2, 3, 667 * DT, FC), g["ricker_dense_6x7"])
+    tab = fd.source_table("ricker", 669, DT, FC)
+    assert np.array_equal(tab[[0, 1, 2, 10, 100, 500, 666, 667, 668]], g["ricker_amp"][:9])
+    assert fd.courant_number(eps, mu, DT, DX) == 0.14989629517391773  # SURVEY A.6 / fdtd.py:25-27
+
+
+def test_hash_uniform_host_definition(lib):
+    def ref(seed, g, r, c):
+        M = (1 << 64) - 1
+        z = ((((g << 40) ^ (r << 20) ^ c) + seed * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019)) & M
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        z ^= z >> 31
+        return (z >> 40) / 16777216.0
+
+    vals = []
+    for seed, g, r, c in [(0, 0, 0, 0), (2026, 0, 5, 7), (77, 3, 65535, 65535), (2**63 + 5, 1023, 12345, 54321)]:
+        v = lib.fdtd2d_hash_uniform(seed, g, r, c)
+        assert v == ref(seed, g, r, c) and 0.0 <= v < 1.0
+        vals.append(v)
+    assert len(set(vals)) == len(vals)
+    u = np.array([lib.fdtd2d_hash_uniform(9, 0, i, j) for i in range(64) for j in range(64)])
+    assert abs(u.mean() - 0.5) < 0.02 and u.min() >= 0 and u.max() < 1
+
+
+def test_slab_partition():
+    for rows, world in [(65536, 8), (16384, 3), (1000, 7), (200, 2)]:
+        spans = [fd.slab_rows(rows, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == rows
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
