@@ -231,6 +231,7 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = sim.launch_count
+    tl0 = sim.tile_launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -241,7 +242,7 @@ def main():
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = sim.launch_count - l0
-    tile_launches = sim.tile_launch_count
+    tile_launches = sim.tile_launch_count - tl0
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

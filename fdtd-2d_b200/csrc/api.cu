@@ -11,6 +11,7 @@
 
 #include "../../include/fdtd2d.h"
 #include "common.cuh"
+#include "tile_fast.cuh"
 #include "tile_generic.cuh"
 
 using namespace fdtd2d;
@@ -47,10 +48,22 @@ static int fail(int code, const char* fmt, ...) {
 // tile geometry of the generic kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int G_TH = 36, G_TW = 128, G_NT = 256;
+// register-resident fast kernel (fp32): F_MR rows per thread, F_NW warps -> F_TH x 128 tiles
+constexpr int F_MR = 4, F_NW = 8, F_MINB = 3, F_TH = F_MR * F_NW, F_NT = F_NW * 32;
 constexpr int MIN_LAST = 8;  // smallest core extent allowed for the last tile row/column (ring safety)
 
 struct TilePlan {
     int k = 0, hx = 0, CH = 0, CW = 0, tiles_y = 0, tiles_x = 0;
+};
+
+// One cached pass configuration: the tile grid for k steps and, in hybrid mode, which tiles are plain
+// (fast kernel) and which need the generic kernel (Mur ring, sources, probes, array edges).
+struct PassPlan {
+    bool valid = false;
+    TilePlan tp;
+    int n_generic = 0, n_fast = 0;
+    int* d_generic = nullptr;
+    int* d_fast = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -82,6 +95,10 @@ struct fdtd2d_sim {
     std::vector<int> probe_perm;  // sorted position -> caller's index
     long long step = 0, launches = 0;
     int variant = 0;
+    cudaStream_t side_stream = nullptr;  // generic (edge) tiles run here, concurrently with the fast tiles
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    PassPlan hybrid[FDTD2D_MAX_K + 1];
+    std::vector<Cell> h_src, h_probe;  // host copies (sorted) for tile classification
 };
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
@@ -101,11 +118,11 @@ static int plan_axis(int extent, int core_max, int quantum, int* core, int* tile
     return -1;
 }
 
-static int plan_tiles(const fdtd2d_sim* s, int k, TilePlan* tp) {
+static int plan_tiles(const fdtd2d_sim* s, int k, int TH, TilePlan* tp) {
     const int vn = (int)(16 / s->esize);
     tp->k = k;
     tp->hx = (int)round_up((size_t)k, (size_t)vn);
-    if (plan_axis(s->Rl, G_TH - 2 * k, 1, &tp->CH, &tp->tiles_y) != 0 ||
+    if (plan_axis(s->Rl, TH - 2 * k, 1, &tp->CH, &tp->tiles_y) != 0 ||
         plan_axis(s->C, G_TW - 2 * tp->hx, vn, &tp->CW, &tp->tiles_x) != 0)
         return fail(FDTD2D_EINVAL, "cannot tile a %d x %d grid with k=%d", s->Rl, s->C, k);
     return 0;
@@ -184,22 +201,31 @@ static int hy_rows(const fdtd2d_sim* s) {
     return (s->row0 + s->Rl == s->Rg) ? s->Rl - 1 : s->Rl;
 }
 
-template <typename T> static int set_smem_attr() {
-    static bool done[2] = {false, false};
-    const int idx = sizeof(T) == 4 ? 0 : 1;
-    if (!done[idx]) {
-        CUDA_TRY(cudaFuncSetAttribute(tile_generic_kernel<T, G_TH, G_TW, G_NT>,
+template <typename T, int TH> static int set_generic_attr() {
+    static bool done = false;
+    if (!done) {
+        CUDA_TRY(cudaFuncSetAttribute(tile_generic_kernel<T, TH, G_TW, G_NT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(6 * G_TH * G_TW * sizeof(T))));
-        done[idx] = true;
+                                      (int)(6 * TH * G_TW * sizeof(T))));
+        done = true;
     }
     return 0;
 }
 
-template <typename T> static int launch_pass(fdtd2d_sim* s, int k, int phases) {
-    TilePlan tp;
-    if (int rc = plan_tiles(s, k, &tp)) return rc;
-    PassParams<T> p;
+constexpr size_t F_SMEM = (size_t)(2 * F_TH * FAST_TW + 2 * F_NW * FAST_TW) * sizeof(float);
+
+static int set_fast_attr() {
+    static bool done = false;
+    if (!done) {
+        CUDA_TRY(cudaFuncSetAttribute(tile_fast_kernel<F_MR, F_NW, F_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)F_SMEM));
+        done = true;
+    }
+    return 0;
+}
+
+template <typename T> static void fill_params(const fdtd2d_sim* s, const TilePlan& tp, int phases, PassParams<T>* pp) {
+    PassParams<T>& p = *pp;
     memset(&p, 0, sizeof p);
     for (int f = 0; f < 3; ++f) {
         p.in[f] = static_cast<const T*>(s->field[s->cur][f]);
@@ -216,7 +242,7 @@ template <typename T> static int launch_pass(fdtd2d_sim* s, int k, int phases) {
     p.Rl = s->Rl;
     p.own_begin = s->row_begin;
     p.own_end = s->row_end;
-    p.k = k;
+    p.k = tp.k;
     p.hx = tp.hx;
     p.phases = phases;
     p.CH = tp.CH;
@@ -234,8 +260,15 @@ template <typename T> static int launch_pass(fdtd2d_sim* s, int k, int phases) {
     p.n_probe = s->n_probe;
     p.trace = static_cast<T*>(s->d_trace);
     p.trace_cap = s->trace_cap;
+}
 
-    if (int rc = set_smem_attr<T>()) return rc;
+// Generic kernel over the whole tile grid (fp64, per-function passes, variant 1).
+template <typename T> static int launch_generic_all(fdtd2d_sim* s, int k, int phases) {
+    TilePlan tp;
+    if (int rc = plan_tiles(s, k, G_TH, &tp)) return rc;
+    PassParams<T> p;
+    fill_params(s, tp, phases, &p);
+    if (int rc = set_generic_attr<T, G_TH>()) return rc;
     const long long n_tiles = (long long)s->batch * tp.tiles_y * tp.tiles_x;
     if (n_tiles > 0x7fffffffLL) return fail(FDTD2D_EINVAL, "too many tiles");
     const size_t smem = 6 * G_TH * G_TW * sizeof(T);
@@ -245,8 +278,120 @@ template <typename T> static int launch_pass(fdtd2d_sim* s, int k, int phases) {
     return 0;
 }
 
+static void free_plans(fdtd2d_sim* s) {
+    for (PassPlan& pl : s->hybrid) {
+        cudaFree(pl.d_generic);
+        cudaFree(pl.d_fast);
+        pl = PassPlan();
+    }
+}
+
+// Split the F_TH x 128 tile grid into plain tiles (fast kernel) and the rest (generic kernel).
+static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
+    TilePlan& tp = pl->tp;
+    if (int rc = plan_tiles(s, k, F_TH, &tp)) return rc;
+    const int per_grid = tp.tiles_y * tp.tiles_x;
+    const long long n_tiles = (long long)s->batch * per_grid;
+    if (n_tiles > 0x7fffffffLL) return fail(FDTD2D_EINVAL, "too many tiles");
+    std::vector<unsigned char> special((size_t)n_tiles, 0);
+    auto mark = [&](int b, int lrow, int col, int row_pad_lo, int row_pad_hi, int col_pad_lo, int col_pad_hi) {
+        // tiles whose window [t*CH - pad_lo, t*CH + CH + pad_hi) contains the cell
+        const int ty_lo = std::max(0, (lrow - tp.CH - row_pad_hi + 1 + tp.CH - 1) / tp.CH - 1);
+        const int tx_lo = std::max(0, (col - tp.CW - col_pad_hi + 1 + tp.CW - 1) / tp.CW - 1);
+        for (int ty = ty_lo; ty < tp.tiles_y; ++ty) {
+            const int r0 = ty * tp.CH - row_pad_lo, r1 = ty * tp.CH + tp.CH + row_pad_hi;
+            if (lrow < r0) break;
+            if (lrow >= r1) continue;
+            for (int tx = tx_lo; tx < tp.tiles_x; ++tx) {
+                const int c0 = tx * tp.CW - col_pad_lo, c1 = tx * tp.CW + tp.CW + col_pad_hi;
+                if (col < c0) break;
+                if (col >= c1) continue;
+                special[(size_t)b * per_grid + (size_t)ty * tp.tiles_x + tx] = 1;
+            }
+        }
+    };
+    // a source anywhere in the haloed tile; a probe in the core
+    for (const Cell& c : s->h_src)
+        mark(c.grid, c.row - s->row0, c.col, k, F_TH - k - tp.CH, tp.hx, FAST_TW - tp.hx - tp.CW);
+    for (const Cell& c : s->h_probe) mark(c.grid, c.row - s->row0, c.col, 0, 0, 0, 0);
+    std::vector<int> gen, fast;
+    for (int b = 0; b < s->batch; ++b)
+        for (int ty = 0; ty < tp.tiles_y; ++ty) {
+            const int lr0 = ty * tp.CH - k, gr0 = lr0 + s->row0;
+            const bool rows_plain = lr0 >= 0 && lr0 + F_TH <= s->Rl && gr0 >= RING && gr0 + F_TH <= s->Rg - RING;
+            for (int tx = 0; tx < tp.tiles_x; ++tx) {
+                const int lc0 = tx * tp.CW - tp.hx;
+                const bool cols_plain = lc0 >= RING && lc0 + FAST_TW <= s->C - RING;
+                const int id = b * per_grid + ty * tp.tiles_x + tx;
+                (rows_plain && cols_plain && !special[id] ? fast : gen).push_back(id);
+            }
+        }
+    pl->n_generic = (int)gen.size();
+    pl->n_fast = (int)fast.size();
+    if (pl->n_generic) {
+        CUDA_TRY(cudaMalloc(&pl->d_generic, sizeof(int) * gen.size()));
+        CUDA_TRY(cudaMemcpyAsync(pl->d_generic, gen.data(), sizeof(int) * gen.size(), cudaMemcpyHostToDevice, s->stream));
+    }
+    if (pl->n_fast) {
+        CUDA_TRY(cudaMalloc(&pl->d_fast, sizeof(int) * fast.size()));
+        CUDA_TRY(cudaMemcpyAsync(pl->d_fast, fast.data(), sizeof(int) * fast.size(), cudaMemcpyHostToDevice, s->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));  // the host vectors die here
+    pl->valid = true;
+    return 0;
+}
+
+// fp32 hybrid pass: plain tiles on the register-resident kernel, the rest on the generic kernel
+// (same tile grid), the two launches overlapped on two streams.
+static int launch_hybrid(fdtd2d_sim* s, int k) {
+    PassPlan& pl = s->hybrid[k];
+    if (!pl.valid)
+        if (int rc = classify_tiles(s, k, &pl)) return rc;
+    PassParams<float> p;
+    fill_params(s, pl.tp, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC, &p);
+    const bool both = pl.n_generic > 0 && pl.n_fast > 0;
+    cudaStream_t gstream = s->stream;
+    if (both) {
+        if (!s->side_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventRecord(s->ev_fork, s->stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
+        gstream = s->side_stream;
+    }
+    if (pl.n_generic) {
+        if (int rc = set_generic_attr<float, F_TH>()) return rc;
+        p.tile_list = pl.d_generic;
+        tile_generic_kernel<float, F_TH, G_TW, G_NT>
+            <<<(unsigned)pl.n_generic, G_NT, 6 * F_TH * G_TW * sizeof(float), gstream>>>(p);
+        CUDA_TRY(cudaGetLastError());
+        s->launches += 1;
+    }
+    if (pl.n_fast) {
+        if (int rc = set_fast_attr()) return rc;
+        p.tile_list = pl.d_fast;
+        tile_fast_kernel<F_MR, F_NW, F_MINB><<<(unsigned)pl.n_fast, F_NT, F_SMEM, s->stream>>>(p);
+        CUDA_TRY(cudaGetLastError());
+        s->launches += 1;
+    }
+    if (both) {
+        CUDA_TRY(cudaEventRecord(s->ev_join, s->side_stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+    }
+    return 0;
+}
+
 static int run_pass(fdtd2d_sim* s, int k, int phases) {
-    int rc = s->dtype == FDTD2D_F32 ? launch_pass<float>(s, k, phases) : launch_pass<double>(s, k, phases);
+    const int all = FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC;
+    int rc;
+    if (s->dtype == FDTD2D_F64)
+        rc = launch_generic_all<double>(s, k, phases);
+    else if (phases == all && s->variant != 1)
+        rc = launch_hybrid(s, k);
+    else
+        rc = launch_generic_all<float>(s, k, phases);
     if (rc) return rc;
     s->cur ^= 1;
     return 0;
@@ -380,6 +525,10 @@ int fdtd2d_destroy(fdtd2d_sim* s) {
     cudaFree(s->d_probe);
     cudaFree(s->d_probe_range);
     cudaFree(s->d_trace);
+    free_plans(s);
+    if (s->side_stream) cudaStreamDestroy(s->side_stream);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
     return 0;
@@ -596,6 +745,8 @@ int fdtd2d_set_sources(fdtd2d_sim* s, int n_cells, const int32_t* grid, const in
     s->d_src_range = nullptr;
     s->d_amp = nullptr;
     s->n_src = s->n_waves = s->amp_steps = 0;
+    s->h_src.clear();
+    free_plans(s);
     if (n_cells == 0) return 0;
     REQUIRE(n_cells > 0 && row && col && wave && tables && n_waves > 0 && n_steps > 0, "bad source arguments");
     std::vector<Cell> cells;
@@ -607,6 +758,7 @@ int fdtd2d_set_sources(fdtd2d_sim* s, int n_cells, const int32_t* grid, const in
     CUDA_TRY(cudaMemcpy(s->d_src, cells.data(), sizeof(Cell) * n_cells, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(s->d_src_range, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(s->d_amp, tables, sizeof(double) * (size_t)n_waves * n_steps, cudaMemcpyHostToDevice));
+    s->h_src = cells;
     s->n_src = n_cells;
     s->n_waves = n_waves;
     s->amp_steps = n_steps;
@@ -627,6 +779,8 @@ int fdtd2d_set_probes(fdtd2d_sim* s, int n_probes, const int32_t* grid, const in
     s->n_probe = 0;
     s->trace_cap = 0;
     s->probe_perm.clear();
+    s->h_probe.clear();
+    free_plans(s);
     if (n_probes == 0) return 0;
     REQUIRE(n_probes > 0 && row && col && capacity_steps > 0, "bad probe arguments");
     std::vector<Cell> cells;
@@ -639,6 +793,7 @@ int fdtd2d_set_probes(fdtd2d_sim* s, int n_probes, const int32_t* grid, const in
     CUDA_TRY(cudaMemcpy(s->d_probe, cells.data(), sizeof(Cell) * n_probes, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(s->d_probe_range, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemset(s->d_trace, 0, tbytes));
+    s->h_probe = cells;
     s->n_probe = n_probes;
     s->trace_cap = capacity_steps;
     return 0;
