@@ -9,17 +9,17 @@ There is no CPU fallback.
 """
 from . import _lib
 
-DEFAULT_K = 4  # leapfrog steps per HBM round trip when the caller does not choose
+DEFAULT_K = 8  # leapfrog steps per HBM round trip when the caller does not choose (fp32; fp64 uses 4)
 
 from ._lib import EXPORTED_SYMBOLS, Fdtd2dError
 from .api import (EPSILON0, MU0, grid_init, material_init, release_handles, ricker, sinusoidal, update_Ez,
                   update_Hx_Hy)
 from .build import LIB_PATH, build
-from .distributed import HaloExchange, SlabSimulation, slab_rows
+from .distributed import HaloExchange, InProcessSlabs, SlabSimulation, slab_rows
 from .simulation import (Simulation, courant_number, ricker_amplitude, sinusoidal_amplitude, source_table)
 
 __all__ = [
     "grid_init", "material_init", "update_Hx_Hy", "update_Ez", "ricker", "sinusoidal", "Simulation",
     "courant_number", "ricker_amplitude", "sinusoidal_amplitude", "source_table", "build", "LIB_PATH",
-    "Fdtd2dError", "EXPORTED_SYMBOLS", "SlabSimulation", "HaloExchange", "slab_rows", "DEFAULT_K", "EPSILON0", "MU0", "release_handles",
+    "Fdtd2dError", "EXPORTED_SYMBOLS", "SlabSimulation", "InProcessSlabs", "HaloExchange", "slab_rows", "DEFAULT_K", "EPSILON0", "MU0", "release_handles",
 ]

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -48,8 +49,14 @@ static int fail(int code, const char* fmt, ...) {
 // tile geometry of the generic kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int G_TH = 36, G_TW = 128, G_NT = 256;
-// register-resident fast kernel (fp32): F_MR rows per thread, F_NW warps -> F_TH x 128 tiles
-constexpr int F_MR = 4, F_NW = 8, F_MINB = 3, F_TH = F_MR * F_NW, F_NT = F_NW * 32;
+// register-resident fast kernel (fp32): MR rows per thread, NW warps -> (MR*NW) x 128 tiles.
+// Several shapes are compiled; fdtd2d_set_fast_config / FDTD2D_FAST_CFG picks one (default below).
+struct FastCfg {
+    int MR, NW;
+};
+static const FastCfg kFastCfgs[] = {{4, 8}, {4, 12}, {4, 16}, {6, 8}, {8, 8}, {2, 16}};
+constexpr int N_FAST_CFG = sizeof(kFastCfgs) / sizeof(kFastCfgs[0]);
+constexpr int DEFAULT_FAST_CFG = 3;  // 48 x 128 tiles, 2 CTAs/SM: best measured (profiles/r1_sweep.txt)
 constexpr int MIN_LAST = 8;  // smallest core extent allowed for the last tile row/column (ring safety)
 
 struct TilePlan {
@@ -95,6 +102,7 @@ struct fdtd2d_sim {
     std::vector<int> probe_perm;  // sorted position -> caller's index
     long long step = 0, launches = 0;
     int variant = 0;
+    int fast_cfg = DEFAULT_FAST_CFG;
     cudaStream_t side_stream = nullptr;  // generic (edge) tiles run here, concurrently with the fast tiles
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     PassPlan hybrid[FDTD2D_MAX_K + 1];
@@ -212,15 +220,25 @@ template <typename T, int TH> static int set_generic_attr() {
     return 0;
 }
 
-constexpr size_t F_SMEM = (size_t)(2 * F_TH * FAST_TW + 2 * F_NW * FAST_TW) * sizeof(float);
+static size_t fast_smem(int MR, int NW) { return (size_t)(2 * MR * NW * FAST_TW + 2 * NW * FAST_TW) * sizeof(float); }
 
-static int set_fast_attr() {
+template <int MR, int NW, int MINB>
+static int launch_fast_t(fdtd2d_sim* s, const PassParams<float>& p, int n_tiles) {
     static bool done = false;
+    const size_t smem = fast_smem(MR, NW);
     if (!done) {
-        CUDA_TRY(cudaFuncSetAttribute(tile_fast_kernel<F_MR, F_NW, F_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)F_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(tile_fast_kernel<MR, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
     }
+    tile_fast_kernel<MR, NW, MINB><<<(unsigned)n_tiles, NW * 32, smem, s->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <int TH> static int launch_generic_list_t(const PassParams<float>& p, int n_tiles, cudaStream_t st) {
+    if (int rc = set_generic_attr<float, TH>()) return rc;
+    tile_generic_kernel<float, TH, G_TW, G_NT><<<(unsigned)n_tiles, G_NT, 6 * TH * G_TW * sizeof(float), st>>>(p);
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
@@ -286,9 +304,10 @@ static void free_plans(fdtd2d_sim* s) {
     }
 }
 
-// Split the F_TH x 128 tile grid into plain tiles (fast kernel) and the rest (generic kernel).
+// Split the TH x 128 tile grid into plain tiles (fast kernel) and the rest (generic kernel).
 static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
     TilePlan& tp = pl->tp;
+    const int F_TH = kFastCfgs[s->fast_cfg].MR * kFastCfgs[s->fast_cfg].NW;
     if (int rc = plan_tiles(s, k, F_TH, &tp)) return rc;
     const int per_grid = tp.tiles_y * tp.tiles_x;
     const long long n_tiles = (long long)s->batch * per_grid;
@@ -361,19 +380,32 @@ static int launch_hybrid(fdtd2d_sim* s, int k) {
         CUDA_TRY(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
         gstream = s->side_stream;
     }
+    const FastCfg fc = kFastCfgs[s->fast_cfg];
     if (pl.n_generic) {
-        if (int rc = set_generic_attr<float, F_TH>()) return rc;
         p.tile_list = pl.d_generic;
-        tile_generic_kernel<float, F_TH, G_TW, G_NT>
-            <<<(unsigned)pl.n_generic, G_NT, 6 * F_TH * G_TW * sizeof(float), gstream>>>(p);
-        CUDA_TRY(cudaGetLastError());
+        int rc;
+        switch (fc.MR * fc.NW) {
+            case 32: rc = launch_generic_list_t<32>(p, pl.n_generic, gstream); break;
+            case 48: rc = launch_generic_list_t<48>(p, pl.n_generic, gstream); break;
+            case 64: rc = launch_generic_list_t<64>(p, pl.n_generic, gstream); break;
+            default: return fail(FDTD2D_EINVAL, "no generic kernel for %d-row tiles", fc.MR * fc.NW);
+        }
+        if (rc) return rc;
         s->launches += 1;
     }
     if (pl.n_fast) {
-        if (int rc = set_fast_attr()) return rc;
         p.tile_list = pl.d_fast;
-        tile_fast_kernel<F_MR, F_NW, F_MINB><<<(unsigned)pl.n_fast, F_NT, F_SMEM, s->stream>>>(p);
-        CUDA_TRY(cudaGetLastError());
+        int rc;
+        switch (s->fast_cfg) {
+            case 0: rc = launch_fast_t<4, 8, 3>(s, p, pl.n_fast); break;
+            case 1: rc = launch_fast_t<4, 12, 2>(s, p, pl.n_fast); break;
+            case 2: rc = launch_fast_t<4, 16, 1>(s, p, pl.n_fast); break;
+            case 3: rc = launch_fast_t<6, 8, 2>(s, p, pl.n_fast); break;
+            case 4: rc = launch_fast_t<8, 8, 1>(s, p, pl.n_fast); break;
+            case 5: rc = launch_fast_t<2, 16, 2>(s, p, pl.n_fast); break;
+            default: return fail(FDTD2D_EINVAL, "bad fast config");
+        }
+        if (rc) return rc;
         s->launches += 1;
     }
     if (both) {
@@ -496,6 +528,10 @@ static int create_impl(fdtd2d_sim** out, int Rg, int C, int row_begin, int row_e
             return fail(e == cudaErrorMemoryAllocation ? FDTD2D_ENOMEM : FDTD2D_ECUDA,
                         "device allocation of %zu bytes failed: %s", nb, cudaGetErrorString(e));
         }
+    }
+    if (const char* e = getenv("FDTD2D_FAST_CFG")) {
+        const int v = atoi(e);
+        if (v >= 0 && v < N_FAST_CFG) s->fast_cfg = v;
     }
     *out = s;
     return 0;
@@ -825,7 +861,7 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
     REQUIRE(k_temporal >= 0 && k_temporal <= FDTD2D_MAX_K, "k_temporal must be in [0, %d]", FDTD2D_MAX_K);
     if (!s->coeffs_set || !s->mur_set) return fail(FDTD2D_ESTATE, "coefficients / Mur coefficient not set");
     if (int rc = use_device(s)) return rc;
-    int k = k_temporal ? k_temporal : 4;
+    int k = k_temporal ? k_temporal : (s->dtype == FDTD2D_F32 ? 8 : 4);
     if (s->has_top_nb || s->has_bot_nb) {
         k = std::min(k, s->halo);
         REQUIRE(n_steps <= s->halo, "a slab handle can advance at most halo=%d steps between halo exchanges", s->halo);

@@ -76,7 +76,7 @@ class SlabSimulation:
     wrapper over `Simulation`.  Mirrors `Simulation`'s interface with GLOBAL row indices."""
 
     def __init__(self, global_rows: int, cols: int, dtype=np.float32, *, dt: float, dx: float, rank: int = 0,
-                 world: int = 1, device: int = 0, halo: int = 4, group=None):
+                 world: int = 1, device: int = 0, halo: int = 8, group=None):
         self.rank, self.world, self.halo = rank, world, halo
         self.global_rows, self.cols = global_rows, cols
         self.row_begin, self.row_end = slab_rows(global_rows, world, rank)
@@ -187,3 +187,57 @@ class SlabSimulation:
             self.tile_launch_count += 1
             self.exchange_halos()
             left -= kk
+
+
+class InProcessSlabs:
+    """All slabs of a global_rows x cols grid driven by ONE process: slab i lives on devices[i % len].
+    Halo blocks move with device-to-device copies (peer copies over NVLink when the slabs sit on
+    different GPUs).  This is the single-process flavour of the decomposition; it also lets the slab
+    logic (row offsets, ghost rows, tile classification) be checked on a one-GPU box."""
+
+    def __init__(self, global_rows, cols, dtype=np.float32, *, dt, dx, world, devices=(0,), halo=8):
+        self.world, self.halo = world, halo
+        self.slabs = [SlabSimulation(global_rows, cols, dtype, dt=dt, dx=dx, rank=r, world=world,
+                                     device=devices[r % len(devices)], halo=halo) for r in range(world)]
+        for s in self.slabs:
+            s._xchg = None  # exchanges are done here, not over torch.distributed
+
+    def each(self, fn):
+        return [fn(s) for s in self.slabs]
+
+    def exchange_halos(self):
+        self.each(lambda s: s.synchronize())
+        for r in range(self.world - 1):
+            up, dn = self.slabs[r], self.slabs[r + 1]
+            for f in FIELDS:
+                up_send, up_recv = up._blocks(f, BOTTOM)
+                dn_send, dn_recv = dn._blocks(f, TOP)
+                dn_recv.copy_(up_send)
+                up_recv.copy_(dn_send)
+        import torch
+
+        for d in {s.sim.device for s in self.slabs}:
+            torch.cuda.synchronize(d)
+
+    def step(self, n_steps, k=0):
+        k = min(k or 8, self.halo) if self.world > 1 else (k or 0)
+        left = n_steps
+        while left > 0:
+            kk = min(k, left) if k else left
+            self.each(lambda s: s.sim.step(kk, kk if self.world > 1 else k))
+            if self.world > 1:
+                self.exchange_halos()
+            left -= kk
+
+    def gather(self):
+        """(Ez, Hx, Hy) of the whole grid in the reference's shapes, assembled from the owned rows
+        (the last slab's Hy is one row short, main.py:84; slicing clamps)."""
+        out = [[], [], []]
+        for s in self.slabs:
+            lo, n = s.row_begin - s.row0, s.row_end - s.row_begin
+            for f, a in enumerate(s.state()):
+                out[f].append(a[..., lo:lo + n, :])
+        return tuple(np.concatenate(parts, axis=-2) for parts in out)
+
+    def close(self):
+        self.each(lambda s: s.close())

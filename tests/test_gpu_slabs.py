@@ -1,0 +1,84 @@
+"""y-slab decomposition on the GPU: 2, 3 and 4 slabs must reproduce the single-domain result bit for bit
+(no reduction is involved).  Runs the slabs of one grid from one process (InProcessSlabs) so that it
+also works on a one-GPU box; with several GPUs visible the slabs are spread over them (peer copies)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+DT, DX, FC = 5e-14, 1e-4, 30e9
+
+
+def _devices():
+    import torch
+
+    return tuple(range(torch.cuda.device_count()))
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("world,k", [(2, 4), (3, 8), (4, 5)])
+def test_slabs_match_single_domain_and_oracle(world, k, dtype):
+    import fdtd2d_b200 as fd
+    from oracle import c_oracle, numpy_oracle as npo
+
+    R, C, n = 700, 900, 43
+    rng = np.random.default_rng(world * 10 + k)
+    eps = (8.85418e-12 * (1 + 9 * rng.random((R, C)))).astype(dtype)
+    mu = (4 * np.pi * 1e-7 * (1 + 0.3 * rng.random((R, C)))).astype(dtype)
+    Ez = (1e-3 * rng.standard_normal((R, C))).astype(dtype)
+    Hx = (1e-6 * rng.standard_normal((R, C - 1))).astype(dtype)
+    Hy = (1e-6 * rng.standard_normal((R - 1, C))).astype(dtype)
+    ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(dtype))
+    amp = npo.source_table("ricker", n, DT, FC)
+    # sources and probes next to / on slab boundaries on purpose
+    b1 = fd.slab_rows(R, world, 1)[0]
+    cells = [(R // 2, C // 2), (b1, 100), (b1 - 1, 300), (b1 + 3, 500), (7, 7)]
+    probes = [(b1, 101), (b1 - 2, 301), (R - 1, C - 1), (0, 0), (R // 2, C // 2)]
+    oEz, oHx, oHy = Ez.copy(), Hx.copy(), Hy.copy()
+    otrace = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, n, amp, cells, probes, omp=True)
+
+    grp = fd.InProcessSlabs(R, C, dtype, dt=DT, dx=DX, world=world, devices=_devices(), halo=8)
+    try:
+        for s in grp.slabs:
+            lo, hi = s.row0, s.row0 + s.local_rows
+            s.set_materials(eps[lo:hi], mu[lo:hi], coef)
+            s.set_state(Ez[lo:hi], Hx[lo:hi], Hy[lo:min(hi, R - 1)])
+            s.set_sources([(0, r, c, 0) for r, c in cells], amp[None, :])
+            s.set_probes(probes, n)
+        grp.step(n, k)
+        gEz, gHx, gHy = grp.gather()
+        traces = [s.read_probes(0, n) for s in grp.slabs]
+    finally:
+        grp.close()
+    assert np.array_equal(gEz, oEz) and np.array_equal(gHx, oHx) and np.array_equal(gHy, oHy)
+    # every probe is recorded by exactly its owner; the others leave zeros
+    total = np.zeros_like(otrace)
+    for p, (r, c) in enumerate(probes):
+        owners = [i for i, s in enumerate(grp.slabs) if s.row_begin <= r < s.row_end]
+        assert len(owners) == 1
+        total[:, p] = traces[owners[0]][:, p]
+    assert np.array_equal(total, otrace)
+
+
+def test_large_slabs_vs_single_domain_fast_path():
+    """4 slabs of a 4096 x 3000 fp32 grid (fast kernel on the plain tiles) == single domain, k = 8."""
+    import fdtd2d_b200 as fd
+
+    R, C, n = 4096, 3000, 40
+    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
+        sim.set_materials_random(9, 9.0)
+        sim.set_point_source(R // 2, C // 2, 700, FC)
+        sim.step_index = 640
+        sim.step(n, 8)
+        ref = sim.state()
+    grp = fd.InProcessSlabs(R, C, np.float32, dt=DT, dx=DX, world=4, devices=_devices(), halo=8)
+    try:
+        for s in grp.slabs:
+            s.set_materials_random(9, 9.0)
+            s.set_point_source(R // 2, C // 2, 700, FC)
+            s.step_index = 640
+        grp.step(n, 8)
+        got = grp.gather()
+    finally:
+        grp.close()
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
