@@ -209,8 +209,11 @@ static int hy_rows(const fdtd2d_sim* s) {
     return (s->row0 + s->Rl == s->Rg) ? s->Rl - 1 : s->Rl;
 }
 
-template <typename T, int TH> static int set_generic_attr() {
-    static bool done = false;
+constexpr int MAX_DEVICES = 64;  // function attributes are per device: remember where they were set
+
+template <typename T, int TH> static int set_generic_attr(int dev) {
+    static bool done_[MAX_DEVICES] = {};
+    bool& done = done_[dev % MAX_DEVICES];
     if (!done) {
         CUDA_TRY(cudaFuncSetAttribute(tile_generic_kernel<T, TH, G_TW, G_NT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -224,7 +227,8 @@ static size_t fast_smem(int MR, int NW) { return (size_t)(2 * MR * NW * FAST_TW 
 
 template <int MR, int NW, int MINB>
 static int launch_fast_t(fdtd2d_sim* s, const PassParams<float>& p, int n_tiles) {
-    static bool done = false;
+    static bool done_[MAX_DEVICES] = {};
+    bool& done = done_[s->device % MAX_DEVICES];
     const size_t smem = fast_smem(MR, NW);
     if (!done) {
         CUDA_TRY(cudaFuncSetAttribute(tile_fast_kernel<MR, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -235,8 +239,8 @@ static int launch_fast_t(fdtd2d_sim* s, const PassParams<float>& p, int n_tiles)
     return 0;
 }
 
-template <int TH> static int launch_generic_list_t(const PassParams<float>& p, int n_tiles, cudaStream_t st) {
-    if (int rc = set_generic_attr<float, TH>()) return rc;
+template <int TH> static int launch_generic_list_t(int dev, const PassParams<float>& p, int n_tiles, cudaStream_t st) {
+    if (int rc = set_generic_attr<float, TH>(dev)) return rc;
     tile_generic_kernel<float, TH, G_TW, G_NT><<<(unsigned)n_tiles, G_NT, 6 * TH * G_TW * sizeof(float), st>>>(p);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -286,7 +290,7 @@ template <typename T> static int launch_generic_all(fdtd2d_sim* s, int k, int ph
     if (int rc = plan_tiles(s, k, G_TH, &tp)) return rc;
     PassParams<T> p;
     fill_params(s, tp, phases, &p);
-    if (int rc = set_generic_attr<T, G_TH>()) return rc;
+    if (int rc = set_generic_attr<T, G_TH>(s->device)) return rc;
     const long long n_tiles = (long long)s->batch * tp.tiles_y * tp.tiles_x;
     if (n_tiles > 0x7fffffffLL) return fail(FDTD2D_EINVAL, "too many tiles");
     const size_t smem = 6 * G_TH * G_TW * sizeof(T);
@@ -385,9 +389,9 @@ static int launch_hybrid(fdtd2d_sim* s, int k) {
         p.tile_list = pl.d_generic;
         int rc;
         switch (fc.MR * fc.NW) {
-            case 32: rc = launch_generic_list_t<32>(p, pl.n_generic, gstream); break;
-            case 48: rc = launch_generic_list_t<48>(p, pl.n_generic, gstream); break;
-            case 64: rc = launch_generic_list_t<64>(p, pl.n_generic, gstream); break;
+            case 32: rc = launch_generic_list_t<32>(s->device, p, pl.n_generic, gstream); break;
+            case 48: rc = launch_generic_list_t<48>(s->device, p, pl.n_generic, gstream); break;
+            case 64: rc = launch_generic_list_t<64>(s->device, p, pl.n_generic, gstream); break;
             default: return fail(FDTD2D_EINVAL, "no generic kernel for %d-row tiles", fc.MR * fc.NW);
         }
         if (rc) return rc;

@@ -82,3 +82,22 @@ def test_large_slabs_vs_single_domain_fast_path():
         grp.close()
     for a, b in zip(got, ref):
         assert np.array_equal(a, b)
+
+
+def test_multiprocess_nccl_slabs():
+    """One rank per GPU over NCCL (the production layout).  Needs >= 2 GPUs; skipped on a 1-GPU box."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 2 if n < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", "29611", os.path.join(root, "tests", "mp_slab_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK bit-exact" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
