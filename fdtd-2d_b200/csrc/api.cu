@@ -13,6 +13,7 @@
 #include "../../include/fdtd2d.h"
 #include "common.cuh"
 #include "tile_fast.cuh"
+#include "tile_tma.cuh"
 #include "tile_generic.cuh"
 
 using namespace fdtd2d;
@@ -48,15 +49,19 @@ static int fail(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------------
 // tile geometry of the generic kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int G_TH = 36, G_TW = 128, G_NT = 256;
+constexpr int G_TH = 36, G_TW = 128;
+// threads per generic CTA: tiles that fill most of an SM's shared memory (1 CTA/SM) get 1024 threads
+template <typename T, int TH> constexpr int generic_nt() { return 6 * TH * G_TW * sizeof(T) > 113 * 1024 ? 1024 : 512; }
 // register-resident fast kernel (fp32): MR rows per thread, NW warps -> (MR*NW) x 128 tiles.
 // Several shapes are compiled; fdtd2d_set_fast_config / FDTD2D_FAST_CFG picks one (default below).
 struct FastCfg {
     int MR, NW;
+    bool tma;  // persistent TMA-fed kernel (tile_tma.cuh) instead of the plain-load kernel (tile_fast.cuh)
 };
-static const FastCfg kFastCfgs[] = {{4, 8}, {4, 12}, {4, 16}, {6, 8}, {8, 8}, {2, 16}};
+static const FastCfg kFastCfgs[] = {{4, 8, false}, {4, 12, false}, {4, 16, false}, {6, 8, false},
+                                    {8, 8, false}, {2, 16, false}, {4, 16, true}};
 constexpr int N_FAST_CFG = sizeof(kFastCfgs) / sizeof(kFastCfgs[0]);
-constexpr int DEFAULT_FAST_CFG = 3;  // 48 x 128 tiles, 2 CTAs/SM: best measured (profiles/r1_sweep.txt)
+constexpr int DEFAULT_FAST_CFG = 6;  // persistent TMA-fed 64 x 128 tiles: best measured (profiles/)
 constexpr int MIN_LAST = 8;  // smallest core extent allowed for the last tile row/column (ring safety)
 
 struct TilePlan {
@@ -107,6 +112,9 @@ struct fdtd2d_sim {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     PassPlan hybrid[FDTD2D_MAX_K + 1];
     std::vector<Cell> h_src, h_probe;  // host copies (sorted) for tile classification
+    TmaMaps tma_maps[2];               // tensor maps with field set 0 / 1 as the pass input
+    int tma_box_rows = 0;              // box height the maps were encoded for (0 = not built)
+    int sm_count = 0;
 };
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
@@ -215,7 +223,7 @@ template <typename T, int TH> static int set_generic_attr(int dev) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[dev % MAX_DEVICES];
     if (!done) {
-        CUDA_TRY(cudaFuncSetAttribute(tile_generic_kernel<T, TH, G_TW, G_NT>,
+        CUDA_TRY(cudaFuncSetAttribute(tile_generic_kernel<T, TH, G_TW, generic_nt<T, TH>()>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(6 * TH * G_TW * sizeof(T))));
         done = true;
@@ -239,9 +247,65 @@ static int launch_fast_t(fdtd2d_sim* s, const PassParams<float>& p, int n_tiles)
     return 0;
 }
 
+// ---- TMA tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_map(const fdtd2d_sim* s, void* base, int box_rows, CUtensorMap* out) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qr));
+        if (!sym || qr != cudaDriverEntryPointSuccess) return fail(FDTD2D_ECUDA, "cuTensorMapEncodeTiled not available");
+        fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    // 2-D view: inner = padded row (pitch floats), outer = all rows of all grids of the batch
+    const cuuint64_t dims[2] = {(cuuint64_t)s->pitch, (cuuint64_t)s->Rl * (cuuint64_t)s->batch};
+    const cuuint64_t strides[1] = {(cuuint64_t)s->pitch * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)FAST_TW, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FDTD2D_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+static int build_tma_maps(fdtd2d_sim* s, int box_rows) {
+    if (s->tma_box_rows == box_rows) return 0;
+    for (int h = 0; h < 2; ++h) {
+        TmaMaps& m = s->tma_maps[h];
+        if (int rc = encode_map(s, s->field[h][0], box_rows, &m.ez)) return rc;
+        if (int rc = encode_map(s, s->field[h][1], box_rows, &m.hx)) return rc;
+        if (int rc = encode_map(s, s->field[h][2], box_rows, &m.hy)) return rc;
+        if (int rc = encode_map(s, s->ce, box_rows, &m.ce)) return rc;
+        if (int rc = encode_map(s, s->ch, box_rows, &m.ch)) return rc;
+    }
+    s->tma_box_rows = box_rows;
+    return 0;
+}
+
+template <int MR, int NW> static int launch_tma_t(fdtd2d_sim* s, const PassParams<float>& p, int n_tiles) {
+    static bool done_[MAX_DEVICES] = {};
+    bool& done = done_[s->device % MAX_DEVICES];
+    const size_t smem = (size_t)(5 * MR * NW * FAST_TW + 2 * NW * FAST_TW) * sizeof(float);
+    if (!done) {
+        CUDA_TRY(cudaFuncSetAttribute(tile_tma_kernel<MR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        done = true;
+    }
+    if (!s->sm_count) CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
+    if (int rc = build_tma_maps(s, MR * NW)) return rc;
+    const int grid = std::min(n_tiles, s->sm_count);
+    tile_tma_kernel<MR, NW><<<grid, NW * 32, smem, s->stream>>>(s->tma_maps[s->cur], p, n_tiles);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 template <int TH> static int launch_generic_list_t(int dev, const PassParams<float>& p, int n_tiles, cudaStream_t st) {
     if (int rc = set_generic_attr<float, TH>(dev)) return rc;
-    tile_generic_kernel<float, TH, G_TW, G_NT><<<(unsigned)n_tiles, G_NT, 6 * TH * G_TW * sizeof(float), st>>>(p);
+    constexpr int NT = generic_nt<float, TH>();
+    tile_generic_kernel<float, TH, G_TW, NT><<<(unsigned)n_tiles, NT, 6 * TH * G_TW * sizeof(float), st>>>(p);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -294,7 +358,8 @@ template <typename T> static int launch_generic_all(fdtd2d_sim* s, int k, int ph
     const long long n_tiles = (long long)s->batch * tp.tiles_y * tp.tiles_x;
     if (n_tiles > 0x7fffffffLL) return fail(FDTD2D_EINVAL, "too many tiles");
     const size_t smem = 6 * G_TH * G_TW * sizeof(T);
-    tile_generic_kernel<T, G_TH, G_TW, G_NT><<<(unsigned)n_tiles, G_NT, smem, s->stream>>>(p);
+    constexpr int NT = generic_nt<T, G_TH>();
+    tile_generic_kernel<T, G_TH, G_TW, NT><<<(unsigned)n_tiles, NT, smem, s->stream>>>(p);
     CUDA_TRY(cudaGetLastError());
     s->launches += 1;
     return 0;
@@ -407,6 +472,7 @@ static int launch_hybrid(fdtd2d_sim* s, int k) {
             case 3: rc = launch_fast_t<6, 8, 2>(s, p, pl.n_fast); break;
             case 4: rc = launch_fast_t<8, 8, 1>(s, p, pl.n_fast); break;
             case 5: rc = launch_fast_t<2, 16, 2>(s, p, pl.n_fast); break;
+            case 6: rc = launch_tma_t<4, 16>(s, p, pl.n_fast); break;
             default: return fail(FDTD2D_EINVAL, "bad fast config");
         }
         if (rc) return rc;

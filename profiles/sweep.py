@@ -38,6 +38,6 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         child(int(sys.argv[1]))
     else:
-        for cfg in range(6):
+        for cfg in [int(c) for c in os.environ.get("SWEEP_CFGS", "0,1,2,3,4,5,6").split(",")]:
             env = dict(os.environ, FDTD2D_FAST_CFG=str(cfg))
             subprocess.run([sys.executable, __file__, str(cfg)], env=env)
