@@ -12,6 +12,7 @@
 
 #include "../../include/fdtd2d.h"
 #include "common.cuh"
+#include "tile_edge.cuh"
 #include "tile_fast.cuh"
 #include "tile_tma.cuh"
 #include "tile_generic.cuh"
@@ -59,7 +60,7 @@ struct FastCfg {
     bool tma;  // persistent TMA-fed kernel (tile_tma.cuh) instead of the plain-load kernel (tile_fast.cuh)
 };
 static const FastCfg kFastCfgs[] = {{4, 8, false}, {4, 12, false}, {4, 16, false}, {6, 8, false},
-                                    {8, 8, false}, {2, 16, false}, {4, 16, true}};
+                                    {8, 8, false}, {2, 16, false}, {4, 16, true},  {4, 16, true}};
 constexpr int N_FAST_CFG = sizeof(kFastCfgs) / sizeof(kFastCfgs[0]);
 constexpr int DEFAULT_FAST_CFG = 6;  // persistent TMA-fed 64 x 128 tiles: best measured (profiles/)
 constexpr int MIN_LAST = 8;  // smallest core extent allowed for the last tile row/column (ring safety)
@@ -286,18 +287,31 @@ static int build_tma_maps(fdtd2d_sim* s, int box_rows) {
     return 0;
 }
 
-template <int MR, int NW> static int launch_tma_t(fdtd2d_sim* s, const PassParams<float>& p, int n_tiles) {
+template <int MR, int NW, bool PAIR> static int launch_tma_t(fdtd2d_sim* s, const PassParams<float>& p, int n_tiles) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[s->device % MAX_DEVICES];
-    const size_t smem = (size_t)(5 * MR * NW * FAST_TW + 2 * NW * FAST_TW) * sizeof(float);
+    const size_t smem = (size_t)(5 * MR * NW * FAST_TW + (PAIR ? 4 : 2) * NW * FAST_TW) * sizeof(float);
     if (!done) {
-        CUDA_TRY(cudaFuncSetAttribute(tile_tma_kernel<MR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(tile_tma_kernel<MR, NW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
     }
     if (!s->sm_count) CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
     if (int rc = build_tma_maps(s, MR * NW)) return rc;
     const int grid = std::min(n_tiles, s->sm_count);
-    tile_tma_kernel<MR, NW><<<grid, NW * 32, smem, s->stream>>>(s->tma_maps[s->cur], p, n_tiles);
+    tile_tma_kernel<MR, NW, PAIR><<<grid, NW * 32, smem, s->stream>>>(s->tma_maps[s->cur], p, n_tiles);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <int MR, int NW> static int launch_edge_t(int dev, const PassParams<float>& p, int n_tiles, cudaStream_t st) {
+    static bool done_[MAX_DEVICES] = {};
+    bool& done = done_[dev % MAX_DEVICES];
+    const size_t smem = (size_t)(2 * MR * NW * FAST_TW + 2 * NW * FAST_TW) * sizeof(float);
+    if (!done) {
+        CUDA_TRY(cudaFuncSetAttribute(tile_edge_kernel<MR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        done = true;
+    }
+    tile_edge_kernel<MR, NW><<<(unsigned)n_tiles, NW * 32, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -453,11 +467,23 @@ static int launch_hybrid(fdtd2d_sim* s, int k) {
     if (pl.n_generic) {
         p.tile_list = pl.d_generic;
         int rc;
-        switch (fc.MR * fc.NW) {
-            case 32: rc = launch_generic_list_t<32>(s->device, p, pl.n_generic, gstream); break;
-            case 48: rc = launch_generic_list_t<48>(s->device, p, pl.n_generic, gstream); break;
-            case 64: rc = launch_generic_list_t<64>(s->device, p, pl.n_generic, gstream); break;
-            default: return fail(FDTD2D_EINVAL, "no generic kernel for %d-row tiles", fc.MR * fc.NW);
+        if (s->variant == 3) {  // debugging aid: shared-memory generic kernel for the non-plain tiles
+            switch (fc.MR * fc.NW) {
+                case 32: rc = launch_generic_list_t<32>(s->device, p, pl.n_generic, gstream); break;
+                case 48: rc = launch_generic_list_t<48>(s->device, p, pl.n_generic, gstream); break;
+                case 64: rc = launch_generic_list_t<64>(s->device, p, pl.n_generic, gstream); break;
+                default: return fail(FDTD2D_EINVAL, "no generic kernel for %d-row tiles", fc.MR * fc.NW);
+            }
+        } else if (fc.MR == 4 && fc.NW == 16) {
+            rc = launch_edge_t<4, 16>(s->device, p, pl.n_generic, gstream);
+        } else if (fc.MR == 6 && fc.NW == 8) {
+            rc = launch_edge_t<6, 8>(s->device, p, pl.n_generic, gstream);
+        } else if (fc.MR == 4 && fc.NW == 12) {
+            rc = launch_edge_t<4, 12>(s->device, p, pl.n_generic, gstream);
+        } else if (fc.MR == 4 && fc.NW == 8) {
+            rc = launch_edge_t<4, 8>(s->device, p, pl.n_generic, gstream);
+        } else {
+            return fail(FDTD2D_EINVAL, "no edge kernel for this tile shape");
         }
         if (rc) return rc;
         s->launches += 1;
@@ -472,7 +498,8 @@ static int launch_hybrid(fdtd2d_sim* s, int k) {
             case 3: rc = launch_fast_t<6, 8, 2>(s, p, pl.n_fast); break;
             case 4: rc = launch_fast_t<8, 8, 1>(s, p, pl.n_fast); break;
             case 5: rc = launch_fast_t<2, 16, 2>(s, p, pl.n_fast); break;
-            case 6: rc = launch_tma_t<4, 16>(s, p, pl.n_fast); break;
+            case 6: rc = launch_tma_t<4, 16, false>(s, p, pl.n_fast); break;
+            case 7: rc = launch_tma_t<4, 16, true>(s, p, pl.n_fast); break;
             default: return fail(FDTD2D_EINVAL, "bad fast config");
         }
         if (rc) return rc;
@@ -969,7 +996,7 @@ int fdtd2d_set_step_index(fdtd2d_sim* s, int64_t step) {
 }
 
 int fdtd2d_set_kernel_variant(fdtd2d_sim* s, int variant) {
-    REQUIRE(s && variant >= 0 && variant <= 2, "bad argument");
+    REQUIRE(s && variant >= 0 && variant <= 3, "bad argument");
     s->variant = variant;
     return 0;
 }

@@ -22,12 +22,18 @@
 // k+6 cells of a ring zone that lies in its core, so that case never arises.
 #pragma once
 #include "common.cuh"
+#include "ring_ops.cuh"
 
 namespace fdtd2d {
 
 template <typename T> __device__ __forceinline__ typename Vec<T>::type zero_vec();
 template <> __device__ __forceinline__ float4 zero_vec<float>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 template <> __device__ __forceinline__ double2 zero_vec<double>() { return make_double2(0.0, 0.0); }
+
+__device__ __forceinline__ void unpack(const float4& v, float* a) { a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w; }
+__device__ __forceinline__ void unpack(const double2& v, double* a) { a[0] = v.x, a[1] = v.y; }
+__device__ __forceinline__ float4 pack(const float* a) { return make_float4(a[0], a[1], a[2], a[3]); }
+__device__ __forceinline__ double2 pack(const double* a) { return make_double2(a[0], a[1]); }
 
 template <typename T, int TH, int TW, int NT>
 __global__ void __launch_bounds__(NT) tile_generic_kernel(const PassParams<T> p) {
@@ -81,136 +87,86 @@ __global__ void __launch_bounds__(NT) tile_generic_kernel(const PassParams<T> p)
     }
     __syncthreads();
 
-    const T coef = p.mur[b];
-    const bool touchL = lc0 < RING;
-    const bool touchR = lc0 + TW > C - RING;
-    const bool touchT = gr0 < RING;
-    const bool touchB = gr0 + TH > Rg - RING;
-    const int src_lo = p.src_range ? p.src_range[b] : 0;
-    const int src_hi = p.src_range ? p.src_range[b + 1] : 0;
-    const int prb_lo = p.probe_range ? p.probe_range[b] : 0;
-    const int prb_hi = p.probe_range ? p.probe_range[b + 1] : 0;
+    TileCtx<T> tc;
+    tc.gr0 = gr0, tc.lc0 = lc0, tc.Rg = Rg, tc.C = C, tc.k = k;
+    tc.coef = p.mur[b];
+    tc.touchL = lc0 < RING;
+    tc.touchR = lc0 + TW > C - RING;
+    tc.touchT = gr0 < RING;
+    tc.touchB = gr0 + TH > Rg - RING;
+    tc.src_lo = p.src_range ? p.src_range[b] : 0;
+    tc.src_hi = p.src_range ? p.src_range[b + 1] : 0;
+    tc.prb_lo = p.probe_range ? p.probe_range[b] : 0;
+    tc.prb_hi = p.probe_range ? p.probe_range[b + 1] : 0;
 
     T* cur = sEa;  // Ez at the start of the step (S0)
     T* nxt = sEb;  // Ez being built (S1..S4)
 
     for (int s = 0; s < k; ++s) {
         // ---- H half-step, main.py:69-74 : rows 0..R-2, cols 0..C-2 -----------------------------
+        // One vector (VN cells of one row) per thread and iteration; row predicates are uniform per
+        // vector, column predicates select between the updated and the old value per element.
         if (p.phases & 1) {
-            for (int idx = tid; idx < N; idx += NT) {
-                const int li = idx / TW, lj = idx - li * TW;
-                const int gi = gr0 + li, gj = lc0 + lj;
-                if (li < TH - 1 && lj < TW - 1 && gi >= 0 && gi <= Rg - 2 && gj >= 0 && gj <= C - 2) {
-                    const T e = cur[idx];
-                    const T c = sCh[idx];
-                    sHx[idx] = sub_rn(sHx[idx], mul_rn(c, sub_rn(cur[idx + TW], e)));
-                    sHy[idx] = add_rn(sHy[idx], mul_rn(c, sub_rn(cur[idx + 1], e)));
+            for (int v = tid; v < N / VN; v += NT) {
+                const int li = v / TWV, lj0 = (v - li * TWV) * VN;
+                const int gi = gr0 + li;
+                if (li >= TH - 1 || gi < 0 || gi > Rg - 2) continue;
+                const int o = li * TW + lj0;
+                T e[VN + 1], dn[VN], c[VN], hx[VN], hy[VN];
+                unpack(*reinterpret_cast<const V*>(cur + o), e);
+                unpack(*reinterpret_cast<const V*>(cur + o + TW), dn);
+                unpack(*reinterpret_cast<const V*>(sCh + o), c);
+                unpack(*reinterpret_cast<const V*>(sHx + o), hx);
+                unpack(*reinterpret_cast<const V*>(sHy + o), hy);
+                e[VN] = (lj0 + VN < TW) ? cur[o + VN] : e[VN - 1];
+#pragma unroll
+                for (int q = 0; q < VN; ++q) {
+                    const int lj = lj0 + q, gj = lc0 + lj;
+                    const bool ok = (lj < TW - 1) & (gj >= 0) & (gj <= C - 2);
+                    const T nx = sub_rn(hx[q], mul_rn(c[q], sub_rn(dn[q], e[q])));
+                    const T ny = add_rn(hy[q], mul_rn(c[q], sub_rn(e[q + 1], e[q])));
+                    hx[q] = ok ? nx : hx[q];
+                    hy[q] = ok ? ny : hy[q];
                 }
+                *reinterpret_cast<V*>(sHx + o) = pack(hx);
+                *reinterpret_cast<V*>(sHy + o) = pack(hy);
             }
             __syncthreads();
         }
         if (p.phases & 2) {
             // ---- S1: interior Ez update, main.py:21-27 : rows 1..R-2, cols 1..C-2 ---------------
-            for (int idx = tid; idx < N; idx += NT) {
-                const int li = idx / TW, lj = idx - li * TW;
-                const int gi = gr0 + li, gj = lc0 + lj;
-                T v = cur[idx];
-                if (li >= 1 && lj >= 1 && gi >= 1 && gi <= Rg - 2 && gj >= 1 && gj <= C - 2) {
-                    const T dhy = sub_rn(sHy[idx], sHy[idx - 1]);
-                    const T dhx = sub_rn(sHx[idx], sHx[idx - TW]);
-                    v = add_rn(v, mul_rn(sub_rn(dhy, dhx), sCe[idx]));
+            for (int v = tid; v < N / VN; v += NT) {
+                const int li = v / TWV, lj0 = (v - li * TWV) * VN;
+                const int gi = gr0 + li;
+                const int o = li * TW + lj0;
+                T e[VN];
+                unpack(*reinterpret_cast<const V*>(cur + o), e);
+                if (li >= 1 && gi >= 1 && gi <= Rg - 2) {
+                    T hy[VN + 1], hx[VN], up[VN], c[VN];
+                    unpack(*reinterpret_cast<const V*>(sHy + o), hy + 1);
+                    unpack(*reinterpret_cast<const V*>(sHx + o), hx);
+                    unpack(*reinterpret_cast<const V*>(sHx + o - TW), up);
+                    unpack(*reinterpret_cast<const V*>(sCe + o), c);
+                    hy[0] = (lj0 > 0) ? sHy[o - 1] : hy[1];
+#pragma unroll
+                    for (int q = 0; q < VN; ++q) {
+                        const int lj = lj0 + q, gj = lc0 + lj;
+                        const bool ok = (lj >= 1) & (gj >= 1) & (gj <= C - 2);
+                        const T curl = sub_rn(sub_rn(hy[q + 1], hy[q]), sub_rn(hx[q], up[q]));
+                        const T nv = add_rn(e[q], mul_rn(curl, c[q]));
+                        e[q] = ok ? nv : e[q];
+                    }
                 }
-                nxt[idx] = v;
+                *reinterpret_cast<V*>(nxt + o) = pack(e);
             }
             __syncthreads();
-            // ---- S2: Mur left/right, main.py:33-41. One thread per (row, side) runs the
-            // reference's five column updates in the reference's order (outermost first), so every
-            // read of the inward neighbour sees the value S1 left there. -----------------------
-            if (touchL || touchR) {
-                for (int w = tid; w < 2 * TH; w += NT) {
-                    const int side = w / TH, li = w - side * TH;
-                    const int gi = gr0 + li;
-                    if (gi < 1 || gi > Rg - 2) continue;
-                    T* n1 = nxt + li * TW;
-                    const T* s0 = cur + li * TW;
-#pragma unroll
-                    for (int q = 0; q < RING; ++q) {
-                        const int gj = side ? C - 1 - q : q;
-                        const int lj = gj - lc0;
-                        const int ln = side ? lj - 1 : lj + 1;
-                        if (lj < 0 || lj >= TW || ln < 0 || ln >= TW) continue;
-                        n1[lj] = add_rn(s0[ln], mul_rn(coef, sub_rn(n1[ln], s0[lj])));
-                    }
-                }
-                __syncthreads();
-            }
-            // ---- S3: Mur top/bottom, main.py:43-51. One thread per (column, side). -------------
-            if (touchT || touchB) {
-                for (int w = tid; w < 2 * TW; w += NT) {
-                    const int side = w / TW, lj = w - side * TW;
-                    const int gj = lc0 + lj;
-                    if (gj < 1 || gj > C - 2) continue;
-#pragma unroll
-                    for (int q = 0; q < RING; ++q) {
-                        const int gi = side ? Rg - 1 - q : q;
-                        const int li = gi - gr0;
-                        const int ln = side ? li - 1 : li + 1;
-                        if (li < 0 || li >= TH || ln < 0 || ln >= TH) continue;
-                        const int o = li * TW + lj, on = ln * TW + lj;
-                        nxt[o] = add_rn(cur[on], mul_rn(coef, sub_rn(nxt[on], cur[o])));
-                    }
-                }
-                __syncthreads();
-            }
-            // ---- S4: 5x5 corner means, main.py:54-61. One thread per corner, reference order. ---
-            if ((touchL || touchR) && (touchT || touchB)) {
-                if (tid < 4) {
-                    const bool top = tid < 2, left = (tid & 1) == 0;
-                    for (int a = 0; a < RING; ++a) {
-                        const int gi = top ? a : Rg - 1 - a;
-                        const int li = gi - gr0, lin = top ? li + 1 : li - 1;
-                        if (li < 0 || li >= TH || lin < 0 || lin >= TH) continue;
-                        for (int c = 0; c < RING; ++c) {
-                            const int gj = left ? c : C - 1 - c;
-                            const int lj = gj - lc0, ljn = left ? lj + 1 : lj - 1;
-                            if (lj < 0 || lj >= TW || ljn < 0 || ljn >= TW) continue;
-                            const T sum = add_rn(nxt[li * TW + ljn], nxt[lin * TW + lj]);
-                            nxt[li * TW + lj] = mul_rn(sum, (T)0.5);  // == sum / 2 exactly
-                        }
-                    }
-                }
-                __syncthreads();
-            }
+            ring_stages<T, TH, TW, NT>(cur, nxt, tc, tid);
             T* t = cur;
             cur = nxt;
             nxt = t;
         }
         if (p.phases & 4) {
-            const long long step = p.step0 + s;
-            // ---- source add, fdtd.py:34 -------------------------------------------------------
-            if (src_hi > src_lo) {
-                if (step < p.amp_steps) {
-                    for (int q = src_lo + tid; q < src_hi; q += NT) {
-                        const Cell sc = p.src[q];
-                        const int li = sc.row - gr0, lj = sc.col - lc0;
-                        if (li >= 0 && li < TH && lj >= 0 && lj < TW) {
-                            const double a = p.amp[(long long)sc.wave * p.amp_steps + step];
-                            cur[li * TW + lj] = add_source(cur[li * TW + lj], a);
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-            // ---- probes: recorded by the tile whose core holds the cell, on the owning slab ---
-            if (prb_hi > prb_lo && step < p.trace_cap) {
-                for (int q = prb_lo + tid; q < prb_hi; q += NT) {
-                    const Cell pc = p.probes[q];
-                    const int li = pc.row - gr0, lj = pc.col - lc0;
-                    if (pc.row >= p.own_begin && pc.row < p.own_end && li >= k && li < k + p.CH && lj >= p.hx &&
-                        lj < p.hx + p.CW)
-                        p.trace[step * p.n_probe + q] = cur[li * TW + lj];
-                }
-            }
+            source_and_probes<T, TH, TW, NT>(cur, p, tc, p.step0 + s, tid);
         }
     }
 

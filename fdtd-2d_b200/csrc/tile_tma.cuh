@@ -36,14 +36,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
+    uint32_t ok, spins = 0;
     do {
+        if (++spins > (1u << 26)) __trap();  // never hang the GPU on a protocol bug
         asm volatile(
             "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
     } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
     asm volatile(
@@ -52,16 +56,21 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         : "memory");
 }
 
-template <int MR, int NW>
+// PAIR = true replaces the two CTA-wide barriers per leapfrog step by point-to-point mbarriers between
+// neighbouring warps (warp w only ever needs one row from warp w+1 and one from warp w-1), with the
+// exchanged rows double-buffered by step parity, so the 16 warps of the CTA drift apart and fill each
+// other's pipeline bubbles instead of draining the SM twice per step.
+template <int MR, int NW, bool PAIR>
 __global__ void __launch_bounds__(NW * 32, 1)
     tile_tma_kernel(const __grid_constant__ TmaMaps maps, const PassParams<float> p, const int n_tiles) {
-    constexpr int TW = 128, TH = MR * NW, N = TH * TW;
+    constexpr int TW = 128, TH = MR * NW, N = TH * TW, XB = PAIR ? 2 : 1;
     constexpr uint32_t STAGE_BYTES = 5u * N * sizeof(float);
     extern __shared__ __align__(128) unsigned char smem_tma[];
     float* stage = reinterpret_cast<float*>(smem_tma);  // [5][TH][TW]: Ez, Hx, Hy, ce, ch of the NEXT tile
-    float* sEz = stage + 5 * N;                         // [NW][TW] first Ez row of every warp
-    float* sHx = sEz + NW * TW;                         // [NW][TW] last Hx row of every warp
+    float* sEz = stage + 5 * N;                         // [XB][NW][TW] first Ez row of every warp
+    float* sHx = sEz + XB * NW * TW;                    // [XB][NW][TW] last Hx row of every warp
     __shared__ __align__(8) uint64_t full_bar;
+    __shared__ __align__(8) uint64_t bar_e[NW], bar_h[NW];  // PAIR: "row of warp w is published"
 
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const int li0 = w * MR, lj = 4 * l;
@@ -83,8 +92,14 @@ __global__ void __launch_bounds__(NW * 32, 1)
 
     if (tid == 0) {
         mbar_init(&full_bar, 1);
+        if (PAIR)
+            for (int i = 0; i < NW; ++i) {
+                mbar_init(&bar_e[i], 1);
+                mbar_init(&bar_h[i], 1);
+            }
         fence_mbar_init();
     }
+    uint32_t g = 0;  // leapfrog steps done by this CTA so far (phase counter of the pair barriers)
     __syncthreads();
     int t = blockIdx.x;
     if (tid == 0 && t < n_tiles) issue(t);
@@ -123,10 +138,17 @@ __global__ void __launch_bounds__(NW * 32, 1)
         }
 
         // ---- k leapfrog steps out of registers ---------------------------------------------
-        for (int s = 0; s < k; ++s) {
-            *reinterpret_cast<float4*>(sEz + w * TW + lj) = make_float4(e[0][0], e[0][1], e[0][2], e[0][3]);
-            __syncthreads();
-            const float4 eb = *reinterpret_cast<const float4*>(sEz + wb);
+        for (int s = 0; s < k; ++s, ++g) {
+            const int xo = PAIR ? (int)(g & 1u) * NW * TW : 0;
+            *reinterpret_cast<float4*>(sEz + xo + w * TW + lj) = make_float4(e[0][0], e[0][1], e[0][2], e[0][3]);
+            if (PAIR) {
+                __syncwarp();
+                if (l == 0) mbar_arrive(&bar_e[w]);
+                if (w + 1 < NW) mbar_wait(&bar_e[w + 1], g & 1u);
+            } else {
+                __syncthreads();
+            }
+            const float4 eb = *reinterpret_cast<const float4*>(sEz + xo + wb);
             const float below[4] = {eb.x, eb.y, eb.z, eb.w};
 #pragma unroll
             for (int r = 0; r < MR; ++r) {  // H half-step, main.py:69-74
@@ -139,10 +161,16 @@ __global__ void __launch_bounds__(NW * 32, 1)
                     hy[r][q] = add_rn(hy[r][q], mul_rn(ch[r][q], sub_rn(right, e[r][q])));
                 }
             }
-            *reinterpret_cast<float4*>(sHx + w * TW + lj) =
+            *reinterpret_cast<float4*>(sHx + xo + w * TW + lj) =
                 make_float4(hx[MR - 1][0], hx[MR - 1][1], hx[MR - 1][2], hx[MR - 1][3]);
-            __syncthreads();
-            const float4 ha = *reinterpret_cast<const float4*>(sHx + wa);
+            if (PAIR) {
+                __syncwarp();
+                if (l == 0) mbar_arrive(&bar_h[w]);
+                if (w > 0) mbar_wait(&bar_h[w - 1], g & 1u);
+            } else {
+                __syncthreads();
+            }
+            const float4 ha = *reinterpret_cast<const float4*>(sHx + xo + wa);
             const float above[4] = {ha.x, ha.y, ha.z, ha.w};
 #pragma unroll
             for (int r = 0; r < MR; ++r) {  // Ez update, main.py:21-27

@@ -125,7 +125,8 @@ int fdtd2d_step_phases(fdtd2d_sim* s, int phases);
 int fdtd2d_get_step_index(const fdtd2d_sim* s, int64_t* step);
 int fdtd2d_set_step_index(fdtd2d_sim* s, int64_t step);
 /* Select the tile kernel: 0 = automatic, 1 = generic shared-memory tiles only,
- * 2 = register-resident fast tiles for plain interior tiles + generic for edge/source/probe tiles. */
+ * 2 = register-resident tiles everywhere (TMA-fed plain tiles + edge-capable tiles; fp32 default),
+ * 3 = register-resident plain tiles + shared-memory generic kernel for edge/source/probe tiles. */
 int fdtd2d_set_kernel_variant(fdtd2d_sim* s, int variant);
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 int fdtd2d_launch_count(const fdtd2d_sim* s, int64_t* launches);
