@@ -51,6 +51,9 @@ _SIGNATURES = {
     "fdtd2d_set_kernel_variant": ([_vp, _i], _i),
     "fdtd2d_launch_count": ([_vp, ctypes.POINTER(_i64)], _i),
     "fdtd2d_halo_block": ([_vp, _i, _i, _pp, _pp, ctypes.POINTER(_sz)], _i),
+    "fdtd2d_halo_block_next": ([_vp, _i, _i, _pp, _pp, ctypes.POINTER(_sz)], _i),
+    "fdtd2d_pass_begin": ([_vp, _i], _i),
+    "fdtd2d_pass_end": ([_vp], _i),
     "fdtd2d_device_field": ([_vp, _i, _pp], _i),
 }
 

@@ -75,6 +75,7 @@ struct PassPlan {
     bool valid = false;
     TilePlan tp;
     int n_generic = 0, n_fast = 0;
+    int n_generic_band = 0, n_fast_band = 0;  // leading entries of each list: tiles that produce halo rows / touch ghost rows
     int* d_generic = nullptr;
     int* d_fast = nullptr;
 };
@@ -116,6 +117,7 @@ struct fdtd2d_sim {
     TmaMaps tma_maps[2];               // tensor maps with field set 0 / 1 as the pass input
     int tma_box_rows = 0;              // box height the maps were encoded for (0 = not built)
     int sm_count = 0;
+    int open_pass_k = 0;  // > 0 between fdtd2d_pass_begin and fdtd2d_pass_end
 };
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
@@ -416,18 +418,33 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
     for (const Cell& c : s->h_src)
         mark(c.grid, c.row - s->row0, c.col, k, F_TH - k - tp.CH, tp.hx, FAST_TW - tp.hx - tp.CW);
     for (const Cell& c : s->h_probe) mark(c.grid, c.row - s->row0, c.col, 0, 0, 0, 0);
-    std::vector<int> gen, fast;
+    // slab handles: tile rows whose core holds rows that are sent to a neighbour, or ghost rows, form the
+    // "band" that fdtd2d_pass_begin launches first so the halo exchange can overlap the rest of the pass
+    const int own_first = s->row_begin - s->row0, own_last = s->row_end - s->row0;
+    auto in_band = [&](int ty) {
+        const int r0 = ty * tp.CH, r1 = std::min(s->Rl, r0 + tp.CH);
+        if (s->has_top_nb && r0 < own_first + s->halo) return true;
+        if (s->has_bot_nb && r1 > own_last - s->halo) return true;
+        return false;
+    };
+    std::vector<int> gen, fast, gen_rest, fast_rest;
     for (int b = 0; b < s->batch; ++b)
         for (int ty = 0; ty < tp.tiles_y; ++ty) {
             const int lr0 = ty * tp.CH - k, gr0 = lr0 + s->row0;
             const bool rows_plain = lr0 >= 0 && lr0 + F_TH <= s->Rl && gr0 >= RING && gr0 + F_TH <= s->Rg - RING;
+            const bool band = in_band(ty);
             for (int tx = 0; tx < tp.tiles_x; ++tx) {
                 const int lc0 = tx * tp.CW - tp.hx;
                 const bool cols_plain = lc0 >= RING && lc0 + FAST_TW <= s->C - RING;
                 const int id = b * per_grid + ty * tp.tiles_x + tx;
-                (rows_plain && cols_plain && !special[id] ? fast : gen).push_back(id);
+                const bool plain = rows_plain && cols_plain && !special[id];
+                (plain ? (band ? fast : fast_rest) : (band ? gen : gen_rest)).push_back(id);
             }
         }
+    pl->n_generic_band = (int)gen.size();
+    pl->n_fast_band = (int)fast.size();
+    gen.insert(gen.end(), gen_rest.begin(), gen_rest.end());
+    fast.insert(fast.end(), fast_rest.begin(), fast_rest.end());
     pl->n_generic = (int)gen.size();
     pl->n_fast = (int)fast.size();
     if (pl->n_generic) {
@@ -445,13 +462,17 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
 
 // fp32 hybrid pass: plain tiles on the register-resident kernel, the rest on the generic kernel
 // (same tile grid), the two launches overlapped on two streams.
-static int launch_hybrid(fdtd2d_sim* s, int k) {
+// part: 0 = every tile, 1 = only the band (halo-producing) tiles, 2 = everything but the band
+static int launch_hybrid(fdtd2d_sim* s, int k, int part) {
     PassPlan& pl = s->hybrid[k];
     if (!pl.valid)
         if (int rc = classify_tiles(s, k, &pl)) return rc;
     PassParams<float> p;
     fill_params(s, pl.tp, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC, &p);
-    const bool both = pl.n_generic > 0 && pl.n_fast > 0;
+    const int g_off = part == 2 ? pl.n_generic_band : 0, f_off = part == 2 ? pl.n_fast_band : 0;
+    const int n_gen = part == 1 ? pl.n_generic_band : pl.n_generic - g_off;
+    const int n_fst = part == 1 ? pl.n_fast_band : pl.n_fast - f_off;
+    const bool both = n_gen > 0 && n_fst > 0;
     cudaStream_t gstream = s->stream;
     if (both) {
         if (!s->side_stream) {
@@ -464,42 +485,42 @@ static int launch_hybrid(fdtd2d_sim* s, int k) {
         gstream = s->side_stream;
     }
     const FastCfg fc = kFastCfgs[s->fast_cfg];
-    if (pl.n_generic) {
-        p.tile_list = pl.d_generic;
+    if (n_gen) {
+        p.tile_list = pl.d_generic + g_off;
         int rc;
         if (s->variant == 3) {  // debugging aid: shared-memory generic kernel for the non-plain tiles
             switch (fc.MR * fc.NW) {
-                case 32: rc = launch_generic_list_t<32>(s->device, p, pl.n_generic, gstream); break;
-                case 48: rc = launch_generic_list_t<48>(s->device, p, pl.n_generic, gstream); break;
-                case 64: rc = launch_generic_list_t<64>(s->device, p, pl.n_generic, gstream); break;
+                case 32: rc = launch_generic_list_t<32>(s->device, p, n_gen, gstream); break;
+                case 48: rc = launch_generic_list_t<48>(s->device, p, n_gen, gstream); break;
+                case 64: rc = launch_generic_list_t<64>(s->device, p, n_gen, gstream); break;
                 default: return fail(FDTD2D_EINVAL, "no generic kernel for %d-row tiles", fc.MR * fc.NW);
             }
         } else if (fc.MR == 4 && fc.NW == 16) {
-            rc = launch_edge_t<4, 16>(s->device, p, pl.n_generic, gstream);
+            rc = launch_edge_t<4, 16>(s->device, p, n_gen, gstream);
         } else if (fc.MR == 6 && fc.NW == 8) {
-            rc = launch_edge_t<6, 8>(s->device, p, pl.n_generic, gstream);
+            rc = launch_edge_t<6, 8>(s->device, p, n_gen, gstream);
         } else if (fc.MR == 4 && fc.NW == 12) {
-            rc = launch_edge_t<4, 12>(s->device, p, pl.n_generic, gstream);
+            rc = launch_edge_t<4, 12>(s->device, p, n_gen, gstream);
         } else if (fc.MR == 4 && fc.NW == 8) {
-            rc = launch_edge_t<4, 8>(s->device, p, pl.n_generic, gstream);
+            rc = launch_edge_t<4, 8>(s->device, p, n_gen, gstream);
         } else {
             return fail(FDTD2D_EINVAL, "no edge kernel for this tile shape");
         }
         if (rc) return rc;
         s->launches += 1;
     }
-    if (pl.n_fast) {
-        p.tile_list = pl.d_fast;
+    if (n_fst) {
+        p.tile_list = pl.d_fast + f_off;
         int rc;
         switch (s->fast_cfg) {
-            case 0: rc = launch_fast_t<4, 8, 3>(s, p, pl.n_fast); break;
-            case 1: rc = launch_fast_t<4, 12, 2>(s, p, pl.n_fast); break;
-            case 2: rc = launch_fast_t<4, 16, 1>(s, p, pl.n_fast); break;
-            case 3: rc = launch_fast_t<6, 8, 2>(s, p, pl.n_fast); break;
-            case 4: rc = launch_fast_t<8, 8, 1>(s, p, pl.n_fast); break;
-            case 5: rc = launch_fast_t<2, 16, 2>(s, p, pl.n_fast); break;
-            case 6: rc = launch_tma_t<4, 16, false>(s, p, pl.n_fast); break;
-            case 7: rc = launch_tma_t<4, 16, true>(s, p, pl.n_fast); break;
+            case 0: rc = launch_fast_t<4, 8, 3>(s, p, n_fst); break;
+            case 1: rc = launch_fast_t<4, 12, 2>(s, p, n_fst); break;
+            case 2: rc = launch_fast_t<4, 16, 1>(s, p, n_fst); break;
+            case 3: rc = launch_fast_t<6, 8, 2>(s, p, n_fst); break;
+            case 4: rc = launch_fast_t<8, 8, 1>(s, p, n_fst); break;
+            case 5: rc = launch_fast_t<2, 16, 2>(s, p, n_fst); break;
+            case 6: rc = launch_tma_t<4, 16, false>(s, p, n_fst); break;
+            case 7: rc = launch_tma_t<4, 16, true>(s, p, n_fst); break;
             default: return fail(FDTD2D_EINVAL, "bad fast config");
         }
         if (rc) return rc;
@@ -512,13 +533,17 @@ static int launch_hybrid(fdtd2d_sim* s, int k) {
     return 0;
 }
 
-static int run_pass(fdtd2d_sim* s, int k, int phases) {
+static bool uses_hybrid(const fdtd2d_sim* s, int phases) {
     const int all = FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC;
+    return s->dtype == FDTD2D_F32 && phases == all && s->variant != 1;
+}
+
+static int run_pass(fdtd2d_sim* s, int k, int phases) {
     int rc;
     if (s->dtype == FDTD2D_F64)
         rc = launch_generic_all<double>(s, k, phases);
-    else if (phases == all && s->variant != 1)
-        rc = launch_hybrid(s, k);
+    else if (uses_hybrid(s, phases))
+        rc = launch_hybrid(s, k, 0);
     else
         rc = launch_generic_all<float>(s, k, phases);
     if (rc) return rc;
@@ -1007,11 +1032,11 @@ int fdtd2d_launch_count(const fdtd2d_sim* s, int64_t* launches) {
     return 0;
 }
 
-int fdtd2d_halo_block(fdtd2d_sim* s, int field, int side, void** send_ptr, void** recv_ptr, size_t* nbytes) {
+static int halo_block_impl(fdtd2d_sim* s, int state, int field, int side, void** send_ptr, void** recv_ptr, size_t* nbytes) {
     REQUIRE(s && field >= 0 && field < 3 && (side == 0 || side == 1), "bad argument");
     const bool has = side == 0 ? s->has_top_nb : s->has_bot_nb;
     REQUIRE(has, "no neighbour on that side");
-    char* base = static_cast<char*>(s->field[s->cur][field]);
+    char* base = static_cast<char*>(s->field[state][field]);
     const size_t row_bytes = s->pitch * s->esize;
     const int h = s->halo;
     // local rows: [0,h) top ghosts | owned | [Rl-h, Rl) bottom ghosts
@@ -1022,6 +1047,46 @@ int fdtd2d_halo_block(fdtd2d_sim* s, int field, int side, void** send_ptr, void*
     if (send_ptr) *send_ptr = base + (size_t)send_row * row_bytes;
     if (recv_ptr) *recv_ptr = base + (size_t)recv_row * row_bytes;
     if (nbytes) *nbytes = (size_t)h * row_bytes;
+    return 0;
+}
+
+int fdtd2d_halo_block(fdtd2d_sim* s, int field, int side, void** send_ptr, void** recv_ptr, size_t* nbytes) {
+    REQUIRE(s, "handle is null");
+    return halo_block_impl(s, s->cur, field, side, send_ptr, recv_ptr, nbytes);
+}
+
+int fdtd2d_halo_block_next(fdtd2d_sim* s, int field, int side, void** send_ptr, void** recv_ptr, size_t* nbytes) {
+    REQUIRE(s, "handle is null");
+    return halo_block_impl(s, s->cur ^ 1, field, side, send_ptr, recv_ptr, nbytes);
+}
+
+int fdtd2d_pass_begin(fdtd2d_sim* s, int k) {
+    REQUIRE(s, "handle is null");
+    REQUIRE(k >= 1 && k <= FDTD2D_MAX_K && k <= std::max(1, s->halo), "k must be in [1, min(halo, %d)]", FDTD2D_MAX_K);
+    REQUIRE(s->open_pass_k == 0, "a pass is already open");
+    if (!s->coeffs_set || !s->mur_set) return fail(FDTD2D_ESTATE, "coefficients / Mur coefficient not set");
+    if (int rc = use_device(s)) return rc;
+    const int all = FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC;
+    int rc;
+    if (uses_hybrid(s, all))
+        rc = launch_hybrid(s, k, 1);
+    else  // no band split for the generic-only paths: do the whole pass now
+        rc = s->dtype == FDTD2D_F64 ? launch_generic_all<double>(s, k, all) : launch_generic_all<float>(s, k, all);
+    if (rc) return rc;
+    s->open_pass_k = k;
+    return 0;
+}
+
+int fdtd2d_pass_end(fdtd2d_sim* s) {
+    REQUIRE(s, "handle is null");
+    REQUIRE(s->open_pass_k > 0, "no open pass");
+    if (int rc = use_device(s)) return rc;
+    const int k = s->open_pass_k;
+    if (uses_hybrid(s, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC))
+        if (int rc = launch_hybrid(s, k, 2)) return rc;
+    s->open_pass_k = 0;
+    s->cur ^= 1;
+    s->step += k;
     return 0;
 }
 

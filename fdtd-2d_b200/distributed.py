@@ -86,13 +86,21 @@ class SlabSimulation:
         self.row0, self.local_rows, self.hy_rows = self.sim.row0, self.sim.local_rows, self.sim._hy_rows
         self.tile_launch_count = 0
         self._tensors = {}
-        self._xchg = HaloExchange(rank, world, self._blocks, group) if world > 1 else None
+        self._xchg = self._xchg_next = self._comm = self._main = None
+        if world > 1:
+            import torch
+
+            self._xchg = HaloExchange(rank, world, self._blocks, group)
+            self._xchg_next = HaloExchange(rank, world, lambda f, side: self._blocks(f, side, True), group)
+            # kernels and the exchange are ordered through torch streams: adopt the current one
+            self.set_stream(torch.cuda.current_stream(device).cuda_stream)
+            self._comm = torch.cuda.Stream(device)
 
     # -- halo plumbing ------------------------------------------------------------------------
-    def _blocks(self, field, side):
+    def _blocks(self, field, side, next_state=False):
         import torch
 
-        sp, rp, nb = self.sim.halo_block(field, side)
+        sp, rp, nb = self.sim.halo_block(field, side, next_state)
         out = []
         for ptr in (sp, rp):
             t = self._tensors.get(ptr)
@@ -109,6 +117,11 @@ class SlabSimulation:
     # -- forwarding ---------------------------------------------------------------------------
     def set_stream(self, s):
         self.sim.set_stream(s)
+        if self.world > 1:
+            import torch
+
+            dev = self.sim.device
+            self._main = torch.cuda.default_stream(dev) if not s else torch.cuda.ExternalStream(s, dev)
 
     def set_kernel_variant(self, v):
         self.sim.set_kernel_variant(v)
@@ -170,8 +183,10 @@ class SlabSimulation:
         self.sim.close()
 
     # -- time stepping ------------------------------------------------------------------------
-    def step(self, n_steps: int, k: int = 0):
-        """n_steps leapfrog steps; with several slabs, halos are exchanged after every pass of k steps."""
+    def step(self, n_steps: int, k: int = 0, overlap: bool = True):
+        """n_steps leapfrog steps; with several slabs, halos are exchanged after every pass of k steps.
+        overlap=True starts each exchange as soon as the tiles that produce the boundary rows are done
+        (fdtd2d_pass_begin) and runs it on a side stream while the rest of the pass computes."""
         from . import DEFAULT_K
 
         k = k or DEFAULT_K
@@ -179,13 +194,25 @@ class SlabSimulation:
             self.sim.step(n_steps, k)
             self.tile_launch_count += -(-n_steps // k)
             return
+        import torch
+
         k = min(k, self.halo)
         left = n_steps
         while left > 0:
             kk = min(k, left)
-            self.sim.step(kk, kk)
+            if overlap:
+                self.sim.pass_begin(kk)
+                ev = torch.cuda.Event()
+                ev.record(self._main)
+                self._comm.wait_event(ev)
+                with torch.cuda.stream(self._comm):
+                    self._xchg_next.exchange()
+                self.sim.pass_end()
+                self._main.wait_stream(self._comm)
+            else:
+                self.sim.step(kk, kk)
+                self.exchange_halos()
             self.tile_launch_count += 1
-            self.exchange_halos()
             left -= kk
 
 

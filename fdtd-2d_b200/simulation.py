@@ -245,11 +245,21 @@ class Simulation:
         return v.value
 
     # ---- multi-GPU plumbing -----------------------------------------------------------------
-    def halo_block(self, field: int, side: int):
-        """(send_ptr, recv_ptr, nbytes) of the current state's halo block (see fdtd2d_halo_block)."""
+    def halo_block(self, field: int, side: int, next_state: bool = False):
+        """(send_ptr, recv_ptr, nbytes) of the halo block of the current state, or of the state an open
+        pass is writing (see fdtd2d_halo_block / fdtd2d_halo_block_next)."""
         sp, rp, nb = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t()
-        check(lib().fdtd2d_halo_block(self._h, field, side, ctypes.byref(sp), ctypes.byref(rp), ctypes.byref(nb)))
+        fn = lib().fdtd2d_halo_block_next if next_state else lib().fdtd2d_halo_block
+        check(fn(self._h, field, side, ctypes.byref(sp), ctypes.byref(rp), ctypes.byref(nb)))
         return sp.value, rp.value, nb.value
+
+    def pass_begin(self, k: int):
+        """Launch the halo-producing tiles of a k-step pass (see fdtd2d_pass_begin)."""
+        check(lib().fdtd2d_pass_begin(self._h, k))
+
+    def pass_end(self):
+        """Launch the rest of the open pass and make its result the current state."""
+        check(lib().fdtd2d_pass_end(self._h))
 
     def device_field(self, field: int) -> int:
         p = ctypes.c_void_p()

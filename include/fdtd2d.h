@@ -137,6 +137,14 @@ int fdtd2d_launch_count(const fdtd2d_sim* s, int64_t* launches);
  * smaller rows), 1 = bottom.  send_ptr = the `halo` owned rows next to that side; recv_ptr = the
  * ghost rows on that side.  Blocks are contiguous: halo * pitch elements. */
 int fdtd2d_halo_block(fdtd2d_sim* s, int field, int side, void** send_ptr, void** recv_ptr, size_t* nbytes);
+/* Split pass for overlapping the halo exchange with compute.  fdtd2d_pass_begin launches only the tiles
+ * whose stores produce the rows a neighbour needs (or touch ghost rows) for a k-step pass;
+ * fdtd2d_halo_block_next gives the halo blocks of the state being WRITTEN by that pass, so the caller
+ * can start the exchange on another stream as soon as pass_begin's work is done; fdtd2d_pass_end launches
+ * the remaining tiles, makes the new state current and advances the step index by k. */
+int fdtd2d_pass_begin(fdtd2d_sim* s, int k);
+int fdtd2d_pass_end(fdtd2d_sim* s);
+int fdtd2d_halo_block_next(fdtd2d_sim* s, int field, int side, void** send_ptr, void** recv_ptr, size_t* nbytes);
 /* Raw device pointer of a field of the current state (local_rows x pitch elements per grid). */
 int fdtd2d_device_field(fdtd2d_sim* s, int field, void** ptr);
 

@@ -26,7 +26,8 @@ def main():
     sim.set_point_source(R // 2, C // 2, 700, FC)
     sim.set_probes([(R // 2, C // 2 + 3), (R // 2 - 1, 10), (5, 5), (R - 3, C - 3)], 700)
     sim.step_index = 640
-    sim.step(n, k)
+    sim.step(n // 2, k, overlap=False)  # first half: exchange after each pass
+    sim.step(n - n // 2, k, overlap=True)  # second half: exchange overlapped with the rest of the pass
     torch.cuda.synchronize()
     Ez, Hx, Hy = sim.state()
     lo, cnt = sim.row_begin - sim.row0, sim.row_end - sim.row_begin
