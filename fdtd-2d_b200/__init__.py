@@ -12,14 +12,16 @@ from . import _lib
 DEFAULT_K = 8  # leapfrog steps per HBM round trip when the caller does not choose (fp32; fp64 uses 4)
 
 from ._lib import EXPORTED_SYMBOLS, Fdtd2dError
-from .api import (EPSILON0, MU0, grid_init, material_init, release_handles, ricker, sinusoidal, update_Ez,
+from .api import (EPSILON0, MU0, capture_snapshot, grid_init, material_init, release_handles, ricker, sinusoidal, update_Ez,
                   update_Hx_Hy)
 from .build import LIB_PATH, build
 from .distributed import HaloExchange, InProcessSlabs, SlabSimulation, slab_rows
+from .snapshot import eps_background, make_video_from_frames, seismic_lut
 from .simulation import (Simulation, courant_number, ricker_amplitude, sinusoidal_amplitude, source_table)
 
 __all__ = [
     "grid_init", "material_init", "update_Hx_Hy", "update_Ez", "ricker", "sinusoidal", "Simulation",
+    "capture_snapshot", "make_video_from_frames", "seismic_lut", "eps_background",
     "courant_number", "ricker_amplitude", "sinusoidal_amplitude", "source_table", "build", "LIB_PATH",
     "Fdtd2dError", "EXPORTED_SYMBOLS", "SlabSimulation", "InProcessSlabs", "HaloExchange", "slab_rows", "DEFAULT_K", "EPSILON0", "MU0", "release_handles",
 ]

@@ -54,6 +54,8 @@ _SIGNATURES = {
     "fdtd2d_halo_block_next": ([_vp, _i, _i, _pp, _pp, ctypes.POINTER(_sz)], _i),
     "fdtd2d_pass_begin": ([_vp, _i], _i),
     "fdtd2d_pass_end": ([_vp], _i),
+    "fdtd2d_set_snapshot_background": ([_vp, _vp, _vp], _i),
+    "fdtd2d_render_snapshot": ([_vp, _i, _d, _d, _vp], _i),
     "fdtd2d_device_field": ([_vp, _i, _pp], _i),
 }
 

@@ -102,6 +102,24 @@ def update_Ez(Ez, Hx, Hy, mu, eps, dt, dx):
     return Ez
 
 
+def capture_snapshot(Ez, eps, path, vmax=20, vmin=-20):
+    """Render Ez over the permittivity background and save it as an image (main.py:153-179).  The colour
+    mapping and blending run on the GPU; only the encoded image is written by PIL, as in the reference."""
+    from PIL import Image
+
+    from . import snapshot
+
+    Ez = np.asarray(Ez)
+    if Ez.dtype not in (np.float32, np.float64):
+        Ez = Ez.astype(np.float64)
+    sim = _sim_for(Ez, 0.0, 0.0)
+    R, C = Ez.shape
+    check_state = (np.zeros((R, C - 1), Ez.dtype), np.zeros((R - 1, C), Ez.dtype))
+    sim.set_state(Ez, *check_state)
+    snapshot.set_background(sim, eps)
+    Image.fromarray(snapshot.render(sim, vmax, vmin)).save(path)
+
+
 def release_handles():
     """Free the device buffers cached by the array-in/array-out shims."""
     while _handles:

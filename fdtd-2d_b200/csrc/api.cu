@@ -118,6 +118,9 @@ struct fdtd2d_sim {
     int tma_box_rows = 0;              // box height the maps were encoded for (0 = not built)
     int sm_count = 0;
     int open_pass_k = 0;  // > 0 between fdtd2d_pass_begin and fdtd2d_pass_end
+    unsigned char* d_gray = nullptr;  // snapshot background (Rl x C per grid)
+    unsigned char* d_rgb = nullptr;   // one rendered frame (Rl x C x 3)
+    double* d_lut = nullptr;          // 256 x 3 colormap
 };
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
@@ -203,6 +206,34 @@ __global__ void random_materials_kernel(T* ce, T* ch, T* mur, int Rl, int C, int
             const T u = (T)hash_uniform(seed, (uint32_t)b, 0u, 0u);
             const T eps = mul_rn(eps0, add_rn((T)1, mul_rn(span, u)));
             mur[b] = mur_from(mu0, eps, dt, dx);
+        }
+    }
+}
+
+// Field readout as an image (main.py:153-179): clip Ez to [vmin, vmax], normalise in the run dtype, look
+// up a 256-entry colormap, alpha-blend (alpha = 0.7) over the grayscale permittivity background in
+// float64 and truncate to uint8 -- the same operations, in the same order and precision, as the reference's
+// numpy expression, so the frame leaves the GPU as 3 bytes per cell.
+template <typename T>
+__global__ void snapshot_kernel(const T* ez, const unsigned char* gray, const double* lut, unsigned char* rgb, int Rl,
+                                int C, int pitch, T vmin, T vmax, T span) {
+    const long long n = (long long)Rl * C;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const double alpha = 0.7, one_minus = 1 - 0.7;
+    for (; i < n; i += stride) {
+        const int r = (int)(i / C), c = (int)(i - (long long)r * C);
+        T v = ez[(long long)r * pitch + c];
+        v = v < vmin ? vmin : (v > vmax ? vmax : v);  // np.clip
+        T x = mul_rn(div_rn(sub_rn(v, vmin), span), (T)256);
+        if (x == (T)256) x = (T)255;
+        int idx = (int)x;  // astype(int): truncation
+        idx = idx < 0 ? 0 : (idx > 255 ? 255 : idx);
+        const double bg = __dmul_rn(__ddiv_rn((double)gray[i], 255.0), one_minus);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const double f = __dmul_rn(__dadd_rn(__dmul_rn(lut[idx * 3 + ch], alpha), bg), 255.0);
+            rgb[i * 3 + ch] = (unsigned char)f;
         }
     }
 }
@@ -683,6 +714,9 @@ int fdtd2d_destroy(fdtd2d_sim* s) {
     cudaFree(s->d_probe);
     cudaFree(s->d_probe_range);
     cudaFree(s->d_trace);
+    cudaFree(s->d_gray);
+    cudaFree(s->d_rgb);
+    cudaFree(s->d_lut);
     free_plans(s);
     if (s->side_stream) cudaStreamDestroy(s->side_stream);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -1087,6 +1121,45 @@ int fdtd2d_pass_end(fdtd2d_sim* s) {
     s->open_pass_k = 0;
     s->cur ^= 1;
     s->step += k;
+    return 0;
+}
+
+int fdtd2d_set_snapshot_background(fdtd2d_sim* s, const unsigned char* gray, const double* lut) {
+    REQUIRE(s && gray && lut, "null argument");
+    if (int rc = use_device(s)) return rc;
+    const size_t n = (size_t)s->Rl * s->C * s->batch;
+    if (!s->d_gray) {
+        CUDA_TRY(cudaMalloc(&s->d_gray, n));
+        CUDA_TRY(cudaMalloc(&s->d_rgb, (size_t)s->Rl * s->C * 3));
+        CUDA_TRY(cudaMalloc(&s->d_lut, sizeof(double) * 768));
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->d_gray, gray, n, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->d_lut, lut, sizeof(double) * 768, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int fdtd2d_render_snapshot(fdtd2d_sim* s, int grid, double vmin, double vmax, unsigned char* out_rgb) {
+    REQUIRE(s && out_rgb && grid >= 0 && grid < s->batch, "bad argument");
+    if (!s->d_gray) return fail(FDTD2D_ESTATE, "snapshot background not set");
+    if (int rc = use_device(s)) return rc;
+    const long long n = (long long)s->Rl * s->C;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    const unsigned char* gray = s->d_gray + (size_t)grid * n;
+    if (s->dtype == FDTD2D_F32) {
+        const float* ez = static_cast<const float*>(s->field[s->cur][0]) + (size_t)grid * s->grid_elems;
+        // python-float bounds are weak scalars: the whole normalisation runs in float32 (NEP 50)
+        snapshot_kernel<float><<<blocks, 256, 0, s->stream>>>(ez, gray, s->d_lut, s->d_rgb, s->Rl, s->C, (int)s->pitch, (float)vmin,
+                                                             (float)vmax, (float)(vmax - vmin));
+    } else {
+        const double* ez = static_cast<const double*>(s->field[s->cur][0]) + (size_t)grid * s->grid_elems;
+        snapshot_kernel<double><<<blocks, 256, 0, s->stream>>>(ez, gray, s->d_lut, s->d_rgb, s->Rl, s->C, (int)s->pitch, vmin, vmax,
+                                                              vmax - vmin);
+    }
+    CUDA_TRY(cudaGetLastError());
+    s->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(out_rgb, s->d_rgb, (size_t)n * 3, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     return 0;
 }
 

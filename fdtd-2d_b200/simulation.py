@@ -244,6 +244,19 @@ class Simulation:
         check(lib().fdtd2d_launch_count(self._h, ctypes.byref(v)))
         return v.value
 
+    # ---- field readout as an image (capture_snapshot, main.py:153-179) ----------------------
+    def set_snapshot_background(self, eps):
+        """eps: the host permittivity map (as material_init returns it) behind the frames."""
+        from . import snapshot
+
+        snapshot.set_background(self, eps)
+
+    def render_snapshot(self, vmax=20, vmin=-20, grid: int = 0, out=None):
+        """uint8 (rows, cols, 3) RGB frame of the current Ez, colour-mapped and blended on the device."""
+        from . import snapshot
+
+        return snapshot.render(self, vmax, vmin, grid, out)
+
     # ---- multi-GPU plumbing -----------------------------------------------------------------
     def halo_block(self, field: int, side: int, next_state: bool = False):
         """(send_ptr, recv_ptr, nbytes) of the halo block of the current state, or of the state an open

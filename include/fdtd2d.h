@@ -131,6 +131,14 @@ int fdtd2d_set_kernel_variant(fdtd2d_sim* s, int variant);
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 int fdtd2d_launch_count(const fdtd2d_sim* s, int64_t* launches);
 
+/* ---- field readout as an image: replaces capture_snapshot (main.py:153-179) -------------------------- */
+/* gray: the uint8 permittivity background (main.py:157-165), (R_local, C) per grid, computed once on the
+ * host; lut: 256 x 3 float64 colormap entries (the reference uses matplotlib's "seismic").  */
+int fdtd2d_set_snapshot_background(fdtd2d_sim* s, const unsigned char* gray, const double* lut);
+/* Renders Ez of grid `grid` on the device (clip to [vmin, vmax], colormap, alpha 0.7 over the background,
+ * uint8) and copies the (R_local, C, 3) RGB frame to out_rgb.  Blocks until the frame is on the host. */
+int fdtd2d_render_snapshot(fdtd2d_sim* s, int grid, double vmin, double vmax, unsigned char* out_rgb);
+
 /* ---- multi-GPU y-slabs -------------------------------------------------------------- */
 /* Device pointers and byte counts of the halo blocks of the CURRENT state, for NCCL send/recv or
  * peer copies driven by the host layer.  field: 0 = Ez, 1 = Hx, 2 = Hy.  side: 0 = top (towards

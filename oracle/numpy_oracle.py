@@ -204,3 +204,46 @@ def courant(eps, mu, dt, dx):
     """Courant number as the driver computes it (fdtd.py:25-26)."""
     c = 1 / np.sqrt(eps.min() * mu.min())
     return (c * dt) / dx
+
+
+# -------------------------------------------------------------- readout ----
+def seismic_lut(n: int = 256):
+    """matplotlib's "seismic" lookup table rebuilt from its published construction: five anchor colours
+    (matplotlib/_cm.py `_seismic_data`) evenly spaced on [0, 1], `LinearSegmentedColormap.from_list`
+    -> `_create_lookup_table(N=256, gamma=1)`.  matplotlib itself is absent from the authoring
+    container, so this table is UNPINNED against the real library (tests compare when it is importable)."""
+    anchors = np.array([(0.0, 0.0, 0.3), (0.0, 0.0, 1.0), (1.0, 1.0, 1.0), (1.0, 0.0, 0.0), (0.5, 0.0, 0.0)])
+    x = np.linspace(0, 1, len(anchors)) * (n - 1)
+    xind = (n - 1) * np.linspace(0, 1, n)
+    ind = np.searchsorted(x, xind)[1:-1]
+    lut = np.empty((n, 3))
+    for ch in range(3):
+        y = anchors[:, ch]
+        distance = (xind[1:-1] - x[ind - 1]) / (x[ind] - x[ind - 1])
+        lut[:, ch] = np.concatenate([[y[0]], distance * (y[ind] - y[ind - 1]) + y[ind - 1], [y[-1]]])
+    return np.clip(lut, 0, 1)
+
+
+def snapshot_rgb(Ez, eps, vmax=20, vmin=-20, lut=None):
+    """The uint8 (R, C, 3) array `capture_snapshot` hands to PIL (main.py:153-177), with the colormap
+    call `cmap(X)` spelled out as matplotlib evaluates it for float input: index = int(X * 256), the
+    value 256 mapped to 255."""
+    lut = seismic_lut() if lut is None else lut
+    normed = np.clip(Ez, vmin, vmax)
+    eps_min = 8.85418e-12
+    eps_max = np.max(eps)
+    if eps_max == eps_min:
+        eps_gray = np.full_like(eps, 255, dtype=np.uint8)
+    else:
+        eps_normed = (eps - eps_min) / (eps_max - eps_min)
+        eps_gray = ((1 - eps_normed) * 127 + 128).astype(np.uint8)
+    background = np.stack([eps_gray] * 3, axis=-1)
+    X = (normed - vmin) / (vmax - vmin)
+    xa = np.array(X, copy=True)
+    xa *= 256
+    xa[xa == 256] = 255
+    idx = np.clip(xa.astype(int), 0, 255)
+    rgba = np.concatenate([lut[idx], np.ones(idx.shape + (1,))], axis=-1)
+    rgba[..., 3] = 0.7
+    rgb_float = rgba[..., :3] * rgba[..., 3:] + (background / 255) * (1 - rgba[..., 3:])
+    return (rgb_float * 255).astype(np.uint8)

@@ -117,3 +117,22 @@ def test_slab_partition():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         sizes = [b - a for a, b in spans]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_seismic_lut_construction():
+    from oracle import numpy_oracle as npo
+
+    lut = fd.seismic_lut()
+    assert lut.shape == (256, 3) and np.array_equal(lut, npo.seismic_lut())
+    assert np.allclose(lut[0], (0, 0, 0.3)) and np.allclose(lut[255], (0.5, 0, 0))
+    assert np.allclose(lut[127], (0.99215686, 0.99215686, 1.0), atol=1e-6)  # just below the white anchor
+    try:
+        import matplotlib
+
+        cm = matplotlib.colormaps["seismic"]
+        assert np.array_equal(cm(np.arange(256))[:, :3], lut)
+    except ImportError:
+        pass  # matplotlib is not installed here: the table is pinned only to its published construction
+    g = fd.eps_background(np.array([[8.85418e-12, 2 * 8.85418e-12], [10 * 8.85418e-12, 8.85418e-12]]))
+    assert g.dtype == np.uint8 and g[0, 0] == 255 and g[1, 0] == 128
+    assert (fd.eps_background(np.full((3, 3), 8.85418e-12)) == 255).all()
