@@ -140,8 +140,10 @@ static int plan_axis(int extent, int core_max, int quantum, int* core, int* tile
     return -1;
 }
 
-static int plan_tiles(const fdtd2d_sim* s, int k, int TH, TilePlan* tp) {
-    const int vn = (int)(16 / s->esize);
+static int plan_tiles(const fdtd2d_sim* s, int k, int TH, TilePlan* tp, int col_quantum = 0) {
+    // columns are handled in groups: the 16-byte vector of the generic kernel, 4 cells per lane in the
+    // register-resident kernels
+    const int vn = col_quantum ? col_quantum : (int)(16 / s->esize);
     tp->k = k;
     tp->hx = (int)round_up((size_t)k, (size_t)vn);
     if (plan_axis(s->Rl, TH - 2 * k, 1, &tp->CH, &tp->tiles_y) != 0 ||
@@ -336,17 +338,21 @@ template <int MR, int NW, bool PAIR> static int launch_tma_t(fdtd2d_sim* s, cons
     return 0;
 }
 
-template <int MR, int NW> static int launch_edge_t(int dev, const PassParams<float>& p, int n_tiles, cudaStream_t st) {
+template <typename T, int MR, int NW> static int launch_edge_tt(int dev, const PassParams<T>& p, int n_tiles, cudaStream_t st) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[dev % MAX_DEVICES];
-    const size_t smem = (size_t)(2 * MR * NW * FAST_TW + 2 * NW * FAST_TW) * sizeof(float);
+    const size_t smem = (size_t)(2 * MR * NW * FAST_TW + 2 * NW * FAST_TW) * sizeof(T);
     if (!done) {
-        CUDA_TRY(cudaFuncSetAttribute(tile_edge_kernel<MR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(tile_edge_kernel<T, MR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
     }
-    tile_edge_kernel<MR, NW><<<(unsigned)n_tiles, NW * 32, smem, st>>>(p);
+    tile_edge_kernel<T, MR, NW><<<(unsigned)n_tiles, NW * 32, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+template <int MR, int NW> static int launch_edge_t(int dev, const PassParams<float>& p, int n_tiles, cudaStream_t st) {
+    return launch_edge_tt<float, MR, NW>(dev, p, n_tiles, st);
 }
 
 template <int TH> static int launch_generic_list_t(int dev, const PassParams<float>& p, int n_tiles, cudaStream_t st) {
@@ -395,6 +401,20 @@ template <typename T> static void fill_params(const fdtd2d_sim* s, const TilePla
     p.trace_cap = s->trace_cap;
 }
 
+// fp64: every tile on the register-resident edge-capable kernel (2 rows x 4 columns per thread, 32 x 128 tiles)
+constexpr int D_MR = 2, D_NW = 16;
+static int launch_edge_all_f64(fdtd2d_sim* s, int k) {
+    TilePlan tp;
+    if (int rc = plan_tiles(s, k, D_MR * D_NW, &tp, 4)) return rc;
+    PassParams<double> p;
+    fill_params(s, tp, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC, &p);
+    const long long n_tiles = (long long)s->batch * tp.tiles_y * tp.tiles_x;
+    if (n_tiles > 0x7fffffffLL) return fail(FDTD2D_EINVAL, "too many tiles");
+    if (int rc = launch_edge_tt<double, D_MR, D_NW>(s->device, p, (int)n_tiles, s->stream)) return rc;
+    s->launches += 1;
+    return 0;
+}
+
 // Generic kernel over the whole tile grid (fp64, per-function passes, variant 1).
 template <typename T> static int launch_generic_all(fdtd2d_sim* s, int k, int phases) {
     TilePlan tp;
@@ -424,7 +444,7 @@ static void free_plans(fdtd2d_sim* s) {
 static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
     TilePlan& tp = pl->tp;
     const int F_TH = kFastCfgs[s->fast_cfg].MR * kFastCfgs[s->fast_cfg].NW;
-    if (int rc = plan_tiles(s, k, F_TH, &tp)) return rc;
+    if (int rc = plan_tiles(s, k, F_TH, &tp, 4)) return rc;
     const int per_grid = tp.tiles_y * tp.tiles_x;
     const long long n_tiles = (long long)s->batch * per_grid;
     if (n_tiles > 0x7fffffffLL) return fail(FDTD2D_EINVAL, "too many tiles");
@@ -571,8 +591,9 @@ static bool uses_hybrid(const fdtd2d_sim* s, int phases) {
 
 static int run_pass(fdtd2d_sim* s, int k, int phases) {
     int rc;
+    const int all_phases = FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC;
     if (s->dtype == FDTD2D_F64)
-        rc = launch_generic_all<double>(s, k, phases);
+        rc = (phases == all_phases && s->variant != 1) ? launch_edge_all_f64(s, k) : launch_generic_all<double>(s, k, phases);
     else if (uses_hybrid(s, phases))
         rc = launch_hybrid(s, k, 0);
     else
@@ -1105,7 +1126,8 @@ int fdtd2d_pass_begin(fdtd2d_sim* s, int k) {
     if (uses_hybrid(s, all))
         rc = launch_hybrid(s, k, 1);
     else  // no band split for the generic-only paths: do the whole pass now
-        rc = s->dtype == FDTD2D_F64 ? launch_generic_all<double>(s, k, all) : launch_generic_all<float>(s, k, all);
+        rc = s->dtype == FDTD2D_F64 ? (s->variant != 1 ? launch_edge_all_f64(s, k) : launch_generic_all<double>(s, k, all))
+                                    : launch_generic_all<float>(s, k, all);
     if (rc) return rc;
     s->open_pass_k = k;
     return 0;

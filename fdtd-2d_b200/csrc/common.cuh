@@ -41,6 +41,8 @@ template <> struct Vec<double> {
     static constexpr int N = 2;
 };
 
+__device__ __forceinline__ void unpack4(const float4& v, float* a) { a[0] = v.x, a[1] = v.y, a[2] = v.z, a[3] = v.w; }
+
 // A source or probe cell: grid index in the batch, GLOBAL row, column, waveform index (sources only).
 struct Cell {
     int32_t grid, row, col, wave;

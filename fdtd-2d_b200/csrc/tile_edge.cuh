@@ -16,14 +16,33 @@
 
 namespace fdtd2d {
 
-template <int MR, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<float> p) {
+// four consecutive cells of one row <-> registers (one 128-bit access in fp32, two in fp64)
+__device__ __forceinline__ void load4(const float* p, float* a) { unpack4(*reinterpret_cast<const float4*>(p), a); }
+__device__ __forceinline__ void load4(const double* p, double* a) {
+    const double2 u = *reinterpret_cast<const double2*>(p), v = *reinterpret_cast<const double2*>(p + 2);
+    a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y;
+}
+__device__ __forceinline__ void ldg4(const float* p, float* a) { unpack4(__ldg(reinterpret_cast<const float4*>(p)), a); }
+__device__ __forceinline__ void ldg4(const double* p, double* a) {
+    const double2 u = __ldg(reinterpret_cast<const double2*>(p)), v = __ldg(reinterpret_cast<const double2*>(p + 2));
+    a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y;
+}
+__device__ __forceinline__ void store4(float* p, const float* a) {
+    *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
+}
+__device__ __forceinline__ void store4(double* p, const double* a) {
+    *reinterpret_cast<double2*>(p) = make_double2(a[0], a[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(a[2], a[3]);
+}
+
+template <typename T, int MR, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<T> p) {
     constexpr int TW = 128, TH = MR * NW, N = TH * TW, NT = NW * 32;
     extern __shared__ __align__(16) unsigned char smem_edge[];
-    float* s0 = reinterpret_cast<float*>(smem_edge);  // [TH][TW] Ez before the step
-    float* s1 = s0 + N;                               // [TH][TW] Ez after the interior update
-    float* sEz = s1 + N;                              // [NW][TW] first Ez row of every warp
-    float* sHx = sEz + NW * TW;                       // [NW][TW] last Hx row of every warp
+    T* s0 = reinterpret_cast<T*>(smem_edge);  // [TH][TW] Ez before the step
+    T* s1 = s0 + N;                           // [TH][TW] Ez after the interior update
+    T* sEz = s1 + N;                          // [NW][TW] first Ez row of every warp
+    T* sHx = sEz + NW * TW;                   // [NW][TW] last Hx row of every warp
 
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const int tile = p.tile_list ? p.tile_list[blockIdx.x] : (int)blockIdx.x;
@@ -38,25 +57,21 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
     const long long base = (long long)b * p.grid_stride + (long long)(lr0 + li0) * p.pitch + (lc0 + lj);
 
     // ---- load (zero outside the local array) ------------------------------------------------
-    float e[MR][4], hx[MR][4], hy[MR][4], ce[MR][4], ch[MR][4];
+    T e[MR][4], hx[MR][4], hy[MR][4], ce[MR][4], ch[MR][4];
     const bool col_in = (lc0 + lj >= 0) && (lc0 + lj < p.pitch);
 #pragma unroll
     for (int r = 0; r < MR; ++r) {
         const int row = lr0 + li0 + r;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bx = a, by = a, c1 = a, c2 = a;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) e[r][q] = hx[r][q] = hy[r][q] = ce[r][q] = ch[r][q] = (T)0;
         if (col_in && row >= 0 && row < p.Rl) {
             const long long o = base + (long long)r * p.pitch;
-            a = __ldg(reinterpret_cast<const float4*>(p.in[0] + o));
-            bx = __ldg(reinterpret_cast<const float4*>(p.in[1] + o));
-            by = __ldg(reinterpret_cast<const float4*>(p.in[2] + o));
-            c1 = __ldg(reinterpret_cast<const float4*>(p.ce + o));
-            c2 = __ldg(reinterpret_cast<const float4*>(p.ch + o));
+            ldg4(p.in[0] + o, e[r]);
+            ldg4(p.in[1] + o, hx[r]);
+            ldg4(p.in[2] + o, hy[r]);
+            ldg4(p.ce + o, ce[r]);
+            ldg4(p.ch + o, ch[r]);
         }
-        e[r][0] = a.x, e[r][1] = a.y, e[r][2] = a.z, e[r][3] = a.w;
-        hx[r][0] = bx.x, hx[r][1] = bx.y, hx[r][2] = bx.z, hx[r][3] = bx.w;
-        hy[r][0] = by.x, hy[r][1] = by.y, hy[r][2] = by.z, hy[r][3] = by.w;
-        ce[r][0] = c1.x, ce[r][1] = c1.y, ce[r][2] = c1.z, ce[r][3] = c1.w;
-        ch[r][0] = c2.x, ch[r][1] = c2.y, ch[r][2] = c2.z, ch[r][3] = c2.w;
     }
     // index-range masks of the reference's slices (main.py:70,74 and :27)
     bool hrow[MR], erow[MR], hcol[4], ecol[4];
@@ -73,7 +88,7 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
         ecol[q] = gj >= 1 && gj <= C - 2;
     }
 
-    TileCtx<float> tc;
+    TileCtx<T> tc;
     tc.gr0 = gr0, tc.lc0 = lc0, tc.Rg = Rg, tc.C = C, tc.k = k;
     tc.coef = p.mur[b];
     tc.touchL = lc0 < RING;
@@ -101,60 +116,54 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
 
     for (int s = 0; s < k; ++s) {
         // ---- H half-step ----------------------------------------------------------------------
-        *reinterpret_cast<float4*>(sEz + w * TW + lj) = make_float4(e[0][0], e[0][1], e[0][2], e[0][3]);
+        store4(sEz + w * TW + lj, e[0]);
         __syncthreads();
-        const float4 eb = *reinterpret_cast<const float4*>(sEz + wb);
-        const float below[4] = {eb.x, eb.y, eb.z, eb.w};
+        T below[4];
+        load4(sEz + wb, below);
 #pragma unroll
         for (int r = 0; r < MR; ++r) {
-            const float right3 = __shfl_down_sync(0xffffffffu, e[r][0], 1);
+            const T right3 = __shfl_down_sync(0xffffffffu, e[r][0], 1);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float down = (r + 1 < MR) ? e[r + 1 < MR ? r + 1 : r][q] : below[q];
-                const float right = (q < 3) ? e[r][q < 3 ? q + 1 : 3] : right3;
-                const float nx = sub_rn(hx[r][q], mul_rn(ch[r][q], sub_rn(down, e[r][q])));
-                const float ny = add_rn(hy[r][q], mul_rn(ch[r][q], sub_rn(right, e[r][q])));
+                const T down = (r + 1 < MR) ? e[r + 1 < MR ? r + 1 : r][q] : below[q];
+                const T right = (q < 3) ? e[r][q < 3 ? q + 1 : 3] : right3;
+                const T nx = sub_rn(hx[r][q], mul_rn(ch[r][q], sub_rn(down, e[r][q])));
+                const T ny = add_rn(hy[r][q], mul_rn(ch[r][q], sub_rn(right, e[r][q])));
                 const bool ok = hrow[r] && hcol[q];
                 hx[r][q] = ok ? nx : hx[r][q];
                 hy[r][q] = ok ? ny : hy[r][q];
             }
         }
         // ---- interior Ez update (S1) ----------------------------------------------------------
-        *reinterpret_cast<float4*>(sHx + w * TW + lj) =
-            make_float4(hx[MR - 1][0], hx[MR - 1][1], hx[MR - 1][2], hx[MR - 1][3]);
+        store4(sHx + w * TW + lj, hx[MR - 1]);
         if (staged) {
 #pragma unroll
-            for (int r = 0; r < MR; ++r)
-                *reinterpret_cast<float4*>(s0 + (li0 + r) * TW + lj) = make_float4(e[r][0], e[r][1], e[r][2], e[r][3]);
+            for (int r = 0; r < MR; ++r) store4(s0 + (li0 + r) * TW + lj, e[r]);
         }
         __syncthreads();
-        const float4 ha = *reinterpret_cast<const float4*>(sHx + wa);
-        const float above[4] = {ha.x, ha.y, ha.z, ha.w};
+        T above[4];
+        load4(sHx + wa, above);
 #pragma unroll
         for (int r = 0; r < MR; ++r) {
-            const float left0 = __shfl_up_sync(0xffffffffu, hy[r][3], 1);
+            const T left0 = __shfl_up_sync(0xffffffffu, hy[r][3], 1);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float up = (r > 0) ? hx[r > 0 ? r - 1 : 0][q] : above[q];
-                const float left = (q > 0) ? hy[r][q > 0 ? q - 1 : 0] : left0;
-                const float curl = sub_rn(sub_rn(hy[r][q], left), sub_rn(hx[r][q], up));
-                const float nv = add_rn(e[r][q], mul_rn(curl, ce[r][q]));
+                const T up = (r > 0) ? hx[r > 0 ? r - 1 : 0][q] : above[q];
+                const T left = (q > 0) ? hy[r][q > 0 ? q - 1 : 0] : left0;
+                const T curl = sub_rn(sub_rn(hy[r][q], left), sub_rn(hx[r][q], up));
+                const T nv = add_rn(e[r][q], mul_rn(curl, ce[r][q]));
                 e[r][q] = (erow[r] && ecol[q]) ? nv : e[r][q];
             }
         }
         // ---- boundary stages through shared memory (S2, S3, S4, source, probes) -------------------
         if (staged) {
 #pragma unroll
-            for (int r = 0; r < MR; ++r)
-                *reinterpret_cast<float4*>(s1 + (li0 + r) * TW + lj) = make_float4(e[r][0], e[r][1], e[r][2], e[r][3]);
+            for (int r = 0; r < MR; ++r) store4(s1 + (li0 + r) * TW + lj, e[r]);
             __syncthreads();
-            ring_stages<float, TH, TW, NT>(s0, s1, tc, tid);
-            source_and_probes<float, TH, TW, NT>(s1, p, tc, p.step0 + s, tid);
+            ring_stages<T, TH, TW, NT>(s0, s1, tc, tid);
+            source_and_probes<T, TH, TW, NT>(s1, p, tc, p.step0 + s, tid);
 #pragma unroll
-            for (int r = 0; r < MR; ++r) {
-                const float4 v = *reinterpret_cast<const float4*>(s1 + (li0 + r) * TW + lj);
-                e[r][0] = v.x, e[r][1] = v.y, e[r][2] = v.z, e[r][3] = v.w;
-            }
+            for (int r = 0; r < MR; ++r) load4(s1 + (li0 + r) * TW + lj, e[r]);
         }
     }
 
@@ -165,9 +174,9 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
             const int li = li0 + r;
             if (li >= k && li < k + p.CH && lr0 + li < p.Rl) {
                 const long long o = base + (long long)r * p.pitch;
-                *reinterpret_cast<float4*>(p.out[0] + o) = make_float4(e[r][0], e[r][1], e[r][2], e[r][3]);
-                *reinterpret_cast<float4*>(p.out[1] + o) = make_float4(hx[r][0], hx[r][1], hx[r][2], hx[r][3]);
-                *reinterpret_cast<float4*>(p.out[2] + o) = make_float4(hy[r][0], hy[r][1], hy[r][2], hy[r][3]);
+                store4(p.out[0] + o, e[r]);
+                store4(p.out[1] + o, hx[r]);
+                store4(p.out[2] + o, hy[r]);
             }
         }
     }
