@@ -47,8 +47,78 @@ WORKLOADS = {
                  desc="16384x16384 fp32, random permittivity, temporal-blocked kernel (BASELINE configs[2]; the "
                       "grid the >=70%-of-roofline target is quoted on)"),
     "cfg4": dict(rows=65536, cols=65536, inner=16, desc="65536x65536 fp32 y-slab sharded (BASELINE configs[3]), strong scaling"),
+    "cfg5": dict(rows=256, cols=256, inner=200, batch=1024,
+                 desc="batched 1024 x (256x256) independent fp32 grids per GPU (BASELINE configs[4], dataset generation)"),
     "small": dict(rows=1024, cols=1024, inner=64, desc="1024x1024 fp32 (debug)"),
 }
+
+
+class BatchedRunner:
+    """`batch` independent grids on one GPU behind the interface the bench uses for slabs (cfg5).  With
+    several ranks every rank runs its own `batch` grids: no exchange, weak scaling by construction."""
+
+    def __init__(self, fd, rows, cols, batch, device):
+        self.sim = fd.Simulation(rows, cols, np.float32, dt=DT, dx=DX, device=device, batch=batch)
+        self.fd, self.batch, self.rows, self.cols = fd, batch, rows, cols
+        self.row0, self.local_rows, self.hy_rows = 0, rows, rows - 1
+        self.tile_launch_count = 0
+        self._k = fd.DEFAULT_K
+
+    def set_stream(self, s):
+        self.sim.set_stream(s)
+
+    def set_kernel_variant(self, v):
+        self.sim.set_kernel_variant(v)
+
+    def set_materials_random(self, seed, span=9.0):
+        self.sim.set_materials_random(seed, span)
+
+    def set_materials(self, eps, mu, mur=None):
+        self.sim.set_materials(eps, mu)
+
+    def set_state(self, Ez, Hx, Hy):
+        self.sim.set_state(Ez, Hx, Hy)
+
+    def set_point_source(self, row, col, nsteps, fc=FC):
+        # one point source per grid, frequencies spread over 18..30 GHz like the dataset generator's omega range
+        fcs = np.linspace(18e9, 30e9, self.batch)
+        tables = np.stack([self.fd.source_table("ricker", nsteps, DT, f) for f in fcs[:16]])
+        cells = [(b, self.rows // 2 + (b % 7) - 3, self.cols // 2 + (b % 5) - 2, b % 16) for b in range(self.batch)]
+        self.sim.set_sources(cells, tables)
+
+    def set_probes(self, cells, cap):
+        self.sim.set_probes([(b, self.rows // 2, self.cols // 2 + 20) for b in range(0, self.batch, max(1, self.batch // 8))], cap)
+
+    def step(self, n, k=0):
+        self.sim.step(n, k)
+        self.tile_launch_count += -(-n // (k or self._k))
+
+    def read_Ez(self, out=None):
+        return self.sim.read_Ez(out)
+
+    def read_probes(self, a=0, n=None):
+        return self.sim.read_probes(a, n)
+
+    @property
+    def launch_count(self):
+        return self.sim.launch_count
+
+    @property
+    def step_index(self):
+        return self.sim.step_index
+
+    @step_index.setter
+    def step_index(self, v):
+        self.sim.step_index = v
+
+    def close(self):
+        self.sim.close()
+
+
+def make_sim(fd, wl, grows, cols, rank, world, local_rank, k):
+    if wl.get("batch"):
+        return BatchedRunner(fd, wl["rows"], cols, wl["batch"], local_rank)
+    return fd.SlabSimulation(grows, cols, np.float32, dt=DT, dx=DX, rank=rank, world=world, device=local_rank, halo=k)
 
 
 def peaks():
@@ -189,8 +259,6 @@ def main():
     import torch.distributed as dist
 
     import fdtd2d_b200 as fd
-    from fdtd2d_b200.distributed import SlabSimulation
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -202,13 +270,14 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
 
     strong = args.workload == "cfg4"
+    batch = wl.get("batch", 0)
     cols = wl["cols"]
-    grows = wl["rows"] if strong else wl["rows"] * world  # weak scaling: fixed rows per GPU
+    grows = wl["rows"] if (strong or batch) else wl["rows"] * world  # weak scaling: fixed rows per GPU
     inner = wl["inner"]
     k = args.k or fd.DEFAULT_K
     stream = torch.cuda.current_stream().cuda_stream
 
-    sim = SlabSimulation(grows, cols, np.float32, dt=DT, dx=DX, rank=rank, world=world, device=local_rank, halo=k)
+    sim = make_sim(fd, wl, grows, cols, rank, world, local_rank, k)
     sim.set_stream(stream)
     if args.variant:
         sim.set_kernel_variant(args.variant)
@@ -247,7 +316,7 @@ def main():
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    cells = grows * cols
+    cells = grows * cols * (batch * world if batch else 1)  # whole job
     value = cells * inner * args.steps / (ms * 1e-3) / 1e9
     peak, peak_src = peaks()
     n_pass = -(-inner // k) * args.steps  # tile-kernel launches per rank in the timed region
@@ -268,19 +337,19 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu:
         crow = min(4096, wl["rows"])
-        n = 2
+        n = max(2, int(6e8 / (crow * cols)))  # ~10 s of numpy work at ~60-90 Mcell/s
         v, el = cpu_reference_rate(crow, cols, n)
         cpu = {"value": v, "unit": "Gcell-updates/s", "cores": 1, "kind": "port", "host_cpus": os.cpu_count(),
-               "sample": f"{n} leapfrog steps on a {crow}x{cols} fp32 band of the workload grid, numpy port of the "
-                         f"reference loop ({el:.1f} s)"}
+               "sample": f"{n} leapfrog steps on a {crow}x{cols} fp32 band/grid of the workload, numpy port of the "
+                         f"reference loop ({el:.1f} s); numpy elementwise ops use 1 core"}
     if rank == 0:
         line = {
             "metric": "Gcell-updates/s (fp32 E+H step)", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "global_rows": grows, "cols": cols,
-                       "inner_leapfrog_steps_per_step": inner, "k_temporal": k,
-                       "parallelism": f"y-slabs x{world}" if world > 1 else "single GPU",
+                       "batch_per_gpu": batch or 1, "inner_leapfrog_steps_per_step": inner, "k_temporal": k,
+                       "parallelism": ("independent grids per rank" if batch else f"y-slabs x{world}") if world > 1 else "single GPU",
                        "l2": "state is larger than L2 (inputs larger than L2; no flush needed)",
                        "seed": 2026, "source": "ricker fc=30e9 at centre", "probes": len(probes)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -298,26 +367,26 @@ def main():
 def run_e2e(args, wl, fd, torch, dist, rank, world, local_rank, grows, cols, inner, k, barrier):
     """Public-API path with host buffers: per bench step upload eps, mu, Ez, Hx, Hy from pinned memory,
     form coefficients on the device, run `inner` leapfrog steps, read back Ez and the probe traces."""
-    from fdtd2d_b200.distributed import SlabSimulation, slab_rows
-
     steps = max(2, min(args.steps, 4))
-    sim = SlabSimulation(grows, cols, np.float32, dt=DT, dx=DX, rank=rank, world=world, device=local_rank, halo=k)
+    batch = wl.get("batch", 0)
+    sim = make_sim(fd, wl, grows, cols, rank, world, local_rank, k)
     sim.set_stream(torch.cuda.current_stream().cuda_stream)
     lr, hyr = sim.local_rows, sim.hy_rows
+    pre = (batch,) if batch else ()
 
     def pinned(shape):
-        return torch.zeros(shape, dtype=torch.float32, pin_memory=True).numpy()
+        return torch.zeros(pre + shape, dtype=torch.float32, pin_memory=True).numpy()
 
     eps, mu = pinned((lr, cols)), pinned((lr, cols))
-    eps[...] = synthetic_eps(lr, cols, 2026, sim.row0)
+    eps[...] = synthetic_eps(lr * max(1, batch), cols, 2026, sim.row0).reshape(eps.shape)
     mu[...] = np.float32(4 * np.pi * 1e-7)
     Ez, Hx, Hy = pinned((lr, cols)), pinned((lr, cols - 1)), pinned((hyr, cols))
     out = pinned((lr, cols))
-    mur = fd_mur_coef(eps if sim.row0 == 0 else None, mu, dist, world, torch)
+    mur = None if batch else fd_mur_coef(eps if sim.row0 == 0 else None, mu, dist, world, torch)
     sim.set_point_source(grows // 2, cols // 2, inner, FC)
     sim.set_probes([(grows // 2, cols // 2 + 16), (grows // 4, cols // 4)], inner)
     h2d = (eps.nbytes + mu.nbytes + Ez.nbytes + Hx.nbytes + Hy.nbytes) * world
-    d2h = (out.nbytes + inner * 2 * 4) * world
+    d2h = (out.nbytes + inner * (8 if batch else 2) * 4) * world
 
     def one():
         sim.step_index = 0
@@ -344,7 +413,8 @@ def run_e2e(args, wl, fd, torch, dist, rank, world, local_rank, grows, cols, inn
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     sim.close()
-    return {"value": grows * cols * inner * steps / (ms * 1e-3) / 1e9, "unit": "Gcell-updates/s",
+    cells = grows * cols * (batch * world if batch else 1)
+    return {"value": cells * inner * steps / (ms * 1e-3) / 1e9, "unit": "Gcell-updates/s",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": steps,
             "ms_per_step": ms / steps,
             "what": "Simulation API with pinned host arrays: set_materials(eps, mu) + set_state + step(inner) + "

@@ -304,3 +304,62 @@ def test_errors(fd):
             sim.set_state(np.zeros((32, 32), np.float32), np.zeros((32, 32), np.float32), np.zeros((31, 32), np.float32))
     with pytest.raises(ValueError):
         fd.update_Hx_Hy(np.zeros((20, 20)), np.zeros((20, 20)), np.zeros((19, 20)), np.ones((20, 20)), np.ones((20, 20)), DT, DX)
+
+
+# --------------------------------------------------------------------------------------------
+# ragged sizes: every tiling corner case (last-tile remainders, single tiles, thin grids)
+# --------------------------------------------------------------------------------------------
+def _ragged_cases():
+    rng = np.random.default_rng(12345)
+    cases = [(11, 11, 3, 5), (11, 300, 8, 9), (300, 11, 8, 9), (49, 113, 8, 8), (57, 121, 8, 9), (48, 112, 8, 8),
+             (96, 224, 8, 16), (97, 225, 8, 10), (104, 232, 8, 9), (65, 129, 1, 3), (2 * 48 + 7, 2 * 112 + 7, 8, 8)]
+    for _ in range(14):
+        cases.append((int(rng.integers(11, 400)), int(rng.integers(11, 700)), int(rng.integers(1, 9)), int(rng.integers(1, 20))))
+    return cases
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_ragged_sizes_vs_oracle(fd, oracle, dtype):
+    c_oracle, npo = oracle
+    for (R, C, k, nsteps) in _ragged_cases():
+        rng = np.random.default_rng(R * 7919 + C * 31 + k)
+        eps, mu, Ez, Hx, Hy = _random_problem(rng, R, C, dtype)
+        ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(dtype))
+        cells = [(R // 2, C // 2), (R - 1, 0), (0, C - 1)]
+        amp = npo.source_table("sinusoidal", nsteps, DT, FC)
+        probes = [(0, 0), (R - 1, C - 1), (R // 2, C // 2), (5, C - 6), (R - 6, 5)]
+        oEz, oHx, oHy = Ez.copy(), Hx.copy(), Hy.copy()
+        otrace = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, nsteps, amp, cells, probes)
+        with fd.Simulation(R, C, dtype, dt=DT, dx=DX) as sim:
+            sim.set_coefficients(ce, ch, coef)  # host-precomputed maps this time
+            sim.set_state(Ez, Hx, Hy)
+            sim.set_sources([(0, r, c, 0) for r, c in cells], amp[None, :])
+            sim.set_probes(probes, nsteps)
+            sim.step(nsteps, k)
+            gEz, gHx, gHy = sim.state()
+            gtrace = sim.read_probes()
+        what = f"{R}x{C} k={k} n={nsteps}"
+        assert_bits(gtrace, otrace, "probe trace " + what)
+        assert_bits(gEz, oEz, "Ez " + what)
+        assert_bits(gHx, oHx, "Hx " + what)
+        assert_bits(gHy, oHy, "Hy " + what)
+
+
+@pytest.mark.parametrize("variant", [1, 3])
+def test_kernel_variants_agree(fd, variant):
+    """The shared-memory generic kernel (variant 1: everywhere, 3: edge tiles only) and the default
+    register-resident kernels produce the same bits on a grid with many edge, source and probe tiles."""
+    R, C, n = 700, 1500, 27
+    outs = []
+    for v in (0, variant):
+        with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
+            sim.set_kernel_variant(v)
+            sim.set_materials_random(3, 9.0)
+            amp = fd.source_table("ricker", 700, DT, FC)
+            sim.set_sources([(0, 350, 750, 0), (0, 100, 100, 0), (0, 640, 1400, 0)], amp[None, :])
+            sim.set_probes([(350, 760), (3, 3), (696, 1496), (64, 128)], 700)
+            sim.step_index = 640
+            sim.step(n, 8)
+            outs.append(sim.state() + (sim.read_probes(640, n),))
+    for a, b in zip(*outs):
+        assert_bits(a, b, f"variant {variant} vs default")
