@@ -16,6 +16,7 @@
 #include "tile_fast.cuh"
 #include "tile_tma.cuh"
 #include "tile_generic.cuh"
+#include "grid_resident.cuh"
 
 using namespace fdtd2d;
 
@@ -118,6 +119,8 @@ struct fdtd2d_sim {
     int tma_box_rows = 0;              // box height the maps were encoded for (0 = not built)
     int sm_count = 0;
     int open_pass_k = 0;  // > 0 between fdtd2d_pass_begin and fdtd2d_pass_end
+    int resident_ok = -1;     // cluster-resident kernel usable for this handle? (-1 = not decided yet)
+    int resident_cluster = 0, resident_rpc = 0;  // CTAs per grid, rows per CTA
     unsigned char* d_gray = nullptr;  // snapshot background (Rl x C per grid)
     unsigned char* d_rgb = nullptr;   // one rendered frame (Rl x C x 3)
     double* d_lut = nullptr;          // 256 x 3 colormap
@@ -433,6 +436,7 @@ template <typename T> static int launch_generic_all(fdtd2d_sim* s, int k, int ph
 }
 
 static void free_plans(fdtd2d_sim* s) {
+    s->resident_ok = -1;
     for (PassPlan& pl : s->hybrid) {
         cudaFree(pl.d_generic);
         cudaFree(pl.d_fast);
@@ -581,6 +585,74 @@ static int launch_hybrid(fdtd2d_sim* s, int k, int part) {
         CUDA_TRY(cudaEventRecord(s->ev_join, s->side_stream));
         CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
     }
+    return 0;
+}
+
+// ---- cluster-resident path (grid_resident.cuh) ---------------------------------------------------
+constexpr int RES_MR = 4;  // rows per thread: 64 rows x 256 columns per CTA
+
+// Small fp32 grids that fit a thread-block cluster: whole-run residency instead of k-step tiles.
+static bool resident_eligible(fdtd2d_sim* s) {
+    if (s->resident_ok >= 0) return s->resident_ok != 0;
+    s->resident_ok = 0;
+    if (s->dtype != FDTD2D_F32 || s->has_top_nb || s->has_bot_nb) return false;
+    if (s->C < 16 || s->C > RES_TW || s->Rg < 16 || s->Rg > 8 * RES_MR * RES_NW) return false;
+    if (const char* e = getenv("FDTD2D_NO_RESIDENT"))
+        if (atoi(e)) return false;
+    // every source / probe cell may need a 4-cell slot in its CTA's slot frame
+    std::vector<int> per_grid((size_t)s->batch, 0);
+    for (const Cell& c : s->h_src) per_grid[c.grid] += 1;
+    for (const Cell& c : s->h_probe) per_grid[c.grid] += 1;
+    for (int v : per_grid)
+        if (v > RES_MAX_SLOTS) return false;
+    int n = 1;
+    while (n * RES_MR * RES_NW < s->Rg) n *= 2;
+    if (const char* e = getenv("FDTD2D_RESIDENT_CLUSTER")) {  // tuning knob: more, thinner bands per grid
+        const int v = atoi(e);
+        if ((v == 1 || v == 2 || v == 4 || v == 8) && v >= n) n = v;
+    }
+    int rpc = RES_MR * ((s->Rg + RES_MR * n - 1) / (RES_MR * n));
+    if (rpc < 6 || s->Rg - (n - 1) * rpc < 6) return false;  // first / last band hold the whole top / bottom ring
+    s->resident_cluster = n;
+    s->resident_rpc = rpc;
+    s->resident_ok = 1;
+    return true;
+}
+
+static int launch_resident(fdtd2d_sim* s, int n_steps) {
+    static bool done_[MAX_DEVICES] = {};
+    bool& done = done_[s->device % MAX_DEVICES];
+    const size_t smem = resident_smem_floats(RES_MR) * sizeof(float);
+    if (!done) {
+        CUDA_TRY(cudaFuncSetAttribute(grid_resident_kernel<RES_MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        done = true;
+    }
+    TilePlan tp;
+    tp.k = n_steps;
+    tp.CH = s->resident_rpc;
+    PassParams<float> p;
+    fill_params(s, tp, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC, &p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(s->batch * s->resident_cluster));
+    cfg.blockDim = dim3(RES_NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)s->resident_cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (getenv("FDTD2D_DEBUG")) {
+        int nc = -1;
+        cudaOccupancyMaxActiveClusters(&nc, grid_resident_kernel<RES_MR>, &cfg);
+        fprintf(stderr, "[fdtd2d] resident: %d grids x cluster %d (rpc %d), %zu B smem, max active clusters %d\n", s->batch,
+                s->resident_cluster, s->resident_rpc, smem, nc);
+    }
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_resident_kernel<RES_MR>, p));
+    s->launches += 1;
+    s->cur ^= 1;
     return 0;
 }
 
@@ -1038,6 +1110,13 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
     REQUIRE(k_temporal >= 0 && k_temporal <= FDTD2D_MAX_K, "k_temporal must be in [0, %d]", FDTD2D_MAX_K);
     if (!s->coeffs_set || !s->mur_set) return fail(FDTD2D_ESTATE, "coefficients / Mur coefficient not set");
     if (int rc = use_device(s)) return rc;
+    if (n_steps > 0 && (s->variant == 0 || s->variant == 4) && resident_eligible(s)) {
+        // the whole run in one launch, the grid resident on chip (k_temporal does not apply)
+        if (int rc = launch_resident(s, n_steps)) return rc;
+        s->step += n_steps;
+        return 0;
+    }
+    if (s->variant == 4 && n_steps > 0) return fail(FDTD2D_EINVAL, "variant 4 (cluster-resident) needs fp32, 16..256 columns, 16..512 rows, no slabs");
     int k = k_temporal ? k_temporal : (s->dtype == FDTD2D_F32 ? 8 : 4);
     if (s->has_top_nb || s->has_bot_nb) {
         k = std::min(k, s->halo);
@@ -1076,7 +1155,7 @@ int fdtd2d_set_step_index(fdtd2d_sim* s, int64_t step) {
 }
 
 int fdtd2d_set_kernel_variant(fdtd2d_sim* s, int variant) {
-    REQUIRE(s && variant >= 0 && variant <= 3, "bad argument");
+    REQUIRE(s && variant >= 0 && variant <= 4, "bad argument");
     s->variant = variant;
     return 0;
 }

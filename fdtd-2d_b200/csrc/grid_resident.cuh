@@ -1,0 +1,483 @@
+// Cluster-resident kernel (fp32): one thread-block CLUSTER per grid; the whole grid stays on chip for ALL
+// n leapfrog steps of a call -- HBM is touched once to load the five arrays and once to store the three
+// fields, whatever n is.  This is the path for the small independent grids of the batched mode
+// (BASELINE configs[4]: 1024 x 256^2) and for the reference demo grid (fdtd.py:14-19, 200^2), where
+// overlapped tiling has nothing to amortise: every tile of such a grid touches the Mur ring.
+//
+// Work layout.  A cluster of n CTAs (n = 1, 2, 4 or 8) splits the rows of one grid into n bands of RPC
+// rows (RPC a multiple of MR; at most MR*16 rows per CTA, at most 256 columns).  Inside a CTA warp w owns
+// rows [w*MR, (w+1)*MR) of the band and lane l owns columns [4l, 4l+4) and [128+4l, 128+4l+4): MR x 8
+// cells of Ez, Hx, Hy per thread live in REGISTERS from the first step to the last.  The coefficient maps
+// dt/(eps*dx), dt/(mu*dx) live in shared memory (each thread re-reads only the slots it wrote).
+// Neighbours:
+//   columns across lanes            -> warp shuffles (rotating, so column 127 <-> 128 is one more select),
+//   rows across warps               -> one row per warp through shared memory (as in tile_fast.cuh),
+//   rows across the CTAs of a cluster -> DISTRIBUTED SHARED MEMORY: the first warp stores its first Ez row
+//     straight into the shared memory of the CTA above (st.shared::cluster), the last warp its last Hx row
+//     into the CTA below, and signals a remote mbarrier (arrive.release.cluster); only the one warp that
+//     needs the row waits (try_wait.acquire.cluster) and it does so just before its last row, so the
+//     ~200-cycle DSMEM latency hides behind its other rows.  Rows are double-buffered by step parity: a CTA
+//     can never run more than one step ahead of a neighbour, so two buffers suffice and there is NO
+//     cluster-wide barrier inside the time loop.
+// Index ranges of the reference's slices (main.py:70,74 rows 0..R-2 / cols 0..C-2 for H, :27 rows 1..R-2 /
+// cols 1..C-2 for Ez) are imposed by zeroing the on-chip copy of the coefficient at the excluded cells:
+// x -/+ 0*(..) leaves x unchanged (for finite fields), so the inner loops carry no masks.  Every cell the Ez
+// mask excludes is overwritten by the boundary stages below, exactly as in the reference.
+//
+// Boundary stages (main.py:29-61) run on small shared-memory frames holding only the ring: the 6 outermost
+// columns on each side for every row (frames L, R), rows 0..5 (frame T, first CTA) and R-6..R-1 (frame B,
+// last CTA), each as S0 (Ez before the step, the reference's Ez_prev) and S1 (after the interior update).
+// S2 (Mur left/right) is evaluated with one thread per ring cell, S3 (top/bottom) with one thread per column
+// in the reference's k order, S4 (5x5 corner means, a Jacobi sweep: every read is of a not-yet-processed
+// cell) with one thread per corner cell; then the owners pull the finished ring back into registers.
+// Source cells and probes that are not in a ring frame get a 4-cell slot in a small frame the same way, so
+// the float64 source add (fdtd.py:34) and the probe sampling work on shared memory, not on registers.
+// Results are bit-identical to the tile kernels and to the oracle.
+#pragma once
+#include "common.cuh"
+#include "tile_edge.cuh"
+#include "tile_tma.cuh"
+
+namespace fdtd2d {
+
+constexpr int RES_TW = 256;         // columns per CTA (two 128-column halves per warp row)
+constexpr int RES_NW = 16;          // warps per CTA
+constexpr int RES_MAX_SLOTS = 255;  // 4-cell slots for source / probe cells outside the ring frames (per CTA)
+constexpr int RES_MAX_CELLS = 256;  // probes per CTA; sources inside ring frames per CTA
+constexpr int RES_LW = 8, RES_RW = 12, RES_ZW = RES_LW + RES_RW;  // left | right ring frame columns of one row
+
+// shared-memory floats of one CTA (see the carve-up at the top of the kernel)
+__host__ __device__ constexpr size_t resident_smem_floats(int MR) {
+    return (size_t)2 * MR * RES_NW * RES_TW                   // coefficient maps
+           + 2 * RES_NW * RES_TW                              // row exchange between warps
+           + 4 * RES_TW                                       // row exchange between CTAs (2 rows x 2 parities)
+           + 2 * (MR * RES_NW * RES_ZW + 12 * RES_TW)         // S0 and S1 frames: LR, T, B
+           + 12 * RES_TW                                      // T2, B2: finished top / bottom rows
+           + 2 * 256 * 4                                      // slot frame + per-slot source waveforms
+           + 2 * RES_MAX_CELLS * 2                            // probe list, ring-source list
+           + MR * RES_NW * (RES_TW / 4) / 4;                  // slot table (bytes)
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster4(uint32_t addr, const float* a) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3])
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    do {
+        if (++spins > (1u << 26)) __trap();  // never hang the GPU on a protocol bug
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// p.k = number of leapfrog steps of this launch; p.CH = rows per CTA (RPC); gridDim.x = batch * cluster size.
+template <int MR>
+__global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const PassParams<float> p) {
+    static_assert(MR == 4, "the S2 lane mapping (4 rows x 8 ring cells per warp) assumes 4 rows per warp");
+    constexpr int TW = RES_TW, NW = RES_NW, TH = MR * NW, NT = NW * 32, LW = RES_LW, ZW = RES_ZW;
+    constexpr unsigned FULL = 0xffffffffu;
+    // ring frames, addressed as float offsets from F: [LR0 | T0 | B0] = S0, the same again = S1, then T2, B2, slots
+    constexpr int oLR = 0, oT = TH * ZW, oB = oT + 6 * TW, DELTA = oB + 6 * TW;
+    constexpr int oT2 = 2 * DELTA, oB2 = oT2 + 6 * TW, oSlot = oB2 + 6 * TW;
+    extern __shared__ __align__(16) unsigned char smem_res[];
+    float* sCe = reinterpret_cast<float*>(smem_res);  // [TH][TW] dt/(eps*dx), zero where Ez is not updated
+    float* sCh = sCe + TH * TW;                       // [TH][TW] dt/(mu*dx), zero where H is not updated
+    float* sEz = sCh + TH * TW;                       // [NW][TW] first Ez row of every warp
+    float* sHx = sEz + NW * TW;                       // [NW][TW] last Hx row of every warp
+    float* rEz = sHx + NW * TW;                       // [2][TW] first Ez row of the CTA below (it writes it)
+    float* rHx = rEz + 2 * TW;                        // [2][TW] last Hx row of the CTA above (it writes it)
+    float* F = rHx + 2 * TW;                          // ring frames (see the offsets above)
+    int* slotW = reinterpret_cast<int*>(F + oSlot + 256 * 4);  // [256][4] waveform of a slot cell's source or -1
+    int* plist = slotW + 256 * 4;                     // [RES_MAX_CELLS][2] probes of this band: frame offset, trace column
+    int* rlist = plist + RES_MAX_CELLS * 2;           // [RES_MAX_CELLS][2] sources inside ring frames: offset, wave*amp_steps
+    unsigned char* slot_tbl = reinterpret_cast<unsigned char*>(rlist + RES_MAX_CELLS * 2);  // [TH][TW/4] slot or 0xFF
+    __shared__ __align__(8) uint64_t barE[2], barH[2];
+    __shared__ int s_counts[2];  // probes, ring sources of this band
+
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const int crank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
+    const int b = blockIdx.x / csize;
+    const int R = p.Rg, C = p.C, RPC = p.CH, n_steps = p.k;
+    const int row_lo = crank * RPC;
+    const int nrows = min(RPC, R - row_lo);
+    const bool isTop = crank == 0, isBot = crank == csize - 1;
+    const bool has_above = !isTop, has_below = !isBot;
+    const int wl = (nrows - 1) / MR;  // the warp that holds the band's last row
+    const int li0 = w * MR;
+    const int cR0 = ((C - 6) >> 2) << 2;  // first column of the right ring frame (4-aligned, >= 8 for C >= 16)
+    const int cg[2] = {4 * l, 128 + 4 * l};
+    const float coef = p.mur[b];
+    const long long gbase = (long long)b * p.grid_stride;
+
+    // ---- load: fields -> registers, coefficient maps -> shared memory (masked) ---------------------
+    float e[MR][2][4], hx[MR][2][4], hy[MR][2][4];
+#pragma unroll
+    for (int r = 0; r < MR; ++r) {
+        const int lr = li0 + r, gi = row_lo + lr;
+        const bool hrow = gi <= R - 2, erow = gi >= 1 && gi <= R - 2;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            float ce4[4], ch4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) e[r][g][q] = hx[r][g][q] = hy[r][g][q] = ce4[q] = ch4[q] = 0.0f;
+            if (lr < nrows && cg[g] < p.pitch) {
+                const long long o = gbase + (long long)gi * p.pitch + cg[g];
+                ldg4(p.in[0] + o, e[r][g]);
+                ldg4(p.in[1] + o, hx[r][g]);
+                ldg4(p.in[2] + o, hy[r][g]);
+                ldg4(p.ce + o, ce4);
+                ldg4(p.ch + o, ch4);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int gj = cg[g] + q;
+                if (!(hrow && gj <= C - 2)) ch4[q] = 0.0f;             // main.py:70,74: rows 0..R-2, cols 0..C-2
+                if (!(erow && gj >= 1 && gj <= C - 2)) ce4[q] = 0.0f;  // main.py:27: rows 1..R-2, cols 1..C-2
+            }
+            store4(sCe + lr * TW + cg[g], ce4);
+            store4(sCh + lr * TW + cg[g], ch4);
+        }
+    }
+
+    // ---- set-up: barriers; where the source / probe cells of this band live in shared memory --------
+    for (int i = tid; i < TH * (TW / 4) / 4; i += NT) reinterpret_cast<unsigned*>(slot_tbl)[i] = 0xffffffffu;
+    for (int i = tid; i < 256 * 4; i += NT) slotW[i] = -1;
+    __syncthreads();
+    // offset (from F) of the finished value of cell (gi, gj) of this band once a step's boundary stages are done
+    auto ring_off = [&](int gi, int gj) -> int {
+        const int lr = gi - row_lo;
+        if (isTop && gi <= 5) return oT2 + gi * TW + gj;
+        if (isBot && gi >= R - 6) return oB2 + (gi - (R - 6)) * TW + gj;
+        if (gj < LW) return DELTA + oLR + lr * ZW + gj;
+        if (gj >= cR0) return DELTA + oLR + lr * ZW + LW + (gj - cR0);
+        return -1;  // not in a ring frame: the cell gets a slot
+    };
+    if (tid == 0) {
+        mbar_init(&barE[0], 1), mbar_init(&barE[1], 1), mbar_init(&barH[0], 1), mbar_init(&barH[1], 1);
+        fence_mbar_init();
+        int n_slot = 0, n_prb = 0, n_rsrc = 0;
+        auto slot_of = [&](int lr, int col) -> int {
+            unsigned char& t = slot_tbl[lr * (TW / 4) + (col >> 2)];
+            if (t == 0xFF) {
+                if (n_slot >= RES_MAX_SLOTS) __trap();  // the host checks eligibility; never overrun the frame
+                t = (unsigned char)n_slot++;
+            }
+            return t;
+        };
+        const int s_lo = p.src_range ? p.src_range[b] : 0, s_hi = p.src_range ? p.src_range[b + 1] : 0;
+        for (int q = s_lo; q < s_hi; ++q) {
+            const Cell c = p.src[q];
+            if (c.row < row_lo || c.row >= row_lo + nrows) continue;
+            const int off = ring_off(c.row, c.col);
+            if (off >= 0) {
+                if (n_rsrc >= RES_MAX_CELLS) __trap();
+                rlist[2 * n_rsrc] = off, rlist[2 * n_rsrc + 1] = c.wave * p.amp_steps, ++n_rsrc;
+            } else {
+                slotW[slot_of(c.row - row_lo, c.col) * 4 + (c.col & 3)] = c.wave;
+            }
+        }
+        const int p_lo = p.probe_range ? p.probe_range[b] : 0, p_hi = p.probe_range ? p.probe_range[b + 1] : 0;
+        for (int q = p_lo; q < p_hi; ++q) {
+            const Cell c = p.probes[q];
+            if (c.row < row_lo || c.row >= row_lo + nrows) continue;
+            int off = ring_off(c.row, c.col);
+            if (off < 0) off = oSlot + slot_of(c.row - row_lo, c.col) * 4 + (c.col & 3);
+            if (n_prb >= RES_MAX_CELLS) __trap();
+            plist[2 * n_prb] = off, plist[2 * n_prb + 1] = q, ++n_prb;
+        }
+        s_counts[0] = n_prb, s_counts[1] = n_rsrc;
+    }
+    __syncthreads();
+    const int n_prb = s_counts[0], n_rsrc = s_counts[1];
+    unsigned spmask = 0;  // bit r*2+g: my group (r, g) holds a source or probe cell and has a slot
+#pragma unroll
+    for (int r = 0; r < MR; ++r)
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+            if (slot_tbl[(li0 + r) * (TW / 4) + (cg[g] >> 2)] != 0xFF) spmask |= 1u << (r * 2 + g);
+    // my groups' columns inside the LR frame of a row (-1: not a ring group)
+    const int zo[2] = {cg[0] < LW ? cg[0] : (cg[0] >= cR0 && cg[0] < cR0 + RES_RW ? LW + cg[0] - cR0 : -1),
+                       cg[1] >= cR0 && cg[1] < cR0 + RES_RW ? LW + cg[1] - cR0 : -1};
+    float* const zrow = F + oLR + li0 * ZW;  // LR frame (S0) of my first row; S1 is DELTA further
+    // do my rows reach the top / bottom ring rows?
+    const bool warp_tb = (isTop && row_lo + li0 <= 5) || (isBot && row_lo + li0 + MR - 1 >= R - 6 && row_lo + li0 < R);
+    // S2 (Mur left/right) of my warp's rows: lane -> (row l>>3, ring cell l&7)
+    const int s2row = li0 + (l >> 3), s2k = l & 7, s2gi = row_lo + s2row;
+    const bool s2act = s2k < RING && s2row < nrows && s2gi >= 1 && s2gi <= R - 2;
+    float* const s2L = F + DELTA + oLR + s2row * ZW + s2k;                       // S1 of cell (row, k); S0 is DELTA before
+    float* const s2R = F + DELTA + oLR + s2row * ZW + LW + (C - 1 - s2k - cR0);  // S1 of cell (row, C-1-k)
+    // registers -> S0 / S1 frames (delta = 0 / DELTA)
+    auto park = [&](int delta) {
+#pragma unroll
+        for (int r = 0; r < MR; ++r) {
+            if (zo[0] >= 0) store4(zrow + delta + r * ZW + zo[0], e[r][0]);
+            if (zo[1] >= 0) store4(zrow + delta + r * ZW + zo[1], e[r][1]);
+        }
+        if (warp_tb) {
+#pragma unroll
+            for (int r = 0; r < MR; ++r) {
+                const int gi = row_lo + li0 + r;
+                if (isTop && gi <= 5) {
+                    store4(F + delta + oT + gi * TW + cg[0], e[r][0]);
+                    store4(F + delta + oT + gi * TW + cg[1], e[r][1]);
+                } else if (isBot && gi >= R - 6 && gi < R) {
+                    store4(F + delta + oB + (gi - (R - 6)) * TW + cg[0], e[r][0]);
+                    store4(F + delta + oB + (gi - (R - 6)) * TW + cg[1], e[r][1]);
+                }
+            }
+        }
+    };
+    // Finished value of every cell of the 6 top (or bottom) rows from their S0 / S1 frames: S2, S3 and S4 of
+    // SURVEY Appendix A evaluated per cell.  `i` is the depth from the edge (0 = edge row), `top` picks the frame.
+    auto tb_pass = [&](const bool top) {
+        const float* A0 = F + (top ? oT : oB);
+        const float* A1 = A0 + DELTA;
+        float* A2 = F + (top ? oT2 : oB2);
+        auto fr = [&](int i) { return (top ? i : 5 - i) * TW; };
+        auto s0 = [&](int i, int j) { return A0[fr(i) + j]; };
+        auto s1 = [&](int i, int j) { return A1[fr(i) + j]; };
+        auto S2v = [&](int i, int j) -> float {  // main.py:33-41, rows 1..R-2
+            if (i >= 1) {
+                if (j <= 4) return add_rn(s0(i, j + 1), mul_rn(coef, sub_rn(s1(i, j + 1), s0(i, j))));
+                if (j >= C - 5 && j <= C - 1) return add_rn(s0(i, j - 1), mul_rn(coef, sub_rn(s1(i, j - 1), s0(i, j))));
+            }
+            return s1(i, j);
+        };
+        auto S3v = [&](int i, int j) -> float {  // main.py:43-51, columns 1..C-2
+            if (i <= 4 && j >= 1 && j <= C - 2) return add_rn(s0(i + 1, j), mul_rn(coef, sub_rn(S2v(i + 1, j), s0(i, j))));
+            return S2v(i, j);
+        };
+        const int j = tid & (TW - 1);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int i = (tid >> 8) + 2 * t;
+            float v;
+            if (i <= 4 && (j <= 4 || (j >= C - 5 && j <= C - 1)))  // main.py:54-61: reads of not-yet-processed cells
+                v = mul_rn(add_rn(S3v(i, j <= 4 ? j + 1 : j - 1), S3v(i + 1, j)), 0.5f);  // == sum / 2 exactly
+            else
+                v = S3v(i, j);
+            A2[fr(i) + j] = v;
+        }
+    };
+    auto sample_probes = [&](long long step) {
+        if (tid < n_prb && step < p.trace_cap) p.trace[step * p.n_probe + plist[2 * tid + 1]] = F[plist[2 * tid]];
+    };
+    // addresses in the neighbours' shared memory
+    const uint32_t up_rank = has_above ? crank - 1 : crank, dn_rank = has_below ? crank + 1 : crank;
+    const uint32_t up_rEz = map_to_rank(smem_u32(rEz), up_rank), up_barE = map_to_rank(smem_u32(&barE[0]), up_rank);
+    const uint32_t dn_rHx = map_to_rank(smem_u32(rHx), dn_rank), dn_barH = map_to_rank(smem_u32(&barH[0]), dn_rank);
+    const bool edge_dn = (w == wl) && has_below;  // my last row needs the Ez row of the CTA below
+    const bool edge_up = (w == 0) && has_above;   // my first row needs the Hx row of the CTA above
+    const bool cta_tb = isTop || isBot;
+    cluster_sync_all();  // every CTA's barriers are initialised before anyone signals them
+
+#pragma unroll 1
+    for (int s = 0; s < n_steps; ++s) {
+        const int par = s & 1;
+        const uint32_t ph = (uint32_t)(s >> 1) & 1u;
+        // ---- publish the first Ez row of every warp; the band's first row also goes to the CTA above ----
+        store4(sEz + w * TW + cg[0], e[0][0]);
+        store4(sEz + w * TW + cg[1], e[0][1]);
+        if (edge_up) {
+            st_cluster4(up_rEz + (uint32_t)(par * TW + cg[0]) * 4u, e[0][0]);
+            st_cluster4(up_rEz + (uint32_t)(par * TW + cg[1]) * 4u, e[0][1]);
+            __syncwarp();
+            if (l == 0) mbar_arrive_cluster(up_barE + 8u * par);
+        }
+        park(0);  // S0: Ez is not changed by the H half-step
+        __syncthreads();
+        if (s > 0) sample_probes(p.step0 + s - 1);  // the previous step's frames are intact until the next park
+        // ---- H half-step (main.py:69-74) ---------------------------------------------------------------
+        const float* belowp = sEz + (w + 1 < NW ? w + 1 : NW - 1) * TW;
+#pragma unroll
+        for (int r = 0; r < MR; ++r) {
+            float dn[2][4];
+            if (r + 1 < MR) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dn[g][q] = e[r + 1 < MR ? r + 1 : r][g][q];
+            } else {
+                if (edge_dn) {
+                    mbar_wait_cluster(&barE[par], ph);
+                    belowp = rEz + par * TW;
+                }
+                load4(belowp + cg[0], dn[0]);
+                load4(belowp + cg[1], dn[1]);
+            }
+            float c[2][4];
+            load4(sCh + (li0 + r) * TW + cg[0], c[0]);
+            load4(sCh + (li0 + r) * TW + cg[1], c[1]);
+            const float ra = __shfl_sync(FULL, e[r][0][0], (l + 1) & 31);
+            const float rb = __shfl_sync(FULL, e[r][1][0], (l + 1) & 31);
+            const float right3[2] = {l == 31 ? rb : ra, rb};
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float right = (q < 3) ? e[r][g][q < 3 ? q + 1 : 3] : right3[g];
+                    hx[r][g][q] = sub_rn(hx[r][g][q], mul_rn(c[g][q], sub_rn(dn[g][q], e[r][g][q])));
+                    hy[r][g][q] = add_rn(hy[r][g][q], mul_rn(c[g][q], sub_rn(right, e[r][g][q])));
+                }
+        }
+        // ---- publish the last Hx row of every warp; the band's last row also goes to the CTA below -----
+        store4(sHx + w * TW + cg[0], hx[MR - 1][0]);
+        store4(sHx + w * TW + cg[1], hx[MR - 1][1]);
+        if (edge_dn) {
+            st_cluster4(dn_rHx + (uint32_t)(par * TW + cg[0]) * 4u, hx[MR - 1][0]);
+            st_cluster4(dn_rHx + (uint32_t)(par * TW + cg[1]) * 4u, hx[MR - 1][1]);
+            __syncwarp();
+            if (l == 0) mbar_arrive_cluster(dn_barH + 8u * par);
+        }
+        __syncthreads();
+        // ---- interior Ez update (main.py:21-27), last row first so the remote row is needed last --------
+        const float* abovep = sHx + (w > 0 ? w - 1 : 0) * TW;
+#pragma unroll
+        for (int rr = 0; rr < MR; ++rr) {
+            const int r = MR - 1 - rr;
+            float up[2][4];
+            if (r > 0) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) up[g][q] = hx[r > 0 ? r - 1 : 0][g][q];
+            } else {
+                if (edge_up) {
+                    mbar_wait_cluster(&barH[par], ph);
+                    abovep = rHx + par * TW;
+                }
+                load4(abovep + cg[0], up[0]);
+                load4(abovep + cg[1], up[1]);
+            }
+            float c[2][4];
+            load4(sCe + (li0 + r) * TW + cg[0], c[0]);
+            load4(sCe + (li0 + r) * TW + cg[1], c[1]);
+            const float la = __shfl_sync(FULL, hy[r][0][3], (l + 31) & 31);
+            const float lb = __shfl_sync(FULL, hy[r][1][3], (l + 31) & 31);
+            const float left0[2] = {la, l == 0 ? la : lb};
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float left = (q > 0) ? hy[r][g][q > 0 ? q - 1 : 0] : left0[g];
+                    const float curl = sub_rn(sub_rn(hy[r][g][q], left), sub_rn(hx[r][g][q], up[g][q]));
+                    e[r][g][q] = add_rn(e[r][g][q], mul_rn(curl, c[g][q]));
+                }
+        }
+        const long long step = p.step0 + s;
+        // ---- S1 -> ring frames; source / probe cells outside the frames go through their slot -------------
+        park(DELTA);
+        if (spmask) {
+#pragma unroll
+            for (int r = 0; r < MR; ++r)
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+                    if (spmask >> (r * 2 + g) & 1u) {
+                        const int sl = slot_tbl[(li0 + r) * (TW / 4) + (cg[g] >> 2)];
+                        float* f = F + oSlot + sl * 4;
+                        store4(f, e[r][g]);
+                        if (step < p.amp_steps)
+                            for (int q = 0; q < 4; ++q) {  // source add (fdtd.py:34): float64 sum, then cast
+                                const int wv = slotW[sl * 4 + q];
+                                if (wv >= 0) f[q] = add_source(f[q], p.amp[(long long)wv * p.amp_steps + step]);
+                            }
+                        load4(f, e[r][g]);
+                    }
+        }
+        __syncwarp();
+        // ---- S2: Mur left/right (main.py:33-41) of my warp's own rows, one lane per ring cell; all cells are
+        // read before any is written (the reference's k order reads column k+1 before overwriting it) ------
+        {
+            float vl = 0.0f, vr = 0.0f;
+            if (s2act) {
+                vl = add_rn(s2L[1 - DELTA], mul_rn(coef, sub_rn(s2L[1], s2L[-DELTA])));
+                vr = add_rn(s2R[-1 - DELTA], mul_rn(coef, sub_rn(s2R[-1], s2R[-DELTA])));
+            }
+            __syncwarp();
+            if (s2act) *s2L = vl, *s2R = vr;
+        }
+        // ---- top / bottom rows: S2, S3, S4 in one pass over their frames (all threads of the CTA) ------------
+        if (cta_tb) {
+            __syncthreads();
+            if (isTop) tb_pass(true);
+            if (isBot) tb_pass(false);
+        }
+        if (n_rsrc) {  // sources inside a ring frame are added once the frame is finished
+            __syncthreads();
+            if (tid < n_rsrc && step < p.amp_steps) {
+                float* f = F + rlist[2 * tid];
+                *f = add_source(*f, p.amp[(long long)rlist[2 * tid + 1] + step]);
+            }
+        }
+        if (cta_tb || n_rsrc)
+            __syncthreads();
+        else
+            __syncwarp();
+        // ---- finished ring -> registers ---------------------------------------------------------------------
+#pragma unroll
+        for (int r = 0; r < MR; ++r) {
+            if (zo[0] >= 0) load4(zrow + DELTA + r * ZW + zo[0], e[r][0]);
+            if (zo[1] >= 0) load4(zrow + DELTA + r * ZW + zo[1], e[r][1]);
+        }
+        if (warp_tb) {
+#pragma unroll
+            for (int r = 0; r < MR; ++r) {
+                const int gi = row_lo + li0 + r;
+                if (isTop && gi <= 5) {
+                    load4(F + oT2 + gi * TW + cg[0], e[r][0]);
+                    load4(F + oT2 + gi * TW + cg[1], e[r][1]);
+                } else if (isBot && gi >= R - 6 && gi < R) {
+                    load4(F + oB2 + (gi - (R - 6)) * TW + cg[0], e[r][0]);
+                    load4(F + oB2 + (gi - (R - 6)) * TW + cg[1], e[r][1]);
+                }
+            }
+        }
+    }
+    if (n_steps > 0 && n_prb) {
+        __syncthreads();
+        sample_probes(p.step0 + n_steps - 1);
+    }
+
+    // ---- store the fields -----------------------------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < MR; ++r) {
+        const int lr = li0 + r, gi = row_lo + lr;
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+            if (lr < nrows && cg[g] < p.pitch) {
+                const long long o = gbase + (long long)gi * p.pitch + cg[g];
+                store4(p.out[0] + o, e[r][g]);
+                store4(p.out[1] + o, hx[r][g]);
+                store4(p.out[2] + o, hy[r][g]);
+            }
+    }
+    cluster_sync_all();  // no CTA may exit while a neighbour can still write into its shared memory
+}
+
+}  // namespace fdtd2d
