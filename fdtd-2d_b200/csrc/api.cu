@@ -120,7 +120,7 @@ struct fdtd2d_sim {
     int sm_count = 0;
     int open_pass_k = 0;  // > 0 between fdtd2d_pass_begin and fdtd2d_pass_end
     int resident_ok = -1;     // cluster-resident kernel usable for this handle? (-1 = not decided yet)
-    int resident_cluster = 0, resident_rpc = 0;  // CTAs per grid, rows per CTA
+    int resident_cluster = 0, resident_rpc = 0, resident_edge = 0, resident_mr = 0;  // CTAs per grid, rows per middle / first CTA, rows per thread
     unsigned char* d_gray = nullptr;  // snapshot background (Rl x C per grid)
     unsigned char* d_rgb = nullptr;   // one rendered frame (Rl x C x 3)
     double* d_lut = nullptr;          // 256 x 3 colormap
@@ -589,14 +589,25 @@ static int launch_hybrid(fdtd2d_sim* s, int k, int part) {
 }
 
 // ---- cluster-resident path (grid_resident.cuh) ---------------------------------------------------
-constexpr int RES_MR = 4;  // rows per thread: 64 rows x 256 columns per CTA
+// Rows per thread of the cluster-resident kernel: a CTA holds MR*16 rows x 256 columns.  MR = 3 leaves the
+// compiler enough registers to keep every loop-invariant address live (MR = 4 rematerialises them each step).
+constexpr int RES_MR_DEFAULT = 3;
+
+static int resident_mr() {
+    if (const char* e = getenv("FDTD2D_RESIDENT_MR")) {
+        const int v = atoi(e);
+        if (v >= 2 && v <= 4) return v;
+    }
+    return RES_MR_DEFAULT;
+}
 
 // Small fp32 grids that fit a thread-block cluster: whole-run residency instead of k-step tiles.
 static bool resident_eligible(fdtd2d_sim* s) {
     if (s->resident_ok >= 0) return s->resident_ok != 0;
     s->resident_ok = 0;
     if (s->dtype != FDTD2D_F32 || s->has_top_nb || s->has_bot_nb) return false;
-    if (s->C < 16 || s->C > RES_TW || s->Rg < 16 || s->Rg > 8 * RES_MR * RES_NW) return false;
+    const int mr = resident_mr(), band = mr * RES_NW;
+    if (s->C < 16 || s->C > RES_TW || s->Rg < 16 || s->Rg > 8 * band) return false;
     if (const char* e = getenv("FDTD2D_NO_RESIDENT"))
         if (atoi(e)) return false;
     // every source / probe cell may need a 4-cell slot in its CTA's slot frame
@@ -605,31 +616,50 @@ static bool resident_eligible(fdtd2d_sim* s) {
     for (const Cell& c : s->h_probe) per_grid[c.grid] += 1;
     for (int v : per_grid)
         if (v > RES_MAX_SLOTS) return false;
-    int n = 1;
-    while (n * RES_MR * RES_NW < s->Rg) n *= 2;
+    int n = (s->Rg + band - 1) / band;
     if (const char* e = getenv("FDTD2D_RESIDENT_CLUSTER")) {  // tuning knob: more, thinner bands per grid
         const int v = atoi(e);
-        if ((v == 1 || v == 2 || v == 4 || v == 8) && v >= n) n = v;
+        if (v >= n && v <= 8) n = v;
     }
-    int rpc = RES_MR * ((s->Rg + RES_MR * n - 1) / (RES_MR * n));
-    if (rpc < 6 || s->Rg - (n - 1) * rpc < 6) return false;  // first / last band hold the whole top / bottom ring
+    // The first and last CTA of a cluster also run the top / bottom boundary pass: give them `trim` rows fewer
+    // than the middle ones when the grid leaves room (rows: edge | (n-2) x rpc | what is left, at most edge).
+    int trim = 2 * mr;
+    if (const char* e = getenv("FDTD2D_RESIDENT_TRIM")) trim = std::max(0, atoi(e)) / mr * mr;
+    int rpc = 0, edge = 0, last = 0;
+    for (;; trim -= mr) {
+        if (n <= 2 || trim <= 0) {
+            rpc = edge = mr * ((s->Rg + mr * n - 1) / (mr * n));
+            last = s->Rg - (n - 1) * rpc;
+            break;
+        }
+        // smallest rpc (multiple of mr) with 2 * (rpc - trim) + (n - 2) * rpc >= Rg
+        rpc = mr * ((s->Rg + 2 * trim + mr * n - 1) / (mr * n));
+        edge = rpc - trim;
+        last = s->Rg - edge - (n - 2) * rpc;  // rows of the last CTA
+        if (rpc <= band && edge >= 6 && last >= 6 && last <= rpc) break;
+    }
+    if (n == 1) last = s->Rg;
+    if (rpc > band || edge < 6 || last < 6 || last > rpc) return false;  // first / last band hold the whole ring
+    s->resident_mr = mr;
     s->resident_cluster = n;
     s->resident_rpc = rpc;
+    s->resident_edge = edge;
     s->resident_ok = 1;
     return true;
 }
 
-static int launch_resident(fdtd2d_sim* s, int n_steps) {
+template <int MR> static int launch_resident_t(fdtd2d_sim* s, int n_steps) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[s->device % MAX_DEVICES];
-    const size_t smem = resident_smem_floats(RES_MR) * sizeof(float);
+    const size_t smem = resident_smem_floats(MR) * sizeof(float);
     if (!done) {
-        CUDA_TRY(cudaFuncSetAttribute(grid_resident_kernel<RES_MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(grid_resident_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
     }
     TilePlan tp;
     tp.k = n_steps;
     tp.CH = s->resident_rpc;
+    tp.CW = s->resident_edge;
     PassParams<float> p;
     fill_params(s, tp, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC, &p);
     cudaLaunchConfig_t cfg = {};
@@ -646,14 +676,22 @@ static int launch_resident(fdtd2d_sim* s, int n_steps) {
     cfg.numAttrs = 1;
     if (getenv("FDTD2D_DEBUG")) {
         int nc = -1;
-        cudaOccupancyMaxActiveClusters(&nc, grid_resident_kernel<RES_MR>, &cfg);
-        fprintf(stderr, "[fdtd2d] resident: %d grids x cluster %d (rpc %d), %zu B smem, max active clusters %d\n", s->batch,
-                s->resident_cluster, s->resident_rpc, smem, nc);
+        cudaOccupancyMaxActiveClusters(&nc, grid_resident_kernel<MR>, &cfg);
+        fprintf(stderr, "[fdtd2d] resident: %d grids x cluster %d (%d | %d rows per CTA, %d per thread), %zu B smem, max active clusters %d\n",
+                s->batch, s->resident_cluster, s->resident_edge, s->resident_rpc, MR, smem, nc);
     }
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_resident_kernel<RES_MR>, p));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_resident_kernel<MR>, p));
     s->launches += 1;
     s->cur ^= 1;
     return 0;
+}
+
+static int launch_resident(fdtd2d_sim* s, int n_steps) {
+    switch (s->resident_mr) {
+        case 2: return launch_resident_t<2>(s, n_steps);
+        case 3: return launch_resident_t<3>(s, n_steps);
+        default: return launch_resident_t<4>(s, n_steps);
+    }
 }
 
 static bool uses_hybrid(const fdtd2d_sim* s, int phases) {
@@ -1116,7 +1154,7 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
         s->step += n_steps;
         return 0;
     }
-    if (s->variant == 4 && n_steps > 0) return fail(FDTD2D_EINVAL, "variant 4 (cluster-resident) needs fp32, 16..256 columns, 16..512 rows, no slabs");
+    if (s->variant == 4 && n_steps > 0) return fail(FDTD2D_EINVAL, "variant 4 (cluster-resident) needs fp32, 16..256 columns, 16..384 rows, no slabs");
     int k = k_temporal ? k_temporal : (s->dtype == FDTD2D_F32 ? 8 : 4);
     if (s->has_top_nb || s->has_bot_nb) {
         k = std::min(k, s->halo);

@@ -12,13 +12,14 @@
 // Neighbours:
 //   columns across lanes            -> warp shuffles (rotating, so column 127 <-> 128 is one more select),
 //   rows across warps               -> one row per warp through shared memory (as in tile_fast.cuh),
-//   rows across the CTAs of a cluster -> DISTRIBUTED SHARED MEMORY: the first warp stores its first Ez row
-//     straight into the shared memory of the CTA above (st.shared::cluster), the last warp its last Hx row
-//     into the CTA below, and signals a remote mbarrier (arrive.release.cluster); only the one warp that
-//     needs the row waits (try_wait.acquire.cluster) and it does so just before its last row, so the
-//     ~200-cycle DSMEM latency hides behind its other rows.  Rows are double-buffered by step parity: a CTA
-//     can never run more than one step ahead of a neighbour, so two buffers suffice and there is NO
-//     cluster-wide barrier inside the time loop.
+//   rows across the CTAs of a cluster -> DISTRIBUTED SHARED MEMORY: the first warp sends its first Ez row
+//     straight from registers into the shared memory of the CTA above and the last warp its last Hx row into
+//     the CTA below with st.async (...mbarrier::complete_tx::bytes): the stores themselves signal the
+//     receiver's mbarrier, so there is no fence (a release.cluster arrive costs a MEMBAR.GPU) and no
+//     cluster-wide barrier inside the time loop.  Only the one warp that needs the row arms the barrier
+//     (arrive.expect_tx) and waits, just before its last row, so the DSMEM latency hides behind its other
+//     rows.  Rows are double-buffered by step parity: a CTA can never run more than one step ahead of a
+//     neighbour, so two buffers suffice.
 // Index ranges of the reference's slices (main.py:70,74 rows 0..R-2 / cols 0..C-2 for H, :27 rows 1..R-2 /
 // cols 1..C-2 for Ez) are imposed by zeroing the on-chip copy of the coefficient at the excluded cells:
 // x -/+ 0*(..) leaves x unchanged (for finite fields), so the inner loops carry no masks.  Every cell the Ez
@@ -77,31 +78,22 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void st_cluster4(uint32_t addr, const float* a) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3])
+// 16 bytes straight into another CTA's shared memory through the async proxy; the store itself signals the
+// destination CTA's mbarrier (complete_tx), so no fence and no separate arrive are needed.
+__device__ __forceinline__ void st_async4(uint32_t remote_addr, const float* a, uint32_t remote_bar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr),
+                 "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "r"(remote_bar)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok, spins = 0;
-    do {
-        if (++spins > (1u << 26)) __trap();  // never hang the GPU on a protocol bug
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
 
-// p.k = number of leapfrog steps of this launch; p.CH = rows per CTA (RPC); gridDim.x = batch * cluster size.
+// p.k = number of leapfrog steps of this launch; p.CW / p.CH = rows of the first / of every other CTA of a cluster
+// (multiples of MR); gridDim.x = batch * cluster size.
 template <int MR>
 __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const PassParams<float> p) {
-    static_assert(MR == 4, "the S2 lane mapping (4 rows x 8 ring cells per warp) assumes 4 rows per warp");
+    static_assert(MR >= 1 && MR <= 4, "the S2 lane mapping (one lane per ring cell, 8 lanes per row) covers at most 4 rows per warp");
     constexpr int TW = RES_TW, NW = RES_NW, TH = MR * NW, NT = NW * 32, LW = RES_LW, ZW = RES_ZW;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr uint32_t ROW_BYTES = TW * sizeof(float);  // one exchanged row: every lane sends 2 x 16 bytes
     // ring frames, addressed as float offsets from F: [LR0 | T0 | B0] = S0, the same again = S1, then T2, B2, slots
     constexpr int oLR = 0, oT = TH * ZW, oB = oT + 6 * TW, DELTA = oB + 6 * TW;
     constexpr int oT2 = 2 * DELTA, oB2 = oT2 + 6 * TW, oSlot = oB2 + 6 * TW;
@@ -123,9 +115,11 @@ __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const Pas
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const int crank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
     const int b = blockIdx.x / csize;
-    const int R = p.Rg, C = p.C, RPC = p.CH, n_steps = p.k;
-    const int row_lo = crank * RPC;
-    const int nrows = min(RPC, R - row_lo);
+    const int R = p.Rg, C = p.C, n_steps = p.k;
+    // bands: p.CW rows for the first CTA, p.CH for the others (the last one takes what is left).  The first and
+    // last CTA also run the top / bottom boundary pass, so the host gives them fewer rows.
+    const int row_lo = crank == 0 ? 0 : p.CW + (crank - 1) * p.CH;
+    const int nrows = crank == 0 ? min(p.CW, R) : min(p.CH, R - row_lo);
     const bool isTop = crank == 0, isBot = crank == csize - 1;
     const bool has_above = !isTop, has_below = !isBot;
     const int wl = (nrows - 1) / MR;  // the warp that holds the band's last row
@@ -224,20 +218,29 @@ __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const Pas
     // my groups' columns inside the LR frame of a row (-1: not a ring group)
     const int zo[2] = {cg[0] < LW ? cg[0] : (cg[0] >= cR0 && cg[0] < cR0 + RES_RW ? LW + cg[0] - cR0 : -1),
                        cg[1] >= cR0 && cg[1] < cR0 + RES_RW ? LW + cg[1] - cR0 : -1};
-    float* const zrow = F + oLR + li0 * ZW;  // LR frame (S0) of my first row; S1 is DELTA further
+    const bool z0 = zo[0] >= 0, z1 = zo[1] >= 0;
+    float* const zp0 = F + oLR + li0 * ZW + zo[0];  // S0 slot of my group 0 in the LR frame of my first row
+    float* const zp1 = F + oLR + li0 * ZW + zo[1];  // (S1 is DELTA further; never dereferenced when !z0 / !z1)
     // do my rows reach the top / bottom ring rows?
     const bool warp_tb = (isTop && row_lo + li0 <= 5) || (isBot && row_lo + li0 + MR - 1 >= R - 6 && row_lo + li0 < R);
-    // S2 (Mur left/right) of my warp's rows: lane -> (row l>>3, ring cell l&7)
+    // S2 (Mur left/right) of my warp's rows: lane -> (row l>>3, ring cell l&7).  Rows of the top / bottom ring
+    // are updated in their T / B frame, the others in the LR frame; S0 is always DELTA before S1.
     const int s2row = li0 + (l >> 3), s2k = l & 7, s2gi = row_lo + s2row;
-    const bool s2act = s2k < RING && s2row < nrows && s2gi >= 1 && s2gi <= R - 2;
-    float* const s2L = F + DELTA + oLR + s2row * ZW + s2k;                       // S1 of cell (row, k); S0 is DELTA before
-    float* const s2R = F + DELTA + oLR + s2row * ZW + LW + (C - 1 - s2k - cR0);  // S1 of cell (row, C-1-k)
+    const bool s2act = (l >> 3) < MR && s2k < RING && s2row < nrows && s2gi >= 1 && s2gi <= R - 2;
+    float *s2L, *s2R;  // S1 of cell (row, k) / (row, C-1-k)
+    if (isTop && s2gi <= 5) {
+        s2L = F + DELTA + oT + s2gi * TW + s2k, s2R = F + DELTA + oT + s2gi * TW + (C - 1 - s2k);
+    } else if (isBot && s2gi >= R - 6) {
+        s2L = F + DELTA + oB + (s2gi - (R - 6)) * TW + s2k, s2R = F + DELTA + oB + (s2gi - (R - 6)) * TW + (C - 1 - s2k);
+    } else {
+        s2L = F + DELTA + oLR + s2row * ZW + s2k, s2R = F + DELTA + oLR + s2row * ZW + LW + (C - 1 - s2k - cR0);
+    }
     // registers -> S0 / S1 frames (delta = 0 / DELTA)
     auto park = [&](int delta) {
 #pragma unroll
         for (int r = 0; r < MR; ++r) {
-            if (zo[0] >= 0) store4(zrow + delta + r * ZW + zo[0], e[r][0]);
-            if (zo[1] >= 0) store4(zrow + delta + r * ZW + zo[1], e[r][1]);
+            if (z0) store4(zp0 + delta + r * ZW, e[r][0]);
+            if (z1) store4(zp1 + delta + r * ZW, e[r][1]);
         }
         if (warp_tb) {
 #pragma unroll
@@ -253,35 +256,31 @@ __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const Pas
             }
         }
     };
-    // Finished value of every cell of the 6 top (or bottom) rows from their S0 / S1 frames: S2, S3 and S4 of
-    // SURVEY Appendix A evaluated per cell.  `i` is the depth from the edge (0 = edge row), `top` picks the frame.
+    // Finished value of every cell of the 6 top (or bottom) rows from their frames: S0 and S2 (S1 with the Mur
+    // left/right update already applied in place by the rows' owners); S3 and S4 of SURVEY Appendix A evaluated
+    // per cell.  `i` is the depth from the edge (0 = edge row), `top` picks the frame.
     auto tb_pass = [&](const bool top) {
         const float* A0 = F + (top ? oT : oB);
         const float* A1 = A0 + DELTA;
         float* A2 = F + (top ? oT2 : oB2);
         auto fr = [&](int i) { return (top ? i : 5 - i) * TW; };
-        auto s0 = [&](int i, int j) { return A0[fr(i) + j]; };
-        auto s1 = [&](int i, int j) { return A1[fr(i) + j]; };
-        auto S2v = [&](int i, int j) -> float {  // main.py:33-41, rows 1..R-2
-            if (i >= 1) {
-                if (j <= 4) return add_rn(s0(i, j + 1), mul_rn(coef, sub_rn(s1(i, j + 1), s0(i, j))));
-                if (j >= C - 5 && j <= C - 1) return add_rn(s0(i, j - 1), mul_rn(coef, sub_rn(s1(i, j - 1), s0(i, j))));
+        auto S3v = [&](int i, int j) -> float {  // main.py:43-51, rows 0..4 from the edge, columns 1..C-2
+            const float s2 = A1[fr(i) + j];
+            if (i <= 4 && j >= 1 && j <= C - 2) {
+                const float a = A0[fr(i + 1) + j], b2 = A1[fr(i + 1) + j], c0 = A0[fr(i) + j];
+                return add_rn(a, mul_rn(coef, sub_rn(b2, c0)));
             }
-            return s1(i, j);
-        };
-        auto S3v = [&](int i, int j) -> float {  // main.py:43-51, columns 1..C-2
-            if (i <= 4 && j >= 1 && j <= C - 2) return add_rn(s0(i + 1, j), mul_rn(coef, sub_rn(S2v(i + 1, j), s0(i, j))));
-            return S2v(i, j);
+            return s2;
         };
         const int j = tid & (TW - 1);
+        const bool corner_col = j <= 4 || (j >= C - 5 && j <= C - 1);
+        const int jn = j <= 4 ? j + 1 : j - 1;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
             const int i = (tid >> 8) + 2 * t;
-            float v;
-            if (i <= 4 && (j <= 4 || (j >= C - 5 && j <= C - 1)))  // main.py:54-61: reads of not-yet-processed cells
-                v = mul_rn(add_rn(S3v(i, j <= 4 ? j + 1 : j - 1), S3v(i + 1, j)), 0.5f);  // == sum / 2 exactly
-            else
-                v = S3v(i, j);
+            float v = S3v(i, j);
+            if (i <= 4 && corner_col)  // main.py:54-61: every read is of a not-yet-processed cell
+                v = mul_rn(add_rn(S3v(i, jn), S3v(i + 1, j)), 0.5f);  // == sum / 2 exactly
             A2[fr(i) + j] = v;
         }
     };
@@ -295,125 +294,128 @@ __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const Pas
     const bool edge_dn = (w == wl) && has_below;  // my last row needs the Ez row of the CTA below
     const bool edge_up = (w == 0) && has_above;   // my first row needs the Hx row of the CTA above
     const bool cta_tb = isTop || isBot;
+    const bool warp_on = li0 < nrows;  // warps past the end of the band only help with the top / bottom pass
+    {  // rows nobody publishes are still read as a neighbour row by the last active warp: keep them finite
+        const float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        store4(sEz + w * TW + cg[0], z), store4(sEz + w * TW + cg[1], z);
+        store4(sHx + w * TW + cg[0], z), store4(sHx + w * TW + cg[1], z);
+    }
+    // one row of the H half-step (main.py:69-74); dn = the Ez row below it
+    auto h_row = [&](const int r, const float (&dn)[2][4]) {
+        float c[2][4];
+        load4(sCh + (li0 + r) * TW + cg[0], c[0]);
+        load4(sCh + (li0 + r) * TW + cg[1], c[1]);
+        const float ra = __shfl_sync(FULL, e[r][0][0], (l + 1) & 31);
+        const float rb = __shfl_sync(FULL, e[r][1][0], (l + 1) & 31);
+        const float right3[2] = {l == 31 ? rb : ra, rb};
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float right = (q < 3) ? e[r][g][q < 3 ? q + 1 : 3] : right3[g];
+                hx[r][g][q] = sub_rn(hx[r][g][q], mul_rn(c[g][q], sub_rn(dn[g][q], e[r][g][q])));
+                hy[r][g][q] = add_rn(hy[r][g][q], mul_rn(c[g][q], sub_rn(right, e[r][g][q])));
+            }
+    };
+    // one row of the interior Ez update (main.py:21-27); up = the Hx row above it
+    auto e_row = [&](const int r, const float (&up)[2][4]) {
+        float c[2][4];
+        load4(sCe + (li0 + r) * TW + cg[0], c[0]);
+        load4(sCe + (li0 + r) * TW + cg[1], c[1]);
+        const float la = __shfl_sync(FULL, hy[r][0][3], (l + 31) & 31);
+        const float lb = __shfl_sync(FULL, hy[r][1][3], (l + 31) & 31);
+        const float left0[2] = {la, l == 0 ? la : lb};
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float left = (q > 0) ? hy[r][g][q > 0 ? q - 1 : 0] : left0[g];
+                const float curl = sub_rn(sub_rn(hy[r][g][q], left), sub_rn(hx[r][g][q], up[g][q]));
+                e[r][g][q] = add_rn(e[r][g][q], mul_rn(curl, c[g][q]));
+            }
+    };
     cluster_sync_all();  // every CTA's barriers are initialised before anyone signals them
 
 #pragma unroll 1
     for (int s = 0; s < n_steps; ++s) {
         const int par = s & 1;
         const uint32_t ph = (uint32_t)(s >> 1) & 1u;
-        // ---- publish the first Ez row of every warp; the band's first row also goes to the CTA above ----
-        store4(sEz + w * TW + cg[0], e[0][0]);
-        store4(sEz + w * TW + cg[1], e[0][1]);
-        if (edge_up) {
-            st_cluster4(up_rEz + (uint32_t)(par * TW + cg[0]) * 4u, e[0][0]);
-            st_cluster4(up_rEz + (uint32_t)(par * TW + cg[1]) * 4u, e[0][1]);
-            __syncwarp();
-            if (l == 0) mbar_arrive_cluster(up_barE + 8u * par);
-        }
-        park(0);  // S0: Ez is not changed by the H half-step
-        __syncthreads();
-        if (s > 0) sample_probes(p.step0 + s - 1);  // the previous step's frames are intact until the next park
-        // ---- H half-step (main.py:69-74) ---------------------------------------------------------------
-        const float* belowp = sEz + (w + 1 < NW ? w + 1 : NW - 1) * TW;
-#pragma unroll
-        for (int r = 0; r < MR; ++r) {
-            float dn[2][4];
-            if (r + 1 < MR) {
-#pragma unroll
-                for (int g = 0; g < 2; ++g)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) dn[g][q] = e[r + 1 < MR ? r + 1 : r][g][q];
-            } else {
-                if (edge_dn) {
-                    mbar_wait_cluster(&barE[par], ph);
-                    belowp = rEz + par * TW;
-                }
-                load4(belowp + cg[0], dn[0]);
-                load4(belowp + cg[1], dn[1]);
+        const long long step = p.step0 + s;
+        if (warp_on) {
+            // ---- publish the first Ez row of every warp; the band's first row also goes to the CTA above ----
+            store4(sEz + w * TW + cg[0], e[0][0]);
+            store4(sEz + w * TW + cg[1], e[0][1]);
+            if (edge_up) {
+                st_async4(up_rEz + (uint32_t)(par * TW + cg[0]) * 4u, e[0][0], up_barE + 8u * par);
+                st_async4(up_rEz + (uint32_t)(par * TW + cg[1]) * 4u, e[0][1], up_barE + 8u * par);
             }
-            float c[2][4];
-            load4(sCh + (li0 + r) * TW + cg[0], c[0]);
-            load4(sCh + (li0 + r) * TW + cg[1], c[1]);
-            const float ra = __shfl_sync(FULL, e[r][0][0], (l + 1) & 31);
-            const float rb = __shfl_sync(FULL, e[r][1][0], (l + 1) & 31);
-            const float right3[2] = {l == 31 ? rb : ra, rb};
-#pragma unroll
-            for (int g = 0; g < 2; ++g)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float right = (q < 3) ? e[r][g][q < 3 ? q + 1 : 3] : right3[g];
-                    hx[r][g][q] = sub_rn(hx[r][g][q], mul_rn(c[g][q], sub_rn(dn[g][q], e[r][g][q])));
-                    hy[r][g][q] = add_rn(hy[r][g][q], mul_rn(c[g][q], sub_rn(right, e[r][g][q])));
-                }
-        }
-        // ---- publish the last Hx row of every warp; the band's last row also goes to the CTA below -----
-        store4(sHx + w * TW + cg[0], hx[MR - 1][0]);
-        store4(sHx + w * TW + cg[1], hx[MR - 1][1]);
-        if (edge_dn) {
-            st_cluster4(dn_rHx + (uint32_t)(par * TW + cg[0]) * 4u, hx[MR - 1][0]);
-            st_cluster4(dn_rHx + (uint32_t)(par * TW + cg[1]) * 4u, hx[MR - 1][1]);
-            __syncwarp();
-            if (l == 0) mbar_arrive_cluster(dn_barH + 8u * par);
+            park(0);  // S0: Ez is not changed by the H half-step
         }
         __syncthreads();
-        // ---- interior Ez update (main.py:21-27), last row first so the remote row is needed last --------
-        const float* abovep = sHx + (w > 0 ? w - 1 : 0) * TW;
+        if (s > 0) sample_probes(step - 1);  // the previous step's frames are intact until the next park
+        if (warp_on) {
+            // ---- H half-step.  The warp whose last row needs the neighbour CTA's Ez row leaves that row for
+            // after the next barrier (no local warp reads its Hx), so the CTA never waits on the remote row. ----
 #pragma unroll
-        for (int rr = 0; rr < MR; ++rr) {
-            const int r = MR - 1 - rr;
-            float up[2][4];
-            if (r > 0) {
+            for (int r = 0; r + 1 < MR; ++r) h_row(r, e[r + 1 < MR ? r + 1 : r]);
+            if (!edge_dn) {
+                float dn[2][4];
+                load4(sEz + (w + 1 < NW ? w + 1 : NW - 1) * TW + cg[0], dn[0]);
+                load4(sEz + (w + 1 < NW ? w + 1 : NW - 1) * TW + cg[1], dn[1]);
+                h_row(MR - 1, dn);
+                store4(sHx + w * TW + cg[0], hx[MR - 1][0]);
+                store4(sHx + w * TW + cg[1], hx[MR - 1][1]);
+            }
+        }
+        __syncthreads();
+        if (warp_on) {
+            if (edge_dn) {
+                float dn[2][4];
+                if (l == 0) mbar_expect_tx(&barE[par], ROW_BYTES);
+                mbar_wait(&barE[par], ph);
+                load4(rEz + par * TW + cg[0], dn[0]);
+                load4(rEz + par * TW + cg[1], dn[1]);
+                h_row(MR - 1, dn);
+                st_async4(dn_rHx + (uint32_t)(par * TW + cg[0]) * 4u, hx[MR - 1][0], dn_barH + 8u * par);
+                st_async4(dn_rHx + (uint32_t)(par * TW + cg[1]) * 4u, hx[MR - 1][1], dn_barH + 8u * par);
+            }
+            // ---- interior Ez update, last row first so the row that needs the CTA above comes last ------------
 #pragma unroll
-                for (int g = 0; g < 2; ++g)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) up[g][q] = hx[r > 0 ? r - 1 : 0][g][q];
-            } else {
+            for (int r = MR - 1; r > 0; --r) e_row(r, hx[r > 0 ? r - 1 : 0]);
+            {
+                float up[2][4];
+                const float* abovep = sHx + (w > 0 ? w - 1 : 0) * TW;
                 if (edge_up) {
-                    mbar_wait_cluster(&barH[par], ph);
+                    if (l == 0) mbar_expect_tx(&barH[par], ROW_BYTES);
+                    mbar_wait(&barH[par], ph);
                     abovep = rHx + par * TW;
                 }
                 load4(abovep + cg[0], up[0]);
                 load4(abovep + cg[1], up[1]);
+                e_row(0, up);
             }
-            float c[2][4];
-            load4(sCe + (li0 + r) * TW + cg[0], c[0]);
-            load4(sCe + (li0 + r) * TW + cg[1], c[1]);
-            const float la = __shfl_sync(FULL, hy[r][0][3], (l + 31) & 31);
-            const float lb = __shfl_sync(FULL, hy[r][1][3], (l + 31) & 31);
-            const float left0[2] = {la, l == 0 ? la : lb};
+            // ---- S1 -> ring frames; source / probe cells outside the frames go through their slot -------------
+            park(DELTA);
+            if (spmask) {
 #pragma unroll
-            for (int g = 0; g < 2; ++g)
+                for (int r = 0; r < MR; ++r)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float left = (q > 0) ? hy[r][g][q > 0 ? q - 1 : 0] : left0[g];
-                    const float curl = sub_rn(sub_rn(hy[r][g][q], left), sub_rn(hx[r][g][q], up[g][q]));
-                    e[r][g][q] = add_rn(e[r][g][q], mul_rn(curl, c[g][q]));
-                }
-        }
-        const long long step = p.step0 + s;
-        // ---- S1 -> ring frames; source / probe cells outside the frames go through their slot -------------
-        park(DELTA);
-        if (spmask) {
-#pragma unroll
-            for (int r = 0; r < MR; ++r)
-#pragma unroll
-                for (int g = 0; g < 2; ++g)
-                    if (spmask >> (r * 2 + g) & 1u) {
-                        const int sl = slot_tbl[(li0 + r) * (TW / 4) + (cg[g] >> 2)];
-                        float* f = F + oSlot + sl * 4;
-                        store4(f, e[r][g]);
-                        if (step < p.amp_steps)
-                            for (int q = 0; q < 4; ++q) {  // source add (fdtd.py:34): float64 sum, then cast
-                                const int wv = slotW[sl * 4 + q];
-                                if (wv >= 0) f[q] = add_source(f[q], p.amp[(long long)wv * p.amp_steps + step]);
-                            }
-                        load4(f, e[r][g]);
-                    }
-        }
-        __syncwarp();
-        // ---- S2: Mur left/right (main.py:33-41) of my warp's own rows, one lane per ring cell; all cells are
-        // read before any is written (the reference's k order reads column k+1 before overwriting it) ------
-        {
+                    for (int g = 0; g < 2; ++g)
+                        if (spmask >> (r * 2 + g) & 1u) {
+                            const int sl = slot_tbl[(li0 + r) * (TW / 4) + (cg[g] >> 2)];
+                            float* f = F + oSlot + sl * 4;
+                            store4(f, e[r][g]);
+                            if (step < p.amp_steps)
+                                for (int q = 0; q < 4; ++q) {  // source add (fdtd.py:34): float64 sum, then cast
+                                    const int wv = slotW[sl * 4 + q];
+                                    if (wv >= 0) f[q] = add_source(f[q], p.amp[(long long)wv * p.amp_steps + step]);
+                                }
+                            load4(f, e[r][g]);
+                        }
+            }
+            __syncwarp();
+            // ---- S2: Mur left/right (main.py:33-41) of my warp's own rows, one lane per ring cell; all cells are
+            // read before any is written (the reference's k order reads column k+1 before overwriting it) ------
             float vl = 0.0f, vr = 0.0f;
             if (s2act) {
                 vl = add_rn(s2L[1 - DELTA], mul_rn(coef, sub_rn(s2L[1], s2L[-DELTA])));
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const Pas
             __syncwarp();
             if (s2act) *s2L = vl, *s2R = vr;
         }
-        // ---- top / bottom rows: S2, S3, S4 in one pass over their frames (all threads of the CTA) ------------
+        // ---- top / bottom rows: S3, S4 in one pass over their frames (all threads of the CTA) ----------------
         if (cta_tb) {
             __syncthreads();
             if (isTop) tb_pass(true);
@@ -440,21 +442,23 @@ __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const Pas
         else
             __syncwarp();
         // ---- finished ring -> registers ---------------------------------------------------------------------
-#pragma unroll
-        for (int r = 0; r < MR; ++r) {
-            if (zo[0] >= 0) load4(zrow + DELTA + r * ZW + zo[0], e[r][0]);
-            if (zo[1] >= 0) load4(zrow + DELTA + r * ZW + zo[1], e[r][1]);
-        }
-        if (warp_tb) {
+        if (warp_on) {
 #pragma unroll
             for (int r = 0; r < MR; ++r) {
-                const int gi = row_lo + li0 + r;
-                if (isTop && gi <= 5) {
-                    load4(F + oT2 + gi * TW + cg[0], e[r][0]);
-                    load4(F + oT2 + gi * TW + cg[1], e[r][1]);
-                } else if (isBot && gi >= R - 6 && gi < R) {
-                    load4(F + oB2 + (gi - (R - 6)) * TW + cg[0], e[r][0]);
-                    load4(F + oB2 + (gi - (R - 6)) * TW + cg[1], e[r][1]);
+                if (z0) load4(zp0 + DELTA + r * ZW, e[r][0]);
+                if (z1) load4(zp1 + DELTA + r * ZW, e[r][1]);
+            }
+            if (warp_tb) {
+#pragma unroll
+                for (int r = 0; r < MR; ++r) {
+                    const int gi = row_lo + li0 + r;
+                    if (isTop && gi <= 5) {
+                        load4(F + oT2 + gi * TW + cg[0], e[r][0]);
+                        load4(F + oT2 + gi * TW + cg[1], e[r][1]);
+                    } else if (isBot && gi >= R - 6 && gi < R) {
+                        load4(F + oB2 + (gi - (R - 6)) * TW + cg[0], e[r][0]);
+                        load4(F + oB2 + (gi - (R - 6)) * TW + cg[1], e[r][1]);
+                    }
                 }
             }
         }

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fdtd2d_b200 as fd, torch
 DT, DX = 5e-14, 1e-3
 R, C = int(os.environ.get("R", 256)), int(os.environ.get("C", 256))
-runs = [(4, b, 1000) for b in (1, 16, 32, 33, 34, 37, 66, 1024)] + [(2, 1024, 200)]
+runs = [(4, b, 1000) for b in [int(x) for x in os.environ.get("BS", "1,33,1024").split(",")]]
 for variant, B, n in runs:
     with fd.Simulation(R, C, np.float32, dt=DT, dx=DX, batch=B) as sim:
         sim.set_stream(torch.cuda.current_stream().cuda_stream)

@@ -45,15 +45,19 @@ def _problem(rng, R, C, scale=1e-3):
 
 # rows choose the cluster size (<=64: 1 CTA, <=128: 2, <=256: 4, <=512: 8) and the ragged last band;
 # columns choose where the right ring frame falls (second half, first half, straddling column 128)
-SHAPES = [(16, 16), (17, 33), (64, 256), (65, 255), (100, 128), (128, 129), (129, 131), (130, 136), (200, 200),
-          (256, 256), (255, 140), (260, 64), (300, 250), (512, 256), (511, 17), (37, 53), (96, 130), (72, 100)]
+SHAPES = [(16, 16), (17, 33), (48, 256), (49, 255), (64, 256), (65, 255), (100, 128), (128, 129), (129, 131), (130, 136),
+          (200, 200), (256, 256), (255, 140), (260, 64), (300, 250), (384, 256), (383, 17), (37, 53), (96, 130), (72, 100)]
+# (rows per thread, shape): MR = 4 bands hold 64 rows (up to 512 rows per grid), MR = 2 bands 32 rows
+CASES = [(3, s) for s in SHAPES] + [(4, s) for s in SHAPES[::2]] + [(4, (512, 256)), (4, (511, 17)), (2, (256, 256)),
+                                                                  (2, (33, 40)), (2, (250, 141))]
 
 
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("mr,shape", CASES)
 @pytest.mark.parametrize("nsteps", [1, 2, 37])
-def test_resident_vs_oracle(fd, oracle, shape, nsteps):
+def test_resident_vs_oracle(fd, oracle, mr, shape, nsteps, monkeypatch):
     c_oracle, npo = oracle
     R, C = shape
+    monkeypatch.setenv("FDTD2D_RESIDENT_MR", str(mr))
     rng = np.random.default_rng(R * 1009 + C * 13 + nsteps)
     eps, mu, Ez, Hx, Hy = _problem(rng, R, C)
     ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(np.float32))
@@ -150,7 +154,7 @@ def test_resident_demo_golden_and_pieces(fd, golden_dir):
         assert_bits(Hy, g["Hy"], "Hy")
 
 
-@pytest.mark.parametrize("cluster", [2, 4, 8])
+@pytest.mark.parametrize("cluster", [3, 4, 5, 7, 8])
 def test_resident_cluster_size_knob(fd, oracle, cluster, monkeypatch):
     """More, thinner bands per grid (FDTD2D_RESIDENT_CLUSTER) must not change a bit."""
     c_oracle, npo = oracle
@@ -178,7 +182,7 @@ def test_resident_cluster_size_knob(fd, oracle, cluster, monkeypatch):
 
 
 def test_resident_not_eligible_is_an_error_when_forced(fd):
-    for (R, C, dtype) in [(64, 300, np.float32), (600, 64, np.float32), (64, 64, np.float64), (12, 64, np.float32), (257, 64, np.float32)]:
+    for (R, C, dtype) in [(64, 300, np.float32), (600, 64, np.float32), (64, 64, np.float64), (12, 64, np.float32), (386, 64, np.float32)]:
         with fd.Simulation(R, C, dtype, dt=DT, dx=DX) as sim:
             sim.set_kernel_variant(4)
             sim.set_materials(*fd.material_init(None, R, C))
