@@ -120,7 +120,7 @@ struct fdtd2d_sim {
     int sm_count = 0;
     int open_pass_k = 0;  // > 0 between fdtd2d_pass_begin and fdtd2d_pass_end
     int resident_ok = -1;     // cluster-resident kernel usable for this handle? (-1 = not decided yet)
-    int resident_cluster = 0, resident_rpc = 0, resident_edge = 0, resident_mr = 0;  // CTAs per grid, rows per middle / first CTA, rows per thread
+    int resident_cluster = 0, resident_rpc = 0, resident_edge = 0, resident_cfg = 0;  // CTAs per grid, rows per middle / first CTA, kResCfgs index
     unsigned char* d_gray = nullptr;  // snapshot background (Rl x C per grid)
     unsigned char* d_rgb = nullptr;   // one rendered frame (Rl x C x 3)
     double* d_lut = nullptr;          // 256 x 3 colormap
@@ -589,16 +589,21 @@ static int launch_hybrid(fdtd2d_sim* s, int k, int part) {
 }
 
 // ---- cluster-resident path (grid_resident.cuh) ---------------------------------------------------
-// Rows per thread of the cluster-resident kernel: a CTA holds MR*16 rows x 256 columns.  MR = 3 leaves the
-// compiler enough registers to keep every loop-invariant address live (MR = 4 rematerialises them each step).
-constexpr int RES_MR_DEFAULT = 3;
+// Shapes of the cluster-resident kernel: MR rows per thread x NW warps -> a CTA holds MR*NW rows x 256 columns.
+// 3 x 16 is the measured best on B200 for 256^2 grids (profiles/); the others are kept selectable for tuning
+// (FDTD2D_RESIDENT_CFG) and are covered by the parity tests.
+struct ResCfg {
+    int MR, NW;
+};
+static const ResCfg kResCfgs[] = {{3, 16}, {4, 12}, {2, 16}, {4, 8}, {3, 12}};
+constexpr int N_RES_CFG = sizeof(kResCfgs) / sizeof(kResCfgs[0]);
 
-static int resident_mr() {
-    if (const char* e = getenv("FDTD2D_RESIDENT_MR")) {
+static int resident_cfg() {
+    if (const char* e = getenv("FDTD2D_RESIDENT_CFG")) {
         const int v = atoi(e);
-        if (v >= 2 && v <= 4) return v;
+        if (v >= 0 && v < N_RES_CFG) return v;
     }
-    return RES_MR_DEFAULT;
+    return 0;
 }
 
 // Small fp32 grids that fit a thread-block cluster: whole-run residency instead of k-step tiles.
@@ -606,7 +611,7 @@ static bool resident_eligible(fdtd2d_sim* s) {
     if (s->resident_ok >= 0) return s->resident_ok != 0;
     s->resident_ok = 0;
     if (s->dtype != FDTD2D_F32 || s->has_top_nb || s->has_bot_nb) return false;
-    const int mr = resident_mr(), band = mr * RES_NW;
+    const int rcfg = resident_cfg(), mr = kResCfgs[rcfg].MR, band = mr * kResCfgs[rcfg].NW;
     if (s->C < 16 || s->C > RES_TW || s->Rg < 16 || s->Rg > 8 * band) return false;
     if (const char* e = getenv("FDTD2D_NO_RESIDENT"))
         if (atoi(e)) return false;
@@ -623,7 +628,7 @@ static bool resident_eligible(fdtd2d_sim* s) {
     }
     // The first and last CTA of a cluster also run the top / bottom boundary pass: give them `trim` rows fewer
     // than the middle ones when the grid leaves room (rows: edge | (n-2) x rpc | what is left, at most edge).
-    int trim = 2 * mr;
+    int trim = 4 * mr;
     if (const char* e = getenv("FDTD2D_RESIDENT_TRIM")) trim = std::max(0, atoi(e)) / mr * mr;
     int rpc = 0, edge = 0, last = 0;
     for (;; trim -= mr) {
@@ -640,7 +645,7 @@ static bool resident_eligible(fdtd2d_sim* s) {
     }
     if (n == 1) last = s->Rg;
     if (rpc > band || edge < 6 || last < 6 || last > rpc) return false;  // first / last band hold the whole ring
-    s->resident_mr = mr;
+    s->resident_cfg = rcfg;
     s->resident_cluster = n;
     s->resident_rpc = rpc;
     s->resident_edge = edge;
@@ -648,12 +653,12 @@ static bool resident_eligible(fdtd2d_sim* s) {
     return true;
 }
 
-template <int MR> static int launch_resident_t(fdtd2d_sim* s, int n_steps) {
+template <int MR, int NW> static int launch_resident_t(fdtd2d_sim* s, int n_steps) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[s->device % MAX_DEVICES];
-    const size_t smem = resident_smem_floats(MR) * sizeof(float);
+    const size_t smem = resident_smem_floats(MR, NW) * sizeof(float);
     if (!done) {
-        CUDA_TRY(cudaFuncSetAttribute(grid_resident_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(grid_resident_kernel<MR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
     }
     TilePlan tp;
@@ -664,7 +669,7 @@ template <int MR> static int launch_resident_t(fdtd2d_sim* s, int n_steps) {
     fill_params(s, tp, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC, &p);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(s->batch * s->resident_cluster));
-    cfg.blockDim = dim3(RES_NW * 32);
+    cfg.blockDim = dim3(NW * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s->stream;
     cudaLaunchAttribute attr[1];
@@ -676,21 +681,23 @@ template <int MR> static int launch_resident_t(fdtd2d_sim* s, int n_steps) {
     cfg.numAttrs = 1;
     if (getenv("FDTD2D_DEBUG")) {
         int nc = -1;
-        cudaOccupancyMaxActiveClusters(&nc, grid_resident_kernel<MR>, &cfg);
-        fprintf(stderr, "[fdtd2d] resident: %d grids x cluster %d (%d | %d rows per CTA, %d per thread), %zu B smem, max active clusters %d\n",
-                s->batch, s->resident_cluster, s->resident_edge, s->resident_rpc, MR, smem, nc);
+        cudaOccupancyMaxActiveClusters(&nc, grid_resident_kernel<MR, NW>, &cfg);
+        fprintf(stderr, "[fdtd2d] resident: %d grids x cluster %d (%d | %d rows per CTA, %d x %d warps), %zu B smem, max active clusters %d\n",
+                s->batch, s->resident_cluster, s->resident_edge, s->resident_rpc, MR, NW, smem, nc);
     }
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_resident_kernel<MR>, p));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_resident_kernel<MR, NW>, p));
     s->launches += 1;
     s->cur ^= 1;
     return 0;
 }
 
 static int launch_resident(fdtd2d_sim* s, int n_steps) {
-    switch (s->resident_mr) {
-        case 2: return launch_resident_t<2>(s, n_steps);
-        case 3: return launch_resident_t<3>(s, n_steps);
-        default: return launch_resident_t<4>(s, n_steps);
+    switch (s->resident_cfg) {
+        case 1: return launch_resident_t<4, 12>(s, n_steps);
+        case 2: return launch_resident_t<2, 16>(s, n_steps);
+        case 3: return launch_resident_t<4, 8>(s, n_steps);
+        case 4: return launch_resident_t<3, 12>(s, n_steps);
+        default: return launch_resident_t<3, 16>(s, n_steps);
     }
 }
 

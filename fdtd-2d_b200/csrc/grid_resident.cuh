@@ -4,36 +4,37 @@
 // (BASELINE configs[4]: 1024 x 256^2) and for the reference demo grid (fdtd.py:14-19, 200^2), where
 // overlapped tiling has nothing to amortise: every tile of such a grid touches the Mur ring.
 //
-// Work layout.  A cluster of n CTAs (n = 1, 2, 4 or 8) splits the rows of one grid into n bands of RPC
-// rows (RPC a multiple of MR; at most MR*16 rows per CTA, at most 256 columns).  Inside a CTA warp w owns
-// rows [w*MR, (w+1)*MR) of the band and lane l owns columns [4l, 4l+4) and [128+4l, 128+4l+4): MR x 8
-// cells of Ez, Hx, Hy per thread live in REGISTERS from the first step to the last.  The coefficient maps
-// dt/(eps*dx), dt/(mu*dx) live in shared memory (each thread re-reads only the slots it wrote).
-// Neighbours:
-//   columns across lanes            -> warp shuffles (rotating, so column 127 <-> 128 is one more select),
-//   rows across warps               -> one row per warp through shared memory (as in tile_fast.cuh),
-//   rows across the CTAs of a cluster -> DISTRIBUTED SHARED MEMORY: the first warp sends its first Ez row
-//     straight from registers into the shared memory of the CTA above and the last warp its last Hx row into
-//     the CTA below with st.async (...mbarrier::complete_tx::bytes): the stores themselves signal the
-//     receiver's mbarrier, so there is no fence (a release.cluster arrive costs a MEMBAR.GPU) and no
-//     cluster-wide barrier inside the time loop.  Only the one warp that needs the row arms the barrier
-//     (arrive.expect_tx) and waits, just before its last row, so the DSMEM latency hides behind its other
-//     rows.  Rows are double-buffered by step parity: a CTA can never run more than one step ahead of a
-//     neighbour, so two buffers suffice.
+// Work layout.  A cluster of n <= 8 CTAs splits the rows of one grid into n bands (multiples of MR rows, at most
+// MR*NW rows, at most 256 columns; the first and last band are shorter because those CTAs also run the top /
+// bottom boundary pass).  Inside a CTA warp w owns rows [w*MR, (w+1)*MR) of the band and lane l owns columns
+// [4l, 4l+4) and [128+4l, 128+4l+4): MR x 8 cells of Ez, Hx, Hy per thread live in REGISTERS from the first step
+// to the last.  The coefficient maps dt/(eps*dx), dt/(mu*dx) live in shared memory (each thread re-reads only the
+// slots it wrote).  Neighbours:
+//   columns across lanes -> warp shuffles (rotating, so column 127 <-> 128 is one more select);
+//   rows across warps    -> every warp publishes its first and last Ez row in shared memory (double-buffered by
+//     step parity) and keeps a REDUNDANT copy of the Hx row just above its rows, which it advances itself from the
+//     Ez row it receives.  So only Ez is exchanged, once per step, and a step has ONE CTA-wide barrier;
+//   rows across the CTAs of a cluster -> DISTRIBUTED SHARED MEMORY: the band's first / last Ez row goes straight
+//     from registers into the neighbour CTA's shared memory with st.async (...mbarrier::complete_tx::bytes): the
+//     stores themselves signal the receiver's mbarrier, so there is no fence (a release.cluster arrive costs a
+//     MEMBAR.GPU) and no cluster-wide barrier inside the time loop.  Only the one warp that needs the row arms
+//     the barrier (arrive.expect_tx) and waits, after all its other rows.  A CTA can never run more than one step
+//     ahead of a neighbour, so two buffers per direction suffice.
 // Index ranges of the reference's slices (main.py:70,74 rows 0..R-2 / cols 0..C-2 for H, :27 rows 1..R-2 /
 // cols 1..C-2 for Ez) are imposed by zeroing the on-chip copy of the coefficient at the excluded cells:
 // x -/+ 0*(..) leaves x unchanged (for finite fields), so the inner loops carry no masks.  Every cell the Ez
 // mask excludes is overwritten by the boundary stages below, exactly as in the reference.
 //
-// Boundary stages (main.py:29-61) run on small shared-memory frames holding only the ring: the 6 outermost
-// columns on each side for every row (frames L, R), rows 0..5 (frame T, first CTA) and R-6..R-1 (frame B,
-// last CTA), each as S0 (Ez before the step, the reference's Ez_prev) and S1 (after the interior update).
-// S2 (Mur left/right) is evaluated with one thread per ring cell, S3 (top/bottom) with one thread per column
-// in the reference's k order, S4 (5x5 corner means, a Jacobi sweep: every read is of a not-yet-processed
-// cell) with one thread per corner cell; then the owners pull the finished ring back into registers.
-// Source cells and probes that are not in a ring frame get a 4-cell slot in a small frame the same way, so
-// the float64 source add (fdtd.py:34) and the probe sampling work on shared memory, not on registers.
-// Results are bit-identical to the tile kernels and to the oracle.
+// Boundary stages (main.py:29-61) run on small shared-memory frames holding only the ring: the outermost columns
+// of every row (frame LR), rows 0..5 (frame T, first CTA) and R-6..R-1 (frame B, last CTA), each as S0 (Ez before
+// the step, the reference's Ez_prev) and S1 (after the interior update).
+//   S2 (Mur left/right): by the warp that owns the row, one lane per ring cell, in place, no CTA barrier;
+//   S3 + S4 (Mur top/bottom, 5x5 corner means -- a Jacobi sweep, every read is of a not-yet-processed cell): one
+//     pass of all threads of the first / last CTA over the six rows, each cell evaluated from S0 and S2;
+// then the owners pull the finished ring back into registers.  Source cells and probes that are not in a ring
+// frame get a 4-cell slot: the owner thread parks the group there, adds the float64 source amplitude
+// (fdtd.py:34) and reloads it; probes are sampled from the frames after the next step's barrier.
+// Results are bit-identical to the tile kernels and to the reference (tests/test_gpu_resident.py).
 #pragma once
 #include "common.cuh"
 #include "tile_edge.cuh"
@@ -42,16 +43,16 @@
 namespace fdtd2d {
 
 constexpr int RES_TW = 256;         // columns per CTA (two 128-column halves per warp row)
-constexpr int RES_NW = 16;          // warps per CTA
 constexpr int RES_MAX_SLOTS = 255;  // 4-cell slots for source / probe cells outside the ring frames (per CTA)
 constexpr int RES_MAX_CELLS = 256;  // probes per CTA; sources inside ring frames per CTA
 constexpr int RES_LW = 8, RES_RW = 12, RES_ZW = RES_LW + RES_RW;  // left | right ring frame columns of one row
 
 // shared-memory floats of one CTA (see the carve-up at the top of the kernel)
-__host__ __device__ constexpr size_t resident_smem_floats(int MR) {
+__host__ __device__ constexpr size_t resident_smem_floats(int MR, int RES_NW) {
     return (size_t)2 * MR * RES_NW * RES_TW                   // coefficient maps
-           + 2 * RES_NW * RES_TW                              // row exchange between warps
-           + 4 * RES_TW                                       // row exchange between CTAs (2 rows x 2 parities)
+           + RES_TW                                           // dt/(mu*dx) of the row above the band
+           + 4 * RES_NW * RES_TW                              // Ez rows exchanged between warps: 2 parities x (first, last)
+           + 4 * RES_TW                                       // Ez rows from the neighbour CTAs: 2 parities x (below, above)
            + 2 * (MR * RES_NW * RES_ZW + 12 * RES_TW)         // S0 and S1 frames: LR, T, B
            + 12 * RES_TW                                      // T2, B2: finished top / bottom rows
            + 2 * 256 * 4                                      // slot frame + per-slot source waveforms
@@ -88,10 +89,13 @@ __device__ __forceinline__ void st_async4(uint32_t remote_addr, const float* a, 
 
 // p.k = number of leapfrog steps of this launch; p.CW / p.CH = rows of the first / of every other CTA of a cluster
 // (multiples of MR); gridDim.x = batch * cluster size.
-template <int MR>
-__global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const PassParams<float> p) {
+// MR rows per thread, NW warps per CTA: a CTA holds a band of at most MR * NW rows.
+template <int MR, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassParams<float> p) {
     static_assert(MR >= 1 && MR <= 4, "the S2 lane mapping (one lane per ring cell, 8 lanes per row) covers at most 4 rows per warp");
-    constexpr int TW = RES_TW, NW = RES_NW, TH = MR * NW, NT = NW * 32, LW = RES_LW, ZW = RES_ZW;
+    static_assert(resident_smem_floats(MR, NW) * 4 + 256 <= 232448, "band does not fit shared memory");
+    static_assert(NW * 32 >= RES_MAX_CELLS, "one thread per probe / ring source");
+    constexpr int TW = RES_TW, TH = MR * NW, NT = NW * 32, LW = RES_LW, ZW = RES_ZW;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr uint32_t ROW_BYTES = TW * sizeof(float);  // one exchanged row: every lane sends 2 x 16 bytes
     // ring frames, addressed as float offsets from F: [LR0 | T0 | B0] = S0, the same again = S1, then T2, B2, slots
@@ -100,16 +104,15 @@ __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const Pas
     extern __shared__ __align__(16) unsigned char smem_res[];
     float* sCe = reinterpret_cast<float*>(smem_res);  // [TH][TW] dt/(eps*dx), zero where Ez is not updated
     float* sCh = sCe + TH * TW;                       // [TH][TW] dt/(mu*dx), zero where H is not updated
-    float* sEz = sCh + TH * TW;                       // [NW][TW] first Ez row of every warp
-    float* sHx = sEz + NW * TW;                       // [NW][TW] last Hx row of every warp
-    float* rEz = sHx + NW * TW;                       // [2][TW] first Ez row of the CTA below (it writes it)
-    float* rHx = rEz + 2 * TW;                        // [2][TW] last Hx row of the CTA above (it writes it)
-    float* F = rHx + 2 * TW;                          // ring frames (see the offsets above)
+    float* sChA = sCh + TH * TW;                      // [TW] dt/(mu*dx) of the row above the band (zero for the first CTA)
+    float* sEx = sChA + TW;                           // [2 parities][first | last][NW][TW] Ez rows published by the warps
+    float* rEz = sEx + 4 * NW * TW;                   // [2 parities][from below | from above][TW] written by the neighbour CTAs
+    float* F = rEz + 4 * TW;                          // ring frames (see the offsets above)
     int* slotW = reinterpret_cast<int*>(F + oSlot + 256 * 4);  // [256][4] waveform of a slot cell's source or -1
     int* plist = slotW + 256 * 4;                     // [RES_MAX_CELLS][2] probes of this band: frame offset, trace column
     int* rlist = plist + RES_MAX_CELLS * 2;           // [RES_MAX_CELLS][2] sources inside ring frames: offset, wave*amp_steps
     unsigned char* slot_tbl = reinterpret_cast<unsigned char*>(rlist + RES_MAX_CELLS * 2);  // [TH][TW/4] slot or 0xFF
-    __shared__ __align__(8) uint64_t barE[2], barH[2];
+    __shared__ __align__(8) uint64_t barB[2], barA[2];  // "the row from below / above of this parity has landed"
     __shared__ int s_counts[2];  // probes, ring sources of this band
 
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
@@ -159,6 +162,31 @@ __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const Pas
         }
     }
 
+    // Redundant copy of the Hx row just above my rows (owned by the warp / CTA above): every warp advances it
+    // itself from the Ez row it receives, so the Ez update needs no second exchange and no second barrier.
+    float hxa[2][4];
+    {
+        const int ga = row_lo + li0 - 1;  // global row above my first row
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            float cha[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hxa[g][q] = cha[q] = 0.0f;
+            if (ga >= 0 && li0 < nrows && cg[g] < p.pitch) {
+                const long long o = gbase + (long long)ga * p.pitch + cg[g];
+                ldg4(p.in[1] + o, hxa[g]);
+                if (w == 0) ldg4(p.ch + o, cha);
+            }
+            if (w == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (cg[g] + q > C - 2) cha[q] = 0.0f;
+                store4(sChA + cg[g], cha);
+            }
+        }
+    }
+    const float* const chAp = (w == 0 ? sChA : sCh + (li0 - 1) * TW);  // dt/(mu*dx) of that row
+
     // ---- set-up: barriers; where the source / probe cells of this band live in shared memory --------
     for (int i = tid; i < TH * (TW / 4) / 4; i += NT) reinterpret_cast<unsigned*>(slot_tbl)[i] = 0xffffffffu;
     for (int i = tid; i < 256 * 4; i += NT) slotW[i] = -1;
@@ -173,7 +201,7 @@ __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const Pas
         return -1;  // not in a ring frame: the cell gets a slot
     };
     if (tid == 0) {
-        mbar_init(&barE[0], 1), mbar_init(&barE[1], 1), mbar_init(&barH[0], 1), mbar_init(&barH[1], 1);
+        mbar_init(&barB[0], 1), mbar_init(&barB[1], 1), mbar_init(&barA[0], 1), mbar_init(&barA[1], 1);
         fence_mbar_init();
         int n_slot = 0, n_prb = 0, n_rsrc = 0;
         auto slot_of = [&](int lr, int col) -> int {
@@ -272,16 +300,28 @@ __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const Pas
             }
             return s2;
         };
-        const int j = tid & (TW - 1);
-        const bool corner_col = j <= 4 || (j >= C - 5 && j <= C - 1);
-        const int jn = j <= 4 ? j + 1 : j - 1;
+        static_assert((6 * TW) % NT == 0, "the six rows split evenly over the threads");
+        if constexpr (NT % TW == 0) {  // a thread keeps its column: the corner test is hoisted out of the cell loop
+            const int j = tid & (TW - 1);
+            const bool corner_col = j <= 4 || (j >= C - 5 && j <= C - 1);
+            const int jn = j <= 4 ? j + 1 : j - 1;
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const int i = (tid >> 8) + 2 * t;
-            float v = S3v(i, j);
-            if (i <= 4 && corner_col)  // main.py:54-61: every read is of a not-yet-processed cell
-                v = mul_rn(add_rn(S3v(i, jn), S3v(i + 1, j)), 0.5f);  // == sum / 2 exactly
-            A2[fr(i) + j] = v;
+            for (int t = 0; t < 6 * TW / NT; ++t) {
+                const int i = tid / TW + t * (NT / TW);
+                float v = S3v(i, j);
+                if (i <= 4 && corner_col)  // main.py:54-61: every read is of a not-yet-processed cell
+                    v = mul_rn(add_rn(S3v(i, jn), S3v(i + 1, j)), 0.5f);  // == sum / 2 exactly
+                A2[fr(i) + j] = v;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 6 * TW / NT; ++t) {
+                const int c = tid + t * NT, i = c / TW, j = c & (TW - 1);
+                float v = S3v(i, j);
+                if (i <= 4 && (j <= 4 || (j >= C - 5 && j <= C - 1)))
+                    v = mul_rn(add_rn(S3v(i, j <= 4 ? j + 1 : j - 1), S3v(i + 1, j)), 0.5f);
+                A2[fr(i) + j] = v;
+            }
         }
     };
     auto sample_probes = [&](long long step) {
@@ -289,16 +329,16 @@ __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const Pas
     };
     // addresses in the neighbours' shared memory
     const uint32_t up_rank = has_above ? crank - 1 : crank, dn_rank = has_below ? crank + 1 : crank;
-    const uint32_t up_rEz = map_to_rank(smem_u32(rEz), up_rank), up_barE = map_to_rank(smem_u32(&barE[0]), up_rank);
-    const uint32_t dn_rHx = map_to_rank(smem_u32(rHx), dn_rank), dn_barH = map_to_rank(smem_u32(&barH[0]), dn_rank);
+    const uint32_t up_rEz = map_to_rank(smem_u32(rEz), up_rank), up_barB = map_to_rank(smem_u32(&barB[0]), up_rank);
+    const uint32_t dn_rEz = map_to_rank(smem_u32(rEz), dn_rank), dn_barA = map_to_rank(smem_u32(&barA[0]), dn_rank);
     const bool edge_dn = (w == wl) && has_below;  // my last row needs the Ez row of the CTA below
     const bool edge_up = (w == 0) && has_above;   // my first row needs the Hx row of the CTA above
     const bool cta_tb = isTop || isBot;
     const bool warp_on = li0 < nrows;  // warps past the end of the band only help with the top / bottom pass
     {  // rows nobody publishes are still read as a neighbour row by the last active warp: keep them finite
         const float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        store4(sEz + w * TW + cg[0], z), store4(sEz + w * TW + cg[1], z);
-        store4(sHx + w * TW + cg[0], z), store4(sHx + w * TW + cg[1], z);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) store4(sEx + (i * NW + w) * TW + cg[0], z), store4(sEx + (i * NW + w) * TW + cg[1], z);
     }
     // one row of the H half-step (main.py:69-74); dn = the Ez row below it
     auto h_row = [&](const int r, const float (&dn)[2][4]) {
@@ -341,59 +381,62 @@ __global__ void __launch_bounds__(RES_NW * 32, 1) grid_resident_kernel(const Pas
         const int par = s & 1;
         const uint32_t ph = (uint32_t)(s >> 1) & 1u;
         const long long step = p.step0 + s;
+        float* const xF = sEx + (par * 2 * NW + w) * TW;  // my slot for the first row; the last row is NW rows further
         if (warp_on) {
-            // ---- publish the first Ez row of every warp; the band's first row also goes to the CTA above ----
-            store4(sEz + w * TW + cg[0], e[0][0]);
-            store4(sEz + w * TW + cg[1], e[0][1]);
-            if (edge_up) {
-                st_async4(up_rEz + (uint32_t)(par * TW + cg[0]) * 4u, e[0][0], up_barE + 8u * par);
-                st_async4(up_rEz + (uint32_t)(par * TW + cg[1]) * 4u, e[0][1], up_barE + 8u * par);
+            // ---- publish my first and last Ez rows; the band's first / last row also go to the neighbour CTAs ----
+            store4(xF + cg[0], e[0][0]);
+            store4(xF + cg[1], e[0][1]);
+            store4(xF + NW * TW + cg[0], e[MR - 1][0]);
+            store4(xF + NW * TW + cg[1], e[MR - 1][1]);
+            if (edge_up) {  // -> "row from below" of the CTA above
+                st_async4(up_rEz + (uint32_t)(par * 2 * TW + cg[0]) * 4u, e[0][0], up_barB + 8u * par);
+                st_async4(up_rEz + (uint32_t)(par * 2 * TW + cg[1]) * 4u, e[0][1], up_barB + 8u * par);
+            }
+            if (edge_dn) {  // -> "row from above" of the CTA below
+                st_async4(dn_rEz + (uint32_t)((par * 2 + 1) * TW + cg[0]) * 4u, e[MR - 1][0], dn_barA + 8u * par);
+                st_async4(dn_rEz + (uint32_t)((par * 2 + 1) * TW + cg[1]) * 4u, e[MR - 1][1], dn_barA + 8u * par);
             }
             park(0);  // S0: Ez is not changed by the H half-step
         }
-        __syncthreads();
+        __syncthreads();  // the only CTA-wide barrier of a step away from the top / bottom ring
         if (s > 0) sample_probes(step - 1);  // the previous step's frames are intact until the next park
         if (warp_on) {
-            // ---- H half-step.  The warp whose last row needs the neighbour CTA's Ez row leaves that row for
-            // after the next barrier (no local warp reads its Hx), so the CTA never waits on the remote row. ----
+            // ---- H half-step; the rows that need a neighbour CTA's Ez row come last ---------------------------
 #pragma unroll
             for (int r = 0; r + 1 < MR; ++r) h_row(r, e[r + 1 < MR ? r + 1 : r]);
-            if (!edge_dn) {
-                float dn[2][4];
-                load4(sEz + (w + 1 < NW ? w + 1 : NW - 1) * TW + cg[0], dn[0]);
-                load4(sEz + (w + 1 < NW ? w + 1 : NW - 1) * TW + cg[1], dn[1]);
-                h_row(MR - 1, dn);
-                store4(sHx + w * TW + cg[0], hx[MR - 1][0]);
-                store4(sHx + w * TW + cg[1], hx[MR - 1][1]);
-            }
-        }
-        __syncthreads();
-        if (warp_on) {
-            if (edge_dn) {
-                float dn[2][4];
-                if (l == 0) mbar_expect_tx(&barE[par], ROW_BYTES);
-                mbar_wait(&barE[par], ph);
-                load4(rEz + par * TW + cg[0], dn[0]);
-                load4(rEz + par * TW + cg[1], dn[1]);
-                h_row(MR - 1, dn);
-                st_async4(dn_rHx + (uint32_t)(par * TW + cg[0]) * 4u, hx[MR - 1][0], dn_barH + 8u * par);
-                st_async4(dn_rHx + (uint32_t)(par * TW + cg[1]) * 4u, hx[MR - 1][1], dn_barH + 8u * par);
-            }
-            // ---- interior Ez update, last row first so the row that needs the CTA above comes last ------------
-#pragma unroll
-            for (int r = MR - 1; r > 0; --r) e_row(r, hx[r > 0 ? r - 1 : 0]);
             {
-                float up[2][4];
-                const float* abovep = sHx + (w > 0 ? w - 1 : 0) * TW;
+                float dn[2][4];
+                const float* belowp = xF + (w + 1 < NW ? TW : 0);  // first row of the warp below
+                if (edge_dn) {
+                    if (l == 0) mbar_expect_tx(&barB[par], ROW_BYTES);
+                    mbar_wait(&barB[par], ph);
+                    belowp = rEz + par * 2 * TW;
+                }
+                load4(belowp + cg[0], dn[0]);
+                load4(belowp + cg[1], dn[1]);
+                h_row(MR - 1, dn);
+            }
+            {   // my copy of the Hx row above my rows (main.py:69-70 for that row)
+                float up[2][4], c[2][4];
+                const float* abovep = xF + NW * TW - (w > 0 ? TW : 0);  // last row of the warp above
                 if (edge_up) {
-                    if (l == 0) mbar_expect_tx(&barH[par], ROW_BYTES);
-                    mbar_wait(&barH[par], ph);
-                    abovep = rHx + par * TW;
+                    if (l == 0) mbar_expect_tx(&barA[par], ROW_BYTES);
+                    mbar_wait(&barA[par], ph);
+                    abovep = rEz + (par * 2 + 1) * TW;
                 }
                 load4(abovep + cg[0], up[0]);
                 load4(abovep + cg[1], up[1]);
-                e_row(0, up);
+                load4(chAp + cg[0], c[0]);
+                load4(chAp + cg[1], c[1]);
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) hxa[g][q] = sub_rn(hxa[g][q], mul_rn(c[g][q], sub_rn(e[0][g][q], up[g][q])));
             }
+            // ---- interior Ez update (no barrier: every Hx row it reads is in my registers) ---------------------
+#pragma unroll
+            for (int r = MR - 1; r > 0; --r) e_row(r, hx[r > 0 ? r - 1 : 0]);
+            e_row(0, hxa);
             // ---- S1 -> ring frames; source / probe cells outside the frames go through their slot -------------
             park(DELTA);
             if (spmask) {

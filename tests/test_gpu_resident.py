@@ -43,21 +43,22 @@ def _problem(rng, R, C, scale=1e-3):
     return eps, mu, Ez, Hx, Hy
 
 
-# rows choose the cluster size (<=64: 1 CTA, <=128: 2, <=256: 4, <=512: 8) and the ragged last band;
+# rows choose the cluster size (48-row bands: 1 CTA up to 48 rows ... 8 CTAs up to 384) and the ragged last band;
 # columns choose where the right ring frame falls (second half, first half, straddling column 128)
 SHAPES = [(16, 16), (17, 33), (48, 256), (49, 255), (64, 256), (65, 255), (100, 128), (128, 129), (129, 131), (130, 136),
           (200, 200), (256, 256), (255, 140), (260, 64), (300, 250), (384, 256), (383, 17), (37, 53), (96, 130), (72, 100)]
-# (rows per thread, shape): MR = 4 bands hold 64 rows (up to 512 rows per grid), MR = 2 bands 32 rows
-CASES = [(3, s) for s in SHAPES] + [(4, s) for s in SHAPES[::2]] + [(4, (512, 256)), (4, (511, 17)), (2, (256, 256)),
-                                                                  (2, (33, 40)), (2, (250, 141))]
+# (kernel shape, grid shape): shape 0 = 3 rows per thread x 16 warps (48-row bands, the default), 1 = 4 x 12 (48 rows),
+# 2 = 2 x 16 (32 rows), 3 = 4 x 8 (32 rows), 4 = 3 x 12 (36 rows); a cluster has at most 8 bands
+SMALL = [(256, 256), (33, 40), (250, 141), (100, 128), (17, 33), (200, 200)]
+CASES = [(0, s) for s in SHAPES] + [(1, s) for s in SHAPES[::2]] + [(c, s) for c in (2, 3, 4) for s in SMALL]
 
 
-@pytest.mark.parametrize("mr,shape", CASES)
+@pytest.mark.parametrize("rcfg,shape", CASES)
 @pytest.mark.parametrize("nsteps", [1, 2, 37])
-def test_resident_vs_oracle(fd, oracle, mr, shape, nsteps, monkeypatch):
+def test_resident_vs_oracle(fd, oracle, rcfg, shape, nsteps, monkeypatch):
     c_oracle, npo = oracle
     R, C = shape
-    monkeypatch.setenv("FDTD2D_RESIDENT_MR", str(mr))
+    monkeypatch.setenv("FDTD2D_RESIDENT_CFG", str(rcfg))
     rng = np.random.default_rng(R * 1009 + C * 13 + nsteps)
     eps, mu, Ez, Hx, Hy = _problem(rng, R, C)
     ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(np.float32))
