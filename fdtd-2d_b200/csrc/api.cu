@@ -215,6 +215,60 @@ __global__ void random_materials_kernel(T* ce, T* ch, T* mur, int Rl, int C, int
     }
 }
 
+// Grayscale structure image -> materials (main.py:109-123): eps = (1 + (bp - 1) * (1 - g/255)) * eps0 in float64
+// (the reference's dtype), then cast to the run dtype -- the cast the caller of material_init does for an fp32
+// run; mu = mu0.  One byte per cell crosses PCIe instead of two float64 maps.
+template <typename T>
+__global__ void gray_materials_kernel(const unsigned char* gray, T* ce, T* ch, int Rl, int C, int pitch, long long grid_stride,
+                                      int batch, double black_point, double eps0, double mu0) {
+    const long long per_grid = (long long)Rl * C, n = per_grid * batch;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int b = (int)(i / per_grid);
+        const long long r = i - (long long)b * per_grid;
+        const int li = (int)(r / C), j = (int)(r - (long long)li * C);
+        const double g = __ddiv_rn((double)gray[i], 255.0);
+        const double factor = __dadd_rn(1.0, __dmul_rn(__dsub_rn(black_point, 1.0), __dsub_rn(1.0, g)));
+        const long long o = (long long)b * grid_stride + (long long)li * pitch + j;
+        ce[o] = (T)__dmul_rn(factor, eps0);
+        ch[o] = (T)mu0;
+    }
+}
+
+// Random two-phase medium of the dataset generator (diffusion_training.py:54-93): a uniform field u in [0,1),
+// blurred with a 15 x 15 Gaussian (zero padding, float32, taps accumulated row-major with one rounding per
+// multiply and per add), thresholded at 0.5 -> eps_hi / eps_lo; mu uniform.  u comes from the counter-based hash
+// (hash_uniform), so a CPU checker rebuilds the same field.  One CTA per 32 x 32 output tile of one grid.
+constexpr int BLOB_K = 15, BLOB_T = 32, BLOB_H = BLOB_T + BLOB_K - 1;
+template <typename T>
+__global__ void __launch_bounds__(256) blob_materials_kernel(T* ce, T* ch, int R, int C, int pitch, long long grid_stride,
+                                                             uint64_t seed, const float* weights, T eps_lo, T eps_hi, T mu) {
+    __shared__ float su[BLOB_H][BLOB_H + 1];
+    __shared__ float sw[BLOB_K * BLOB_K];
+    const int b = blockIdx.z, r0 = blockIdx.y * BLOB_T, c0 = blockIdx.x * BLOB_T;
+    for (int i = threadIdx.x; i < BLOB_K * BLOB_K; i += blockDim.x) sw[i] = weights[(size_t)b * BLOB_K * BLOB_K + i];
+    for (int i = threadIdx.x; i < BLOB_H * BLOB_H; i += blockDim.x) {
+        const int y = i / BLOB_H, x = i - y * BLOB_H;
+        const int gi = r0 + y - BLOB_K / 2, gj = c0 + x - BLOB_K / 2;
+        su[y][x] = (gi >= 0 && gi < R && gj >= 0 && gj < C) ? (float)hash_uniform(seed, (uint32_t)b, (uint32_t)gi, (uint32_t)gj) : 0.0f;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty0 = threadIdx.x >> 5;
+    for (int ty = ty0; ty < BLOB_T; ty += 8) {
+        const int gi = r0 + ty, gj = c0 + tx;
+        if (gi >= R || gj >= C) continue;
+        float acc = 0.0f;
+#pragma unroll
+        for (int ky = 0; ky < BLOB_K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < BLOB_K; ++kx) acc = add_rn(acc, mul_rn(sw[ky * BLOB_K + kx], su[ty + ky][tx + kx]));
+        const long long o = (long long)b * grid_stride + (long long)gi * pitch + gj;
+        ce[o] = acc > 0.5f ? eps_hi : eps_lo;
+        ch[o] = mu;
+    }
+}
+
 // Field readout as an image (main.py:153-179): clip Ez to [vmin, vmax], normalise in the run dtype, look
 // up a 256-entry colormap, alpha-blend (alpha = 0.7) over the grayscale permittivity background in
 // float64 and truncate to uint8 -- the same operations, in the same order and precision, as the reference's
@@ -954,34 +1008,15 @@ int fdtd2d_set_coeffs(fdtd2d_sim* s, const void* ce, const void* ch, const void*
     return 0;
 }
 
+static int finish_materials(fdtd2d_sim* s, double dt, double dx);
+
 int fdtd2d_set_materials(fdtd2d_sim* s, const void* eps, const void* mu, double dt, double dx) {
     REQUIRE(s && eps && mu, "null argument");
     if (int rc = use_device(s)) return rc;
     // stage eps in ce and mu in ch, then transform in place on the device
     if (int rc = transfer_field(s, s->ce, const_cast<void*>(eps), s->Rl, s->C, true)) return rc;
     if (int rc = transfer_field(s, s->ch, const_cast<void*>(mu), s->Rl, s->C, true)) return rc;
-    const long long n = (long long)s->grid_elems * s->batch;
-    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
-    const bool has_corner = s->row0 == 0;
-    if (s->dtype == FDTD2D_F32) {
-        if (has_corner)
-            mur_from_materials_kernel<float><<<(s->batch + 127) / 128, 128, 0, s->stream>>>(
-                (const float*)s->ce, (const float*)s->ch, (long long)s->grid_elems, s->batch, (float)dt, (float)dx,
-                (float*)s->mur);
-        coeff_from_materials_kernel<float><<<blocks, 256, 0, s->stream>>>((float*)s->ce, (float*)s->ch, n, (float)dt,
-                                                                         (float)dx);
-    } else {
-        if (has_corner)
-            mur_from_materials_kernel<double><<<(s->batch + 127) / 128, 128, 0, s->stream>>>(
-                (const double*)s->ce, (const double*)s->ch, (long long)s->grid_elems, s->batch, dt, dx, (double*)s->mur);
-        coeff_from_materials_kernel<double><<<blocks, 256, 0, s->stream>>>((double*)s->ce, (double*)s->ch, n, dt, dx);
-    }
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    s->launches += has_corner ? 2 : 1;
-    s->coeffs_set = true;
-    if (has_corner) s->mur_set = true;
-    return 0;
+    return finish_materials(s, dt, dx);
 }
 
 double fdtd2d_hash_uniform(uint64_t seed, uint32_t grid, uint32_t row, uint32_t col) {
@@ -1007,6 +1042,92 @@ int fdtd2d_set_materials_random(fdtd2d_sim* s, uint64_t seed, double span, doubl
     s->coeffs_set = true;
     s->mur_set = true;
     return 0;
+}
+
+// eps/mu are staged in ce/ch: form the Mur coefficient(s) and the coefficient maps in place (device-side tail of
+// every fdtd2d_set_materials* entry point)
+static int finish_materials(fdtd2d_sim* s, double dt, double dx) {
+    const long long n = (long long)s->grid_elems * s->batch;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    const bool has_corner = s->row0 == 0;
+    if (s->dtype == FDTD2D_F32) {
+        if (has_corner)
+            mur_from_materials_kernel<float><<<(s->batch + 127) / 128, 128, 0, s->stream>>>(
+                (const float*)s->ce, (const float*)s->ch, (long long)s->grid_elems, s->batch, (float)dt, (float)dx,
+                (float*)s->mur);
+        coeff_from_materials_kernel<float><<<blocks, 256, 0, s->stream>>>((float*)s->ce, (float*)s->ch, n, (float)dt,
+                                                                         (float)dx);
+    } else {
+        if (has_corner)
+            mur_from_materials_kernel<double><<<(s->batch + 127) / 128, 128, 0, s->stream>>>(
+                (const double*)s->ce, (const double*)s->ch, (long long)s->grid_elems, s->batch, dt, dx, (double*)s->mur);
+        coeff_from_materials_kernel<double><<<blocks, 256, 0, s->stream>>>((double*)s->ce, (double*)s->ch, n, dt, dx);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->launches += has_corner ? 2 : 1;
+    s->coeffs_set = true;
+    if (has_corner) s->mur_set = true;
+    return 0;
+}
+
+int fdtd2d_set_materials_gray(fdtd2d_sim* s, const unsigned char* gray, double black_point, double dt, double dx) {
+    REQUIRE(s && gray, "null argument");
+    if (int rc = use_device(s)) return rc;
+    const double eps0 = 8.85418e-12, mu0 = 4 * 3.141592653589793 * 1e-7;  // main.py:100-101
+    const size_t n = (size_t)s->Rl * s->C * s->batch;
+    unsigned char* d_g = nullptr;
+    CUDA_TRY(cudaMalloc(&d_g, n));
+    cudaError_t e = cudaMemcpyAsync(d_g, gray, n, cudaMemcpyHostToDevice, s->stream);
+    if (e != cudaSuccess) {
+        cudaFree(d_g);
+        return fail(FDTD2D_ECUDA, "gray upload failed: %s", cudaGetErrorString(e));
+    }
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    if (s->dtype == FDTD2D_F32)
+        gray_materials_kernel<float><<<blocks, 256, 0, s->stream>>>(d_g, (float*)s->ce, (float*)s->ch, s->Rl, s->C, (int)s->pitch,
+                                                                   (long long)s->grid_elems, s->batch, black_point, eps0, mu0);
+    else
+        gray_materials_kernel<double><<<blocks, 256, 0, s->stream>>>(d_g, (double*)s->ce, (double*)s->ch, s->Rl, s->C,
+                                                                    (int)s->pitch, (long long)s->grid_elems, s->batch, black_point,
+                                                                    eps0, mu0);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_g);
+    if (e != cudaSuccess) return fail(FDTD2D_ECUDA, "gray_materials_kernel failed: %s", cudaGetErrorString(e));
+    s->launches += 1;
+    return finish_materials(s, dt, dx);
+}
+
+int fdtd2d_generate_materials_blobs(fdtd2d_sim* s, uint64_t seed, const float* weights, double eps_lo, double eps_hi, double mu,
+                                    double dt, double dx, void* eps_out) {
+    REQUIRE(s && weights, "null argument");
+    REQUIRE(!s->has_top_nb && !s->has_bot_nb, "the blob generator works on whole grids, not slabs");
+    if (int rc = use_device(s)) return rc;
+    float* d_w = nullptr;
+    const size_t wbytes = sizeof(float) * BLOB_K * BLOB_K * (size_t)s->batch;
+    CUDA_TRY(cudaMalloc(&d_w, wbytes));
+    cudaError_t e = cudaMemcpyAsync(d_w, weights, wbytes, cudaMemcpyHostToDevice, s->stream);
+    const dim3 grid((s->C + BLOB_T - 1) / BLOB_T, (s->Rg + BLOB_T - 1) / BLOB_T, s->batch);
+    if (e == cudaSuccess) {
+        if (s->dtype == FDTD2D_F32)
+            blob_materials_kernel<float><<<grid, 256, 0, s->stream>>>((float*)s->ce, (float*)s->ch, s->Rg, s->C, (int)s->pitch,
+                                                                     (long long)s->grid_elems, seed, d_w, (float)eps_lo,
+                                                                     (float)eps_hi, (float)mu);
+        else
+            blob_materials_kernel<double><<<grid, 256, 0, s->stream>>>((double*)s->ce, (double*)s->ch, s->Rg, s->C, (int)s->pitch,
+                                                                      (long long)s->grid_elems, seed, d_w, eps_lo, eps_hi, mu);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_w);
+    if (e != cudaSuccess) return fail(FDTD2D_ECUDA, "blob_materials_kernel failed: %s", cudaGetErrorString(e));
+    s->launches += 1;
+    if (eps_out) {  // the permittivity maps themselves are part of a dataset sample
+        if (int rc = transfer_field(s, s->ce, eps_out, s->Rl, s->C, false)) return rc;
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    return finish_materials(s, dt, dx);
 }
 
 int fdtd2d_download_coeffs(fdtd2d_sim* s, void* ce, void* ch, void* mur_coef) {

@@ -170,6 +170,22 @@ class Simulation:
         mc = np.ascontiguousarray(np.broadcast_to(np.asarray(mur_coef, dtype=self.dtype), (self.batch,)))
         check(lib().fdtd2d_set_mur_coef(self._h, _p(mc)))
 
+    def set_materials_gray(self, gray, black_point: float = 10.0):
+        """Structure image -> materials on the device (main.py:109-123).  gray: uint8 (rows, cols) "L" image
+        already resized (what `Image.open(p).convert("L").resize((cols, rows), LANCZOS)` gives); the device forms
+        eps = (1 + (black_point-1)(1-gray/255)) eps0 in float64, casts to the run dtype and sets mu = mu0."""
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        if gray.shape != self._shape(self.local_rows, self.cols):
+            raise ValueError(f"gray has shape {gray.shape}, expected {self._shape(self.local_rows, self.cols)}")
+        check(lib().fdtd2d_set_materials_gray(self._h, _p(gray), float(black_point), self.dt, self.dx))
+
+    def set_materials_image(self, path, black_point: float = 10.0):
+        """`material_init(path, rows, cols, black_point)` + set_materials with the mapping done on the device."""
+        from PIL import Image
+
+        img = Image.open(path).convert("L").resize((self.cols, self.local_rows), Image.LANCZOS)
+        self.set_materials_gray(np.array(img, dtype=np.uint8), black_point)
+
     def set_materials_random(self, seed: int, span: float = 9.0):
         """Synthetic medium generated on the device: eps = eps0*(1 + span*u), mu = mu0."""
         check(lib().fdtd2d_set_materials_random(self._h, seed, span, self.dt, self.dx))

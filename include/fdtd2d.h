@@ -92,6 +92,18 @@ int fdtd2d_set_mur_coef(fdtd2d_sim* s, const void* mur_coef);
  * eps = eps0*(1 + span*u), u in [0,1) from a counter-based hash of (seed, grid, global row, col);
  * mu = mu0.  eps0 = 8.85418e-12, mu0 = 4*pi*1e-7 (main.py:100-101). See fdtd2d_hash_uniform. */
 int fdtd2d_set_materials_random(fdtd2d_sim* s, uint64_t seed, double span, double dt, double dx);
+/* Structure image -> materials on the device (main.py:109-123): gray is the uint8 "L" image already resized to
+ * (R_local, C) per grid (PIL does that on the host, as in the reference); the device forms
+ * eps = (1 + (black_point - 1) * (1 - gray/255)) * eps0 in float64, casts to the run dtype, sets mu = mu0 and
+ * then the coefficient maps exactly as fdtd2d_set_materials does.  1 byte per cell crosses PCIe. */
+int fdtd2d_set_materials_gray(fdtd2d_sim* s, const unsigned char* gray, double black_point, double dt, double dx);
+/* Random two-phase media of the dataset generator (diffusion_training.py:54-93), one per batch grid, generated
+ * on the device: u = fdtd2d_hash_uniform(seed, grid, row, col) blurred with the grid's 15 x 15 kernel
+ * weights[grid][15*15] (float32, zero padding, row-major accumulation, no FMA), eps = blur > 0.5 ? eps_hi : eps_lo,
+ * mu uniform; then the coefficient maps as fdtd2d_set_materials.  eps_out (optional, host, (R, C) per grid in the
+ * run dtype) receives the permittivity maps.  Whole grids only (not slabs). */
+int fdtd2d_generate_materials_blobs(fdtd2d_sim* s, uint64_t seed, const float* weights, double eps_lo, double eps_hi, double mu,
+                                    double dt, double dx, void* eps_out);
 /* Host-side definition of the generator above (so a CPU checker can rebuild the same map). */
 double fdtd2d_hash_uniform(uint64_t seed, uint32_t grid, uint32_t row, uint32_t col);
 /* Read back the coefficient maps ((R_local, C), run dtype, batch-major) and per-grid Mur coefs. */
@@ -125,8 +137,11 @@ int fdtd2d_step_phases(fdtd2d_sim* s, int phases);
 int fdtd2d_get_step_index(const fdtd2d_sim* s, int64_t* step);
 int fdtd2d_set_step_index(fdtd2d_sim* s, int64_t step);
 /* Select the tile kernel: 0 = automatic, 1 = generic shared-memory tiles only,
- * 2 = register-resident tiles everywhere (TMA-fed plain tiles + edge-capable tiles; fp32 default),
- * 3 = register-resident plain tiles + shared-memory generic kernel for edge/source/probe tiles. */
+ * 2 = register-resident tiles everywhere (TMA-fed plain tiles + edge-capable tiles),
+ * 3 = register-resident plain tiles + shared-memory generic kernel for edge/source/probe tiles,
+ * 4 = cluster-resident kernel (fp32 grids of 16..256 columns and 16..384 rows stay on chip for a whole
+ *     fdtd2d_step call, one thread-block cluster per grid; k_temporal does not apply) or FDTD2D_EINVAL.
+ * Automatic = 4 when the grid is eligible, else 2. */
 int fdtd2d_set_kernel_variant(fdtd2d_sim* s, int variant);
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 int fdtd2d_launch_count(const fdtd2d_sim* s, int64_t* launches);
