@@ -87,6 +87,13 @@ __device__ __forceinline__ void st_async4(uint32_t remote_addr, const float* a, 
                  : "memory");
 }
 
+// A value the compiler must keep in a register: it cannot see through the empty asm, so it does not re-derive
+// thread-constant shared-memory offsets from %tid in every step of the time loop (that was ~1/4 of the loop).
+__device__ __forceinline__ int keep(int v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+
 // p.k = number of leapfrog steps of this launch; p.CW / p.CH = rows of the first / of every other CTA of a cluster
 // (multiples of MR); gridDim.x = batch * cluster size.
 // MR rows per thread, NW warps per CTA: a CTA holds a band of at most MR * NW rows.
@@ -185,7 +192,9 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
             }
         }
     }
-    const float* const chAp = (w == 0 ? sChA : sCh + (li0 - 1) * TW);  // dt/(mu*dx) of that row
+    const int qA = keep(w == 0 ? TH * TW + cg[0] : (li0 - 1) * TW + cg[0]);  // dt/(mu*dx) of that row, offset from sCh
+    const int qC = keep(li0 * TW + cg[0]);                                   // my first row in sCe / sCh
+    const int qX = keep(w * TW + cg[0]);                                     // my slot in a row-exchange block
 
     // ---- set-up: barriers; where the source / probe cells of this band live in shared memory --------
     for (int i = tid; i < TH * (TW / 4) / 4; i += NT) reinterpret_cast<unsigned*>(slot_tbl)[i] = 0xffffffffu;
@@ -247,22 +256,26 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
     const int zo[2] = {cg[0] < LW ? cg[0] : (cg[0] >= cR0 && cg[0] < cR0 + RES_RW ? LW + cg[0] - cR0 : -1),
                        cg[1] >= cR0 && cg[1] < cR0 + RES_RW ? LW + cg[1] - cR0 : -1};
     const bool z0 = zo[0] >= 0, z1 = zo[1] >= 0;
-    float* const zp0 = F + oLR + li0 * ZW + zo[0];  // S0 slot of my group 0 in the LR frame of my first row
-    float* const zp1 = F + oLR + li0 * ZW + zo[1];  // (S1 is DELTA further; never dereferenced when !z0 / !z1)
+    const int zq0 = keep(oLR + li0 * ZW + zo[0]);  // S0 slot of my group 0 in the LR frame of my first row (offset from F)
+    const int zq1 = keep(oLR + li0 * ZW + zo[1]);  // (S1 is DELTA further; never dereferenced when !z0 / !z1)
+    float* const zp0 = F + zq0;
+    float* const zp1 = F + zq1;
     // do my rows reach the top / bottom ring rows?
     const bool warp_tb = (isTop && row_lo + li0 <= 5) || (isBot && row_lo + li0 + MR - 1 >= R - 6 && row_lo + li0 < R);
     // S2 (Mur left/right) of my warp's rows: lane -> (row l>>3, ring cell l&7).  Rows of the top / bottom ring
     // are updated in their T / B frame, the others in the LR frame; S0 is always DELTA before S1.
     const int s2row = li0 + (l >> 3), s2k = l & 7, s2gi = row_lo + s2row;
     const bool s2act = (l >> 3) < MR && s2k < RING && s2row < nrows && s2gi >= 1 && s2gi <= R - 2;
-    float *s2L, *s2R;  // S1 of cell (row, k) / (row, C-1-k)
+    int s2l, s2r;  // S1 of cell (row, k) / (row, C-1-k), as offsets from F
     if (isTop && s2gi <= 5) {
-        s2L = F + DELTA + oT + s2gi * TW + s2k, s2R = F + DELTA + oT + s2gi * TW + (C - 1 - s2k);
+        s2l = DELTA + oT + s2gi * TW + s2k, s2r = DELTA + oT + s2gi * TW + (C - 1 - s2k);
     } else if (isBot && s2gi >= R - 6) {
-        s2L = F + DELTA + oB + (s2gi - (R - 6)) * TW + s2k, s2R = F + DELTA + oB + (s2gi - (R - 6)) * TW + (C - 1 - s2k);
+        s2l = DELTA + oB + (s2gi - (R - 6)) * TW + s2k, s2r = DELTA + oB + (s2gi - (R - 6)) * TW + (C - 1 - s2k);
     } else {
-        s2L = F + DELTA + oLR + s2row * ZW + s2k, s2R = F + DELTA + oLR + s2row * ZW + LW + (C - 1 - s2k - cR0);
+        s2l = DELTA + oLR + s2row * ZW + s2k, s2r = DELTA + oLR + s2row * ZW + LW + (C - 1 - s2k - cR0);
     }
+    float* const s2L = F + keep(s2l);
+    float* const s2R = F + keep(s2r);
     // registers -> S0 / S1 frames (delta = 0 / DELTA)
     auto park = [&](int delta) {
 #pragma unroll
@@ -343,8 +356,8 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
     // one row of the H half-step (main.py:69-74); dn = the Ez row below it
     auto h_row = [&](const int r, const float (&dn)[2][4]) {
         float c[2][4];
-        load4(sCh + (li0 + r) * TW + cg[0], c[0]);
-        load4(sCh + (li0 + r) * TW + cg[1], c[1]);
+        load4(sCh + qC + r * TW, c[0]);
+        load4(sCh + qC + r * TW + 128, c[1]);
         const float ra = __shfl_sync(FULL, e[r][0][0], (l + 1) & 31);
         const float rb = __shfl_sync(FULL, e[r][1][0], (l + 1) & 31);
         const float right3[2] = {l == 31 ? rb : ra, rb};
@@ -360,8 +373,8 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
     // one row of the interior Ez update (main.py:21-27); up = the Hx row above it
     auto e_row = [&](const int r, const float (&up)[2][4]) {
         float c[2][4];
-        load4(sCe + (li0 + r) * TW + cg[0], c[0]);
-        load4(sCe + (li0 + r) * TW + cg[1], c[1]);
+        load4(sCe + qC + r * TW, c[0]);
+        load4(sCe + qC + r * TW + 128, c[1]);
         const float la = __shfl_sync(FULL, hy[r][0][3], (l + 31) & 31);
         const float lb = __shfl_sync(FULL, hy[r][1][3], (l + 31) & 31);
         const float left0[2] = {la, l == 0 ? la : lb};
@@ -381,13 +394,13 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
         const int par = s & 1;
         const uint32_t ph = (uint32_t)(s >> 1) & 1u;
         const long long step = p.step0 + s;
-        float* const xF = sEx + (par * 2 * NW + w) * TW;  // my slot for the first row; the last row is NW rows further
+        float* const xF = sEx + par * (2 * NW * TW) + qX;  // my slot (group 0) for the first row; the last row is NW rows further
         if (warp_on) {
             // ---- publish my first and last Ez rows; the band's first / last row also go to the neighbour CTAs ----
-            store4(xF + cg[0], e[0][0]);
-            store4(xF + cg[1], e[0][1]);
-            store4(xF + NW * TW + cg[0], e[MR - 1][0]);
-            store4(xF + NW * TW + cg[1], e[MR - 1][1]);
+            store4(xF, e[0][0]);
+            store4(xF + 128, e[0][1]);
+            store4(xF + NW * TW, e[MR - 1][0]);
+            store4(xF + NW * TW + 128, e[MR - 1][1]);
             if (edge_up) {  // -> "row from below" of the CTA above
                 st_async4(up_rEz + (uint32_t)(par * 2 * TW + cg[0]) * 4u, e[0][0], up_barB + 8u * par);
                 st_async4(up_rEz + (uint32_t)(par * 2 * TW + cg[1]) * 4u, e[0][1], up_barB + 8u * par);
@@ -410,10 +423,10 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
                 if (edge_dn) {
                     if (l == 0) mbar_expect_tx(&barB[par], ROW_BYTES);
                     mbar_wait(&barB[par], ph);
-                    belowp = rEz + par * 2 * TW;
+                    belowp = rEz + par * 2 * TW + cg[0];
                 }
-                load4(belowp + cg[0], dn[0]);
-                load4(belowp + cg[1], dn[1]);
+                load4(belowp, dn[0]);
+                load4(belowp + 128, dn[1]);
                 h_row(MR - 1, dn);
             }
             {   // my copy of the Hx row above my rows (main.py:69-70 for that row)
@@ -422,12 +435,12 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
                 if (edge_up) {
                     if (l == 0) mbar_expect_tx(&barA[par], ROW_BYTES);
                     mbar_wait(&barA[par], ph);
-                    abovep = rEz + (par * 2 + 1) * TW;
+                    abovep = rEz + (par * 2 + 1) * TW + cg[0];
                 }
-                load4(abovep + cg[0], up[0]);
-                load4(abovep + cg[1], up[1]);
-                load4(chAp + cg[0], c[0]);
-                load4(chAp + cg[1], c[1]);
+                load4(abovep, up[0]);
+                load4(abovep + 128, up[1]);
+                load4(sCh + qA, c[0]);
+                load4(sCh + qA + 128, c[1]);
 #pragma unroll
                 for (int g = 0; g < 2; ++g)
 #pragma unroll

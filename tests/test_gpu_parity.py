@@ -35,6 +35,17 @@ def fd():
     return fdtd2d_b200
 
 
+@pytest.fixture(autouse=True, params=["auto", "tiled"])
+def engine(request, monkeypatch):
+    """Every test runs twice: with the automatic kernel choice (small fp32 grids take the cluster-resident kernel)
+    and with that kernel disabled, so the k-step tile kernels keep their coverage of small and ragged grids."""
+    if request.param == "tiled":
+        monkeypatch.setenv("FDTD2D_NO_RESIDENT", "1")
+    else:
+        monkeypatch.delenv("FDTD2D_NO_RESIDENT", raising=False)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def oracle():
     from oracle import c_oracle, numpy_oracle
