@@ -42,12 +42,12 @@ BYTES_PER_UPDATE_F32 = 32  # read Ez,Hx,Hy,ce,ch + write Ez,Hx,Hy
 
 WORKLOADS = {
     # name: rows-per-GPU, cols, inner leapfrog steps per bench step, description
-    "cfg2": dict(rows=4096, cols=4096, inner=500, desc="4096x4096 fp32, random permittivity (BASELINE configs[1])"),
-    "cfg3": dict(rows=16384, cols=16384, inner=200,
+    "cfg2": dict(rows=4096, cols=4096, inner=10000, desc="4096x4096 fp32, random permittivity, 10k steps (BASELINE configs[1])"),
+    "cfg3": dict(rows=16384, cols=16384, inner=1000,
                  desc="16384x16384 fp32, random permittivity, temporal-blocked kernel (BASELINE configs[2]; the "
                       "grid the >=70%-of-roofline target is quoted on)"),
     "cfg4": dict(rows=65536, cols=65536, inner=16, desc="65536x65536 fp32 y-slab sharded (BASELINE configs[3]), strong scaling"),
-    "cfg5": dict(rows=256, cols=256, inner=200, batch=1024,
+    "cfg5": dict(rows=256, cols=256, inner=400, batch=1024,
                  desc="batched 1024 x (256x256) independent fp32 grids per GPU (BASELINE configs[4], dataset generation)"),
     "small": dict(rows=1024, cols=1024, inner=64, desc="1024x1024 fp32 (debug)"),
 }
