@@ -788,6 +788,22 @@ static int copy2d(const fdtd2d_sim* s, void* dev, void* host, int rows, int widt
 
 static int transfer_field(fdtd2d_sim* s, void* dev, void* host, int rows_host, int width, bool to_device) {
     // per grid: rows_host x width on the host, Rl x pitch on the device
+    if (rows_host == s->Rl && (size_t)s->batch * rows_host < (size_t)0x7fffffff)
+        // the grids are back to back on both sides: the whole batch is one strided copy (1024 small grids would
+        // otherwise be 1024 copies of 256 KB each)
+        return copy2d(s, dev, host, s->batch * rows_host, width, to_device);
+    if (s->batch > 1) {  // Hy: one row fewer per grid on the host than on the device -> one 3-D copy for the batch
+        const size_t wbytes = (size_t)width * s->esize;
+        cudaMemcpy3DParms c = {};
+        const cudaPitchedPtr h = make_cudaPitchedPtr(host, wbytes, wbytes, (size_t)rows_host);
+        const cudaPitchedPtr d = make_cudaPitchedPtr(dev, s->pitch * s->esize, s->pitch * s->esize, (size_t)s->Rl);
+        c.srcPtr = to_device ? h : d;
+        c.dstPtr = to_device ? d : h;
+        c.extent = make_cudaExtent(wbytes, (size_t)rows_host, (size_t)s->batch);
+        c.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+        CUDA_TRY(cudaMemcpy3DAsync(&c, s->stream));
+        return 0;
+    }
     for (int b = 0; b < s->batch; ++b) {
         char* d = static_cast<char*>(dev) + (size_t)b * s->grid_elems * s->esize;
         char* h = static_cast<char*>(host) + (size_t)b * rows_host * width * s->esize;
