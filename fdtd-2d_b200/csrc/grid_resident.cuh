@@ -389,6 +389,12 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
     };
     cluster_sync_all();  // every CTA's barriers are initialised before anyone signals them
 
+#ifdef FDTD2D_RES_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define RES_STAMP(i) { const long long tn = clock64(); tacc[i] += tn - tprev; tprev = tn; }
+#else
+#define RES_STAMP(i)
+#endif
 #pragma unroll 1
     for (int s = 0; s < n_steps; ++s) {
         const int par = s & 1;
@@ -411,12 +417,15 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
             }
             park(0);  // S0: Ez is not changed by the H half-step
         }
+        RES_STAMP(0)
         __syncthreads();  // the only CTA-wide barrier of a step away from the top / bottom ring
+        RES_STAMP(1)
         if (s > 0) sample_probes(step - 1);  // the previous step's frames are intact until the next park
         if (warp_on) {
             // ---- H half-step; the rows that need a neighbour CTA's Ez row come last ---------------------------
 #pragma unroll
             for (int r = 0; r + 1 < MR; ++r) h_row(r, e[r + 1 < MR ? r + 1 : r]);
+            RES_STAMP(2)
             {
                 float dn[2][4];
                 const float* belowp = xF + (w + 1 < NW ? TW : 0);  // first row of the warp below
@@ -446,10 +455,12 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
 #pragma unroll
                     for (int q = 0; q < 4; ++q) hxa[g][q] = sub_rn(hxa[g][q], mul_rn(c[g][q], sub_rn(e[0][g][q], up[g][q])));
             }
+            RES_STAMP(3)
             // ---- interior Ez update (no barrier: every Hx row it reads is in my registers) ---------------------
 #pragma unroll
             for (int r = MR - 1; r > 0; --r) e_row(r, hx[r > 0 ? r - 1 : 0]);
             e_row(0, hxa);
+            RES_STAMP(4)
             // ---- S1 -> ring frames; source / probe cells outside the frames go through their slot -------------
             park(DELTA);
             if (spmask) {
@@ -480,9 +491,11 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
             __syncwarp();
             if (s2act) *s2L = vl, *s2R = vr;
         }
+        RES_STAMP(5)
         // ---- top / bottom rows: S3, S4 in one pass over their frames (all threads of the CTA) ----------------
         if (cta_tb) {
             __syncthreads();
+            RES_STAMP(6)
             if (isTop) tb_pass(true);
             if (isBot) tb_pass(false);
         }
@@ -497,6 +510,7 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
             __syncthreads();
         else
             __syncwarp();
+        RES_STAMP(7)
         // ---- finished ring -> registers ---------------------------------------------------------------------
         if (warp_on) {
 #pragma unroll
@@ -519,6 +533,11 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
             }
         }
     }
+#ifdef FDTD2D_RES_TIMING
+    if (l == 0 && b == 0)
+        for (int i = 0; i < 8; ++i) p.trace[(crank * NW + w) * 8 + i] = (float)tacc[i] / (float)n_steps;
+    if (false)
+#endif
     if (n_steps > 0 && n_prb) {
         __syncthreads();
         sample_probes(p.step0 + n_steps - 1);
