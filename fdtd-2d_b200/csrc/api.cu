@@ -17,6 +17,7 @@
 #include "tile_tma.cuh"
 #include "tile_generic.cuh"
 #include "grid_resident.cuh"
+#include "strip_wave.cuh"
 
 using namespace fdtd2d;
 
@@ -58,10 +59,12 @@ template <typename T, int TH> constexpr int generic_nt() { return 6 * TH * G_TW 
 // Several shapes are compiled; fdtd2d_set_fast_config / FDTD2D_FAST_CFG picks one (default below).
 struct FastCfg {
     int MR, NW;
-    bool tma;  // persistent TMA-fed kernel (tile_tma.cuh) instead of the plain-load kernel (tile_fast.cuh)
+    bool tma;   // persistent TMA-fed kernel (tile_tma.cuh) instead of the plain-load kernel (tile_fast.cuh)
+    bool wave;  // k = 8 passes: runs of plain tiles go to the row-streaming wavefront kernel (strip_wave.cuh)
 };
-static const FastCfg kFastCfgs[] = {{4, 8, false}, {4, 12, false}, {4, 16, false}, {6, 8, false},
-                                    {8, 8, false}, {2, 16, false}, {4, 16, true},  {4, 16, true}};
+static const FastCfg kFastCfgs[] = {{4, 8, false, false},  {4, 12, false, false}, {4, 16, false, false},
+                                    {6, 8, false, false},  {8, 8, false, false},  {2, 16, false, false},
+                                    {4, 16, true, false},  {4, 16, true, false},  {4, 16, true, true}};
 constexpr int N_FAST_CFG = sizeof(kFastCfgs) / sizeof(kFastCfgs[0]);
 constexpr int DEFAULT_FAST_CFG = 6;  // persistent TMA-fed 64 x 128 tiles: best measured (profiles/)
 constexpr int MIN_LAST = 8;  // smallest core extent allowed for the last tile row/column (ring safety)
@@ -79,6 +82,11 @@ struct PassPlan {
     int n_generic_band = 0, n_fast_band = 0;  // leading entries of each list: tiles that produce halo rows / touch ghost rows
     int* d_generic = nullptr;
     int* d_fast = nullptr;
+    // wavefront runs built from the plain tiles: [0, n_wave_rest) avoid the band rows, [n_wave_rest, n_wave_rest + n_wave_all)
+    // cover every plain tile
+    int n_wave_rest = 0, n_wave_all = 0;
+    WaveTask* d_wave = nullptr;
+    int* d_ticket = nullptr;  // next run to hand out (reset before every launch)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -395,6 +403,22 @@ template <int MR, int NW, bool PAIR> static int launch_tma_t(fdtd2d_sim* s, cons
     return 0;
 }
 
+static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket) {
+    static bool done_[MAX_DEVICES] = {};
+    bool& done = done_[s->device % MAX_DEVICES];
+    const size_t smem = wave_smem_bytes();
+    if (!done) {
+        CUDA_TRY(cudaFuncSetAttribute(strip_wave_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        done = true;
+    }
+    if (!s->sm_count) CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
+    const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, s->sm_count);
+    CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int), s->stream));
+    strip_wave_kernel<8><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 template <typename T, int MR, int NW> static int launch_edge_tt(int dev, const PassParams<T>& p, int n_tiles, cudaStream_t st) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[dev % MAX_DEVICES];
@@ -494,6 +518,8 @@ static void free_plans(fdtd2d_sim* s) {
     for (PassPlan& pl : s->hybrid) {
         cudaFree(pl.d_generic);
         cudaFree(pl.d_fast);
+        cudaFree(pl.d_wave);
+        cudaFree(pl.d_ticket);
         pl = PassPlan();
     }
 }
@@ -550,6 +576,45 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
                 (plain ? (band ? fast : fast_rest) : (band ? gen : gen_rest)).push_back(id);
             }
         }
+    if (kFastCfgs[s->fast_cfg].wave && k == 8) {
+        // vertical runs of plain tiles of one tile column -> wavefront tasks of at most WAVE_SEG tiles: long enough
+        // to amortise the 2k warm-up rows, short enough that every warp of the GPU gets several
+        if (!s->sm_count) CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
+        const long long n_plain = (long long)fast.size() + (long long)fast_rest.size();
+        const int WAVE_SEG = (int)std::max<long long>(4, std::min<long long>(16, n_plain / (6LL * s->sm_count * WAVE_NW)));
+        std::vector<unsigned char> is_plain((size_t)n_tiles, 0), is_band((size_t)n_tiles, 0);
+        for (int id : fast) is_plain[id] = 1, is_band[id] = 1;
+        for (int id : fast_rest) is_plain[id] = 1;
+        std::vector<WaveTask> tasks;
+        for (int pass = 0; pass < 2; ++pass) {  // pass 0: plain tiles outside the band; pass 1: all plain tiles
+            for (int b = 0; b < s->batch; ++b)
+                for (int tx = 0; tx < tp.tiles_x; ++tx) {
+                    int run = 0;
+                    for (int ty = 0; ty <= tp.tiles_y; ++ty) {
+                        const int id = b * per_grid + ty * tp.tiles_x + tx;
+                        const bool ok = ty < tp.tiles_y && is_plain[id] && (pass == 1 || !is_band[id]);
+                        if (ok && run < WAVE_SEG) {
+                            ++run;
+                            continue;
+                        }
+                        if (run) {
+                            WaveTask t;
+                            t.b = b, t.x0 = tx * tp.CW - tp.hx, t.y0 = (ty - run) * tp.CH, t.y1 = ty * tp.CH;
+                            tasks.push_back(t);
+                        }
+                        run = ok ? 1 : 0;
+                    }
+                }
+            (pass == 0 ? pl->n_wave_rest : pl->n_wave_all) = (int)tasks.size() - (pass == 0 ? 0 : pl->n_wave_rest);
+        }
+        // small grids do not have enough runs to balance ~1200 independent warps: they stay on the tile kernel
+        if (n_plain < 4LL * WAVE_SEG * s->sm_count * WAVE_NW) tasks.clear(), pl->n_wave_rest = pl->n_wave_all = 0;
+        if (!tasks.empty()) {
+            CUDA_TRY(cudaMalloc(&pl->d_ticket, sizeof(int)));
+            CUDA_TRY(cudaMalloc(&pl->d_wave, sizeof(WaveTask) * tasks.size()));
+            CUDA_TRY(cudaMemcpy(pl->d_wave, tasks.data(), sizeof(WaveTask) * tasks.size(), cudaMemcpyHostToDevice));
+        }
+    }
     pl->n_generic_band = (int)gen.size();
     pl->n_fast_band = (int)fast.size();
     gen.insert(gen.end(), gen_rest.begin(), gen_rest.end());
@@ -618,7 +683,15 @@ static int launch_hybrid(fdtd2d_sim* s, int k, int part) {
         if (rc) return rc;
         s->launches += 1;
     }
-    if (n_fst) {
+    const bool wave = pl.d_wave && part != 1;  // the band tiles of a slab stay on the tile kernel
+    if (wave && n_fst) {
+        const WaveTask* tasks = part == 2 ? pl.d_wave : pl.d_wave + pl.n_wave_rest;
+        const int n_tasks = part == 2 ? pl.n_wave_rest : pl.n_wave_all;
+        p.tile_list = nullptr;
+        if (n_tasks)
+            if (int rc = launch_wave(s, p, tasks, n_tasks, pl.d_ticket)) return rc;
+        s->launches += n_tasks ? 1 : 0;
+    } else if (n_fst) {
         p.tile_list = pl.d_fast + f_off;
         int rc;
         switch (s->fast_cfg) {
@@ -630,6 +703,7 @@ static int launch_hybrid(fdtd2d_sim* s, int k, int part) {
             case 5: rc = launch_fast_t<2, 16, 2>(s, p, n_fst); break;
             case 6: rc = launch_tma_t<4, 16, false>(s, p, n_fst); break;
             case 7: rc = launch_tma_t<4, 16, true>(s, p, n_fst); break;
+            case 8: rc = launch_tma_t<4, 16, false>(s, p, n_fst); break;
             default: return fail(FDTD2D_EINVAL, "bad fast config");
         }
         if (rc) return rc;

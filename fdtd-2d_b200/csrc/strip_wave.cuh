@@ -1,0 +1,153 @@
+// Row-streaming wavefront kernel (fp32, plain regions): K leapfrog steps per HBM round trip with redundancy only in
+// the COLUMN halo.
+//
+// The overlapped tiles of tile_tma.cuh recompute a halo of K rows above and below every 64-row tile (core 48 x 112 of
+// 64 x 128: 34 % of the arithmetic is thrown away at K = 8).  Here one WARP owns a strip of 128 columns (core 112) and
+// marches down a long run of rows, carrying all K time levels of a sliding window of rows in its REGISTERS:
+//   level 0 row i arrives from HBM; for s = 0..K-1 the row stored at level s (row i-s-1) and the arriving one (row i-s)
+//   give level s+1 of row i-s-1 (H half-step main.py:69-74, then the interior Ez update main.py:21-27, which takes
+//   Hx of the row above from the row stored at level s+1); that result is the arriving row of the next level; what
+//   leaves level K-1 is row i-K advanced K steps and goes straight to HBM.
+// So every row is loaded once, stepped K times and stored once; the only recomputation is the 8 halo columns on each
+// side of the strip (12.5 %) and K warm-up rows per run of rows (< 4 %).  A warp never talks to another warp: no
+// __syncthreads, no shared-memory exchange of field rows; column neighbours come from two shuffles per row and level.
+// Rows are prefetched two iterations ahead with cp.async (16 B per lane and array) into a small per-warp ring; the
+// coefficient rows stay in that ring until the last level has used them (K + 3 rows later).
+// Cells next to the strip's edge columns and above the first / below the last row of the run read neighbours that are
+// missing; they go stale one cell per level exactly as in the overlapped tiles and are never stored.
+// Arithmetic and results are bit-identical to the other kernels (same operations, same order).
+#pragma once
+#include "common.cuh"
+#include "tile_edge.cuh"
+
+namespace fdtd2d {
+
+constexpr int WAVE_NW = 8;      // warps per CTA: 2 per scheduler, each may use up to 255 registers for the K-level window
+constexpr int WAVE_P = 3;       // rows prefetched ahead (field ring of P + 1 = 4 rows)
+constexpr int WAVE_NC = 16;     // rows of the coefficient ring (a power of two >= K + P + 2)
+constexpr int WAVE_TW = 128;    // strip width (columns per warp)
+
+// one run of rows of one strip: grid b, haloed strip starts at column x0, rows [y0, y1) are stored
+struct WaveTask {
+    int32_t b, x0, y0, y1;
+};
+
+__host__ __device__ constexpr size_t wave_smem_bytes() {
+    return (size_t)WAVE_NW * ((WAVE_P + 1) * 3 + WAVE_NC * 2) * WAVE_TW * sizeof(float);
+}
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int K>
+__global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassParams<float> p, const WaveTask* tasks, const int n_tasks, int* ticket) {
+    constexpr int TW = WAVE_TW, P = WAVE_P, NF = P + 1, NC = WAVE_NC;
+    static_assert((NF & (NF - 1)) == 0 && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_wave[];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    float* fring = reinterpret_cast<float*>(smem_wave) + (size_t)w * (NF * 3 + NC * 2) * TW + 4 * l;  // [NF][3][TW], my 4 columns
+    float* cring = fring + NF * 3 * TW;                                                              // [NC][2][TW]
+    const bool core = 4 * l >= p.hx && 4 * l < p.hx + p.CW;
+
+    for (;;) {  // runs are handed out dynamically: a warp takes the next one as soon as it is done
+        int t = 0;
+        if (l == 0) t = atomicAdd(ticket, 1);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= n_tasks) break;
+        const WaveTask tk = tasks[t];
+        const long long base = (long long)tk.b * p.grid_stride + tk.x0 + 4 * l;
+        const int i0 = tk.y0 - K, i1 = tk.y1 + K;  // level-0 rows [i0, i1)
+        auto fetch = [&](int row, int fs, int cs) {  // row -> ring slots fs (fields), cs (coefficients)
+            const long long o = base + (long long)row * p.pitch;
+            cp_async16(fring + (fs * 3 + 0) * TW, p.in[0] + o);
+            cp_async16(fring + (fs * 3 + 1) * TW, p.in[1] + o);
+            cp_async16(fring + (fs * 3 + 2) * TW, p.in[2] + o);
+            cp_async16(cring + (cs * 2 + 0) * TW, p.ce + o);
+            cp_async16(cring + (cs * 2 + 1) * TW, p.ch + o);
+        };
+        // The window: two register sets X, Y that swap roles every iteration so that no row is ever moved.  In an
+        // iteration ST[s] (s < K) is the row stored at level s (row i-s-1 when row i arrives), ST[K][1] the Hx of the
+        // last row that left; AR[0] receives the arriving level-0 row and AR[s+1] the result of level s, i.e. the row
+        // arriving at level s+1.  After the iteration the arrived rows ARE the stored rows: the sets swap.
+        float X[K + 1][3][4], Y[K + 1][3][4];
+#pragma unroll
+        for (int s = 0; s <= K; ++s)
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) X[s][f][q] = Y[s][f][q] = 0.0f;
+        // Row i0-1 (the row "stored" at level 0 before the first arrival) does not exist as data; its coefficient slot
+        // is read by level 0 in the first iteration: give it zeros.
+        int fs = 0, cs = 1;  // slots of the next row to FETCH; the coefficient slot of row i0-1 is 0
+        {
+            const float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            store4(cring + 0 * TW, z);
+            store4(cring + 1 * TW, z);
+        }
+#pragma unroll
+        for (int d = 0; d < P; ++d) {
+            fetch(i0 + d, fs, cs);
+            cp_async_commit();
+            fs = (fs + 1) & (NF - 1);
+            cs = (cs + 1) & (NC - 1);
+        }
+        int fr = 0;  // field slot of the arriving row
+        int cr = 0;  // coefficient slot of row i-1 (level 0's stored row)
+        auto iter = [&](float (&ST)[K + 1][3][4], float (&AR)[K + 1][3][4], const int i) {
+            if (i + P < i1) fetch(i + P, fs, cs);
+            cp_async_commit();  // (an empty group keeps the wait count uniform at the end of the run)
+            fs = (fs + 1) & (NF - 1);
+            cs = (cs + 1) & (NC - 1);
+            cp_async_wait<P>();  // row i has landed (every lane reads back only the 16 bytes it copied itself)
+            load4(fring + (fr * 3 + 0) * TW, AR[0][0]);
+            load4(fring + (fr * 3 + 1) * TW, AR[0][1]);
+            load4(fring + (fr * 3 + 2) * TW, AR[0][2]);
+            fr = (fr + 1) & (NF - 1);
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                float ce[4], ch[4];
+                const int c = (cr - s) & (NC - 1);  // coefficient slot of row i-s-1
+                load4(cring + (c * 2 + 0) * TW, ce);
+                load4(cring + (c * 2 + 1) * TW, ch);
+                const float right3 = __shfl_down_sync(FULL, ST[s][0][0], 1);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // H half-step of the stored row (main.py:69-74)
+                    const float right = q < 3 ? ST[s][0][q < 3 ? q + 1 : 3] : right3;
+                    AR[s + 1][1][q] = sub_rn(ST[s][1][q], mul_rn(ch[q], sub_rn(AR[s][0][q], ST[s][0][q])));
+                    AR[s + 1][2][q] = add_rn(ST[s][2][q], mul_rn(ch[q], sub_rn(right, ST[s][0][q])));
+                }
+                const float left0 = __shfl_up_sync(FULL, AR[s + 1][2][3], 1);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // its Ez update (main.py:21-27); Hx of the row above is one level up
+                    const float left = q > 0 ? AR[s + 1][2][q > 0 ? q - 1 : 0] : left0;
+                    const float curl = sub_rn(sub_rn(AR[s + 1][2][q], left), sub_rn(AR[s + 1][1][q], ST[s + 1][1][q]));
+                    AR[s + 1][0][q] = add_rn(ST[s][0][q], mul_rn(curl, ce[q]));
+                }
+            }
+            cr = (cr + 1) & (NC - 1);
+            const int r = i - K;  // the row that just left level K-1, K steps on
+            if (core && r >= tk.y0 && r < tk.y1) {
+                const long long o = base + (long long)r * p.pitch;
+                store4(p.out[0] + o, AR[K][0]);
+                store4(p.out[1] + o, AR[K][1]);
+                store4(p.out[2] + o, AR[K][2]);
+            }
+        };
+        int i = i0;
+#pragma unroll 1
+        for (; i + 1 < i1; i += 2) {
+            iter(X, Y, i);
+            iter(Y, X, i + 1);
+        }
+        if (i < i1) iter(X, Y, i);
+        cp_async_wait<0>();
+        __syncwarp();  // the ring is reused by the next run
+    }
+}
+
+}  // namespace fdtd2d
