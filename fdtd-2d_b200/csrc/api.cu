@@ -66,7 +66,7 @@ static const FastCfg kFastCfgs[] = {{4, 8, false, false},  {4, 12, false, false}
                                     {6, 8, false, false},  {8, 8, false, false},  {2, 16, false, false},
                                     {4, 16, true, false},  {4, 16, true, false},  {4, 16, true, true}};
 constexpr int N_FAST_CFG = sizeof(kFastCfgs) / sizeof(kFastCfgs[0]);
-constexpr int DEFAULT_FAST_CFG = 6;  // persistent TMA-fed 64 x 128 tiles: best measured (profiles/)
+constexpr int DEFAULT_FAST_CFG = 8;  // k = 8 passes of large grids: wavefront strips; otherwise persistent TMA-fed 64 x 128 tiles
 constexpr int MIN_LAST = 8;  // smallest core extent allowed for the last tile row/column (ring safety)
 
 struct TilePlan {
@@ -608,7 +608,11 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
             (pass == 0 ? pl->n_wave_rest : pl->n_wave_all) = (int)tasks.size() - (pass == 0 ? 0 : pl->n_wave_rest);
         }
         // small grids do not have enough runs to balance ~1200 independent warps: they stay on the tile kernel
-        if (n_plain < 4LL * WAVE_SEG * s->sm_count * WAVE_NW) tasks.clear(), pl->n_wave_rest = pl->n_wave_all = 0;
+        // measured on B200 (profiles/): from ~2 plain tiles per warp of the GPU (4096^2) the wavefront wins, below the
+        // persistent tile kernel does (3000^2: 592 vs 496 Gcell/s)
+        long long min_tiles = 2LL * s->sm_count * WAVE_NW;
+        if (const char* e = getenv("FDTD2D_WAVE_MIN_TILES")) min_tiles = std::max(0, atoi(e));
+        if (n_plain < min_tiles) tasks.clear(), pl->n_wave_rest = pl->n_wave_all = 0;
         if (!tasks.empty()) {
             CUDA_TRY(cudaMalloc(&pl->d_ticket, sizeof(int)));
             CUDA_TRY(cudaMalloc(&pl->d_wave, sizeof(WaveTask) * tasks.size()));
