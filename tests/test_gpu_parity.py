@@ -374,3 +374,55 @@ def test_kernel_variants_agree(fd, variant):
             outs.append(sim.state() + (sim.read_probes(640, n),))
     for a, b in zip(*outs):
         assert_bits(a, b, f"variant {variant} vs default")
+
+
+# --------------------------------------------------------------------------------------------
+# the row-streaming wavefront kernel (strip_wave.cuh): k = 8 passes of grids with many plain tiles
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,nsteps", [((300, 517), 40), ((1024, 1024), 24), ((203, 600), 17), ((2000, 260), 32),
+                                          ((700, 1500), 8)])
+def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, monkeypatch):
+    """Forced onto small grids (FDTD2D_WAVE_MIN_TILES=0) so the oracle can check it: runs of plain tiles broken by
+    sources and probes, ragged sizes, the remainder pass (nsteps % 8) on the tile kernel."""
+    monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", "0")
+    c_oracle, npo = oracle
+    R, C = shape
+    rng = np.random.default_rng(R * 31 + C)
+    eps, mu, Ez, Hx, Hy = _random_problem(rng, R, C, "float32")
+    ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(np.float32))
+    cells = [(R // 2, C // 2), (R // 3, C // 4), (7, 9)]
+    amp = npo.source_table("ricker", nsteps, DT, FC) + 0.125
+    probes = [(R // 2, C // 2 + 3), (0, 0), (R - 1, C - 1), (R // 4, C // 3), (3 * R // 4, 2 * C // 3)]
+    oEz, oHx, oHy = Ez.copy(), Hx.copy(), Hy.copy()
+    otrace = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, nsteps, amp, cells, probes, omp=True)
+    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
+        sim.set_kernel_variant(2)  # tile kernels (the cluster-resident kernel would take the small ones)
+        sim.set_coefficients(ce, ch, coef)
+        sim.set_state(Ez, Hx, Hy)
+        sim.set_sources([(0, r, c, 0) for r, c in cells], amp[None, :])
+        sim.set_probes(probes, nsteps)
+        sim.step(nsteps, 8)
+        gEz, gHx, gHy = sim.state()
+        gtrace = sim.read_probes()
+    assert_bits(gtrace, otrace, "probe trace")
+    assert_bits(gEz, oEz, "Ez")
+    assert_bits(gHx, oHx, "Hx")
+    assert_bits(gHy, oHy, "Hy")
+
+
+def test_wavefront_equals_tile_kernel_large(fd, monkeypatch):
+    """6000 x 5000 fp32, 40 steps near the Ricker peak: the wavefront strips (default at this size) and the persistent
+    TMA tile kernel (FDTD2D_WAVE_MIN_TILES huge) must agree bit for bit, also for a 3-grid batch."""
+    outs = []
+    for min_tiles in ("0", "100000000"):
+        monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", min_tiles)
+        with fd.Simulation(6000, 5000, np.float32, dt=DT, dx=DX) as sim:
+            sim.set_materials_random(seed=5, span=9.0)
+            sim.set_point_source(3000, 2500, 700, FC)
+            sim.set_probes([(3000, 2510), (10, 10), (5990, 4990)], 700)
+            sim.step_index = 640
+            sim.step(40, 8)
+            outs.append(sim.state() + (sim.read_probes(640, 40),))
+    assert np.abs(outs[0][0]).max() > 0.1
+    for a, b in zip(*outs):
+        assert_bits(a, b, "wavefront vs tile kernel")

@@ -14,6 +14,15 @@ def _devices():
     return tuple(range(torch.cuda.device_count()))
 
 
+@pytest.fixture(autouse=True, params=["default", "wavefront"])
+def plain_tile_kernel(request, monkeypatch):
+    """Every slab test runs with the default kernel choice and with the wavefront strips forced onto these small
+    grids (in a slab pass the band tiles stay on the tile kernel, the rest of the plain tiles become strip runs)."""
+    if request.param == "wavefront":
+        monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", "0")
+    return request.param
+
+
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
 @pytest.mark.parametrize("world,k", [(2, 4), (3, 8), (4, 5)])
 def test_slabs_match_single_domain_and_oracle(world, k, dtype):
