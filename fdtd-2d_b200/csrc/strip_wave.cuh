@@ -11,8 +11,9 @@
 // So every row is loaded once, stepped K times and stored once; the only recomputation is the 8 halo columns on each
 // side of the strip (12.5 %) and K warm-up rows per run of rows (< 4 %).  A warp never talks to another warp: no
 // __syncthreads, no shared-memory exchange of field rows; column neighbours come from two shuffles per row and level.
-// Rows are prefetched two iterations ahead with cp.async (16 B per lane and array) into a small per-warp ring; the
-// coefficient rows stay in that ring until the last level has used them (K + 3 rows later).
+// Rows are prefetched three iterations ahead with cp.async (16 B per lane and array) into a small per-warp ring; the
+// coefficient rows stay in their ring until the last level has used them (K rows later).  Runs of rows are handed
+// out to the warps dynamically (one atomic per run).
 // Cells next to the strip's edge columns and above the first / below the last row of the run read neighbours that are
 // missing; they go stale one cell per level exactly as in the overlapped tiles and are never stored.
 // Arithmetic and results are bit-identical to the other kernels (same operations, same order).
@@ -23,7 +24,8 @@
 namespace fdtd2d {
 
 constexpr int WAVE_NW = 8;      // warps per CTA: 2 per scheduler, each may use up to 255 registers for the K-level window
-constexpr int WAVE_P = 3;       // rows prefetched ahead (field ring of P + 1 = 4 rows)
+constexpr int WAVE_P = 3;       // rows prefetched ahead (6 was measured: no gain)
+constexpr int WAVE_NF = 4;      // rows of the field ring (a power of two > P)
 constexpr int WAVE_NC = 16;     // rows of the coefficient ring (a power of two >= K + P + 2)
 constexpr int WAVE_TW = 128;    // strip width (columns per warp)
 
@@ -33,7 +35,7 @@ struct WaveTask {
 };
 
 __host__ __device__ constexpr size_t wave_smem_bytes() {
-    return (size_t)WAVE_NW * ((WAVE_P + 1) * 3 + WAVE_NC * 2) * WAVE_TW * sizeof(float);
+    return (size_t)WAVE_NW * (WAVE_NF * 3 + WAVE_NC * 2) * WAVE_TW * sizeof(float);
 }
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
@@ -45,8 +47,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 template <int K>
 __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassParams<float> p, const WaveTask* tasks, const int n_tasks, int* ticket) {
-    constexpr int TW = WAVE_TW, P = WAVE_P, NF = P + 1, NC = WAVE_NC;
-    static_assert((NF & (NF - 1)) == 0 && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
+    constexpr int TW = WAVE_TW, P = WAVE_P, NF = WAVE_NF, NC = WAVE_NC;
+    static_assert((NF & (NF - 1)) == 0 && NF > P && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_wave[];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
