@@ -382,7 +382,8 @@ def main():
                        "batch_per_gpu": batch or 1, "inner_leapfrog_steps_per_step": inner,
                        "k_temporal": None if resident else k,
                        "kernel": ("cluster-resident (grid on chip for the whole step call, 1 launch per bench step)" if resident
-                                  else f"overlapped tiles, {k} leapfrog steps per HBM round trip"),
+                                  else f"{k} leapfrog steps per HBM round trip: row-streaming wavefront strips on the plain regions (k = 8, "
+                                       "large grids) or persistent TMA-fed tiles, edge-capable tiles on the ring / sources / probes"),
                        "parallelism": ("independent grids per rank" if batch else f"y-slabs x{world}") if world > 1 else "single GPU",
                        "l2": "state is larger than L2 (inputs larger than L2; no flush needed)",
                        "seed": 2026, "source": "ricker fc=30e9 at centre", "probes": len(probes)},
