@@ -605,6 +605,13 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
                         run = ok ? 1 : 0;
                     }
                 }
+            // hand the runs out row band by row band: warps that work at the same time then hold neighbouring strips of
+            // the same rows, so the 8 halo columns they share are read from DRAM once and from L2 the second time
+            std::stable_sort(tasks.begin() + (pass == 0 ? 0 : pl->n_wave_rest), tasks.end(), [](const WaveTask& a, const WaveTask& b) {
+                if (a.b != b.b) return a.b < b.b;
+                if (a.y0 != b.y0) return a.y0 < b.y0;
+                return a.x0 < b.x0;
+            });
             (pass == 0 ? pl->n_wave_rest : pl->n_wave_all) = (int)tasks.size() - (pass == 0 ? 0 : pl->n_wave_rest);
         }
         // small grids do not have enough runs to balance ~1200 independent warps: they stay on the tile kernel
