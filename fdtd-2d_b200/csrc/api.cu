@@ -127,6 +127,9 @@ struct fdtd2d_sim {
     int tma_box_rows = 0;              // box height the maps were encoded for (0 = not built)
     int sm_count = 0;
     int open_pass_k = 0;  // > 0 between fdtd2d_pass_begin and fdtd2d_pass_end
+    int ch_uniform = -1;      // dt/(mu*dx) the same in every cell? (-1 = not checked since the maps last changed)
+    float ch_value = 0.0f;
+    int* d_flag = nullptr;
     int resident_ok = -1;     // cluster-resident kernel usable for this handle? (-1 = not decided yet)
     int resident_cluster = 0, resident_rpc = 0, resident_edge = 0, resident_cfg = 0;  // CTAs per grid, rows per middle / first CTA, kResCfgs index
     unsigned char* d_gray = nullptr;  // snapshot background (Rl x C per grid)
@@ -403,18 +406,53 @@ template <int MR, int NW, bool PAIR> static int launch_tma_t(fdtd2d_sim* s, cons
     return 0;
 }
 
+// Is dt/(mu*dx) one value in every cell of the local array?  (True for every material_init output: main.py:105,121.)
+__global__ void uniform_check_kernel(const float* a, int rows, int cols, int pitch, int* differs) {
+    const float v = a[0];
+    const long long n = (long long)rows * cols;
+    int bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+        bad |= a[(long long)r * pitch + c] != v;
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(differs, 1);
+}
+
+static int check_ch_uniform(fdtd2d_sim* s) {
+    if (s->ch_uniform >= 0) return 0;
+    if (!s->d_flag) CUDA_TRY(cudaMalloc(&s->d_flag, sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
+    // the batch grids are back to back: rows = batch * Rl
+    uniform_check_kernel<<<148 * 8, 256, 0, s->stream>>>((const float*)s->ch, s->batch * s->Rl, s->C, (int)s->pitch, s->d_flag);
+    CUDA_TRY(cudaGetLastError());
+    int differs = 1;
+    CUDA_TRY(cudaMemcpyAsync(&differs, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(&s->ch_value, s->ch, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->ch_uniform = differs ? 0 : 1;
+    if (const char* e = getenv("FDTD2D_NO_UNIFORM_CH"))
+        if (atoi(e)) s->ch_uniform = 0;
+    s->launches += 1;
+    return 0;
+}
+
 static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[s->device % MAX_DEVICES];
     const size_t smem = wave_smem_bytes();
     if (!done) {
-        CUDA_TRY(cudaFuncSetAttribute(strip_wave_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(strip_wave_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(strip_wave_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
     }
+    if (int rc = check_ch_uniform(s)) return rc;
     if (!s->sm_count) CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
     const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, s->sm_count);
     CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int), s->stream));
-    strip_wave_kernel<8><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket);
+    if (s->ch_uniform == 1)  // uniform permeability: the map is not read at all (28 instead of 32 B per cell and pass)
+        strip_wave_kernel<8, true><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, s->ch_value);
+    else
+        strip_wave_kernel<8, false><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, 0.0f);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -1010,6 +1048,7 @@ int fdtd2d_destroy(fdtd2d_sim* s) {
     cudaFree(s->d_gray);
     cudaFree(s->d_rgb);
     cudaFree(s->d_lut);
+    cudaFree(s->d_flag);
     free_plans(s);
     if (s->side_stream) cudaStreamDestroy(s->side_stream);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -1105,6 +1144,7 @@ int fdtd2d_set_coeffs(fdtd2d_sim* s, const void* ce, const void* ch, const void*
     if (int rc = transfer_field(s, s->ch, const_cast<void*>(ch), s->Rl, s->C, true)) return rc;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->coeffs_set = true;
+    s->ch_uniform = -1;
     if (mur_coef) return fdtd2d_set_mur_coef(s, mur_coef);
     return 0;
 }
@@ -1141,6 +1181,7 @@ int fdtd2d_set_materials_random(fdtd2d_sim* s, uint64_t seed, double span, doubl
     CUDA_TRY(cudaGetLastError());
     s->launches += 1;
     s->coeffs_set = true;
+    s->ch_uniform = -1;
     s->mur_set = true;
     return 0;
 }
@@ -1168,6 +1209,7 @@ static int finish_materials(fdtd2d_sim* s, double dt, double dx) {
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->launches += has_corner ? 2 : 1;
     s->coeffs_set = true;
+    s->ch_uniform = -1;
     if (has_corner) s->mur_set = true;
     return 0;
 }

@@ -45,8 +45,10 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_sr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int K>
-__global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassParams<float> p, const WaveTask* tasks, const int n_tasks, int* ticket) {
+// UCH: dt/(mu*dx) is the same in every cell (true for every material_init output, main.py:105,121): it comes as a
+// kernel argument and the map is neither fetched nor kept in the ring.
+template <int K, bool UCH>
+__global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassParams<float> p, const WaveTask* tasks, const int n_tasks, int* ticket, const float ch_uniform) {
     constexpr int TW = WAVE_TW, P = WAVE_P, NF = WAVE_NF, NC = WAVE_NC;
     static_assert((NF & (NF - 1)) == 0 && NF > P && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
     constexpr unsigned FULL = 0xffffffffu;
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassP
             cp_async16(fring + (fs * 3 + 1) * TW, p.in[1] + o);
             cp_async16(fring + (fs * 3 + 2) * TW, p.in[2] + o);
             cp_async16(cring + (cs * 2 + 0) * TW, p.ce + o);
-            cp_async16(cring + (cs * 2 + 1) * TW, p.ch + o);
+            if (!UCH) cp_async16(cring + (cs * 2 + 1) * TW, p.ch + o);
         };
         // The window: two register sets X, Y that swap roles every iteration so that no row is ever moved.  In an
         // iteration ST[s] (s < K) is the row stored at level s (row i-s-1 when row i arrives), ST[K][1] the Hx of the
@@ -115,7 +117,10 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassP
                 float ce[4], ch[4];
                 const int c = (cr - s) & (NC - 1);  // coefficient slot of row i-s-1
                 load4(cring + (c * 2 + 0) * TW, ce);
-                load4(cring + (c * 2 + 1) * TW, ch);
+                if (UCH)
+                    ch[0] = ch[1] = ch[2] = ch[3] = ch_uniform;
+                else
+                    load4(cring + (c * 2 + 1) * TW, ch);
                 const float right3 = __shfl_down_sync(FULL, ST[s][0][0], 1);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {  // H half-step of the stored row (main.py:69-74)

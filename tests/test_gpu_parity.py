@@ -381,7 +381,8 @@ def test_kernel_variants_agree(fd, variant):
 # --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape,nsteps", [((300, 517), 40), ((1024, 1024), 24), ((203, 600), 17), ((2000, 260), 32),
                                           ((700, 1500), 8)])
-def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, monkeypatch):
+@pytest.mark.parametrize("uniform_mu", [False, True])
+def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, uniform_mu, monkeypatch):
     """Forced onto small grids (FDTD2D_WAVE_MIN_TILES=0) so the oracle can check it: runs of plain tiles broken by
     sources and probes, ragged sizes, the remainder pass (nsteps % 8) on the tile kernel."""
     monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", "0")
@@ -389,6 +390,8 @@ def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, monkeypatch):
     R, C = shape
     rng = np.random.default_rng(R * 31 + C)
     eps, mu, Ez, Hx, Hy = _random_problem(rng, R, C, "float32")
+    if uniform_mu:  # every material_init output: the kernel then takes dt/(mu*dx) as a scalar and skips the map
+        mu[...] = np.float32(4 * np.pi * 1e-7)
     ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(np.float32))
     cells = [(R // 2, C // 2), (R // 3, C // 4), (7, 9)]
     amp = npo.source_table("ricker", nsteps, DT, FC) + 0.125
