@@ -900,6 +900,11 @@ static int run_pass(fdtd2d_sim* s, int k, int phases) {
 // 2-D copy between a dense host array (rows x width elements) and the padded device layout
 static int copy2d(const fdtd2d_sim* s, void* dev, void* host, int rows, int width, bool to_device) {
     const size_t wbytes = (size_t)width * s->esize;
+    if ((size_t)width == s->pitch) {  // no padding on either side: one linear copy
+        CUDA_TRY(cudaMemcpyAsync(to_device ? dev : host, to_device ? host : dev, wbytes * rows,
+                                 to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, s->stream));
+        return 0;
+    }
     if (to_device)
         CUDA_TRY(cudaMemcpy2DAsync(dev, s->pitch * s->esize, host, wbytes, wbytes, rows, cudaMemcpyHostToDevice,
                                    s->stream));
