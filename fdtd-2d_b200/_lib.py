@@ -9,7 +9,7 @@ from .build import LIB_PATH
 
 F32, F64 = 0, 1
 PHASE_H, PHASE_E, PHASE_SRC = 1, 2, 4
-MAX_K = 8
+MAX_K = 12
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -52,6 +52,7 @@ _SIGNATURES = {
     "fdtd2d_set_step_index": ([_vp, _i64], _i),
     "fdtd2d_set_kernel_variant": ([_vp, _i], _i),
     "fdtd2d_launch_count": ([_vp, ctypes.POINTER(_i64)], _i),
+    "fdtd2d_pass_count": ([_vp, ctypes.POINTER(_i64)], _i),
     "fdtd2d_halo_block": ([_vp, _i, _i, _pp, _pp, ctypes.POINTER(_sz)], _i),
     "fdtd2d_halo_block_next": ([_vp, _i, _i, _pp, _pp, ctypes.POINTER(_sz)], _i),
     "fdtd2d_pass_begin": ([_vp, _i], _i),

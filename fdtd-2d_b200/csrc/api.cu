@@ -116,7 +116,7 @@ struct fdtd2d_sim {
     void* d_trace = nullptr;
     long long trace_cap = 0;
     std::vector<int> probe_perm;  // sorted position -> caller's index
-    long long step = 0, launches = 0;
+    long long step = 0, launches = 0, passes = 0;
     int variant = 0;
     int fast_cfg = DEFAULT_FAST_CFG;
     cudaStream_t side_stream = nullptr;  // generic (edge) tiles run here, concurrently with the fast tiles
@@ -436,25 +436,45 @@ static int check_ch_uniform(fdtd2d_sim* s) {
     return 0;
 }
 
-static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket) {
+// One instantiation of the wavefront kernel: K levels, scalar or uniform dt/(mu*dx), P rows of prefetch, X2 = packed
+// two-wide fp32 instructions (strip_wave_x2_kernel).
+template <int K, bool UCH, int P, bool X2>
+static int launch_wave_t(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, int grid) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[s->device % MAX_DEVICES];
     const size_t smem = wave_smem_bytes();
-    if (!done) {
-        CUDA_TRY(cudaFuncSetAttribute(strip_wave_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(strip_wave_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        done = true;
+    const float chv = UCH ? s->ch_value : 0.0f;
+    if (X2) {
+        if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_x2_kernel<K, UCH, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        strip_wave_x2_kernel<K, UCH, P><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, chv, 0x8000000080000000ull);
+    } else {
+        if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_kernel<K, UCH, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        strip_wave_kernel<K, UCH, P><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, chv);
     }
+    done = true;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// FDTD2D_WAVE_X2=0 selects the scalar instantiations (FADD/FMUL) instead of the packed ones (FADD2/FFMA2)
+static bool wave_x2() {
+    const char* e = getenv("FDTD2D_WAVE_X2");
+    return e ? atoi(e) != 0 : true;
+}
+
+static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k) {
     if (int rc = check_ch_uniform(s)) return rc;
     if (!s->sm_count) CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
     const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, s->sm_count);
     CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int), s->stream));
-    if (s->ch_uniform == 1)  // uniform permeability: the map is not read at all (28 instead of 32 B per cell and pass)
-        strip_wave_kernel<8, true><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, s->ch_value);
-    else
-        strip_wave_kernel<8, false><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, 0.0f);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
+    const bool uch = s->ch_uniform == 1;  // uniform permeability: the map is not read at all (28 instead of 32 B per cell and pass)
+    const bool x2 = wave_x2();
+    if (k == 12) {  // (runs for k = 12 are only built when the permeability is uniform)
+        if (!uch) return fail(FDTD2D_EINVAL, "the 12-level wavefront kernel needs uniform permeability");
+        return x2 ? launch_wave_t<12, true, 2, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<12, true, 2, false>(s, p, tasks, n_tasks, ticket, grid);
+    }
+    if (uch) return x2 ? launch_wave_t<8, true, WAVE_P, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<8, true, WAVE_P, false>(s, p, tasks, n_tasks, ticket, grid);
+    return x2 ? launch_wave_t<8, false, WAVE_P, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<8, false, WAVE_P, false>(s, p, tasks, n_tasks, ticket, grid);
 }
 
 template <typename T, int MR, int NW> static int launch_edge_tt(int dev, const PassParams<T>& p, int n_tiles, cudaStream_t st) {
@@ -562,6 +582,8 @@ static void free_plans(fdtd2d_sim* s) {
     }
 }
 
+static int check_ch_uniform(fdtd2d_sim* s);
+
 // Split the TH x 128 tile grid into plain tiles (fast kernel) and the rest (generic kernel).
 static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
     TilePlan& tp = pl->tp;
@@ -614,7 +636,13 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
                 (plain ? (band ? fast : fast_rest) : (band ? gen : gen_rest)).push_back(id);
             }
         }
-    if (kFastCfgs[s->fast_cfg].wave && k == 8) {
+    // the wavefront kernel exists for k = 8 and, with uniform permeability, for k = 12
+    bool wave_k = kFastCfgs[s->fast_cfg].wave && (k == 8 || k == 12);
+    if (wave_k && k == 12) {
+        if (int rc = check_ch_uniform(s)) return rc;
+        wave_k = s->ch_uniform == 1;
+    }
+    if (wave_k) {
         // vertical runs of plain tiles of one tile column -> wavefront tasks of at most WAVE_SEG tiles: long enough
         // to amortise the 2k warm-up rows, short enough that every warp of the GPU gets several
         if (!s->sm_count) CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
@@ -738,7 +766,7 @@ static int launch_hybrid(fdtd2d_sim* s, int k, int part) {
         const int n_tasks = part == 2 ? pl.n_wave_rest : pl.n_wave_all;
         p.tile_list = nullptr;
         if (n_tasks)
-            if (int rc = launch_wave(s, p, tasks, n_tasks, pl.d_ticket)) return rc;
+            if (int rc = launch_wave(s, p, tasks, n_tasks, pl.d_ticket, k)) return rc;
         s->launches += n_tasks ? 1 : 0;
     } else if (n_fst) {
         p.tile_list = pl.d_fast + f_off;
@@ -864,6 +892,7 @@ template <int MR, int NW> static int launch_resident_t(fdtd2d_sim* s, int n_step
     }
     CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_resident_kernel<MR, NW>, p));
     s->launches += 1;
+    s->passes += 1;
     s->cur ^= 1;
     return 0;
 }
@@ -894,6 +923,7 @@ static int run_pass(fdtd2d_sim* s, int k, int phases) {
         rc = launch_generic_all<float>(s, k, phases);
     if (rc) return rc;
     s->cur ^= 1;
+    s->passes += 1;
     return 0;
 }
 
@@ -1432,6 +1462,16 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
     }
     if (s->variant == 4 && n_steps > 0) return fail(FDTD2D_EINVAL, "variant 4 (cluster-resident) needs fp32, 16..256 columns, 16..384 rows, no slabs");
     int k = k_temporal ? k_temporal : (s->dtype == FDTD2D_F32 ? 8 : 4);
+    if (!k_temporal && s->dtype == FDTD2D_F32 && s->variant != 1 && !s->has_top_nb && !s->has_bot_nb && n_steps >= 12 &&
+        getenv("FDTD2D_AUTO_K12")) {
+        // large grid with uniform permeability: the 12-level wavefront moves a third less DRAM traffic per step, but on
+        // B200 it is bound by latency (2 warps per scheduler at 255 registers), not by DRAM: 1418 against 1564 Gcell/s
+        // at 16384^2 -- so it is opt-in (k_temporal = 12, or this variable for the automatic choice)
+        PassPlan& pl = s->hybrid[12];
+        if (!pl.valid)
+            if (int rc = classify_tiles(s, 12, &pl)) return rc;
+        if (pl.d_wave) k = 12;
+    }
     if (s->has_top_nb || s->has_bot_nb) {
         k = std::min(k, s->halo);
         REQUIRE(n_steps <= s->halo, "a slab handle can advance at most halo=%d steps between halo exchanges", s->halo);
@@ -1471,6 +1511,12 @@ int fdtd2d_set_step_index(fdtd2d_sim* s, int64_t step) {
 int fdtd2d_set_kernel_variant(fdtd2d_sim* s, int variant) {
     REQUIRE(s && variant >= 0 && variant <= 4, "bad argument");
     s->variant = variant;
+    return 0;
+}
+
+int fdtd2d_pass_count(const fdtd2d_sim* s, int64_t* passes) {
+    REQUIRE(s && passes, "null argument");
+    *passes = s->passes;
     return 0;
 }
 
@@ -1535,6 +1581,7 @@ int fdtd2d_pass_end(fdtd2d_sim* s) {
         if (int rc = launch_hybrid(s, k, 2)) return rc;
     s->open_pass_k = 0;
     s->cur ^= 1;
+    s->passes += 1;
     s->step += k;
     return 0;
 }

@@ -24,7 +24,7 @@
 namespace fdtd2d {
 
 constexpr int WAVE_NW = 8;      // warps per CTA: 2 per scheduler, each may use up to 255 registers for the K-level window
-constexpr int WAVE_P = 3;       // rows prefetched ahead (6 was measured: no gain)
+constexpr int WAVE_P = 3;       // rows prefetched ahead at K = 8 (6 was measured: no gain); K = 12 uses 2 so the ring still fits
 constexpr int WAVE_NF = 4;      // rows of the field ring (a power of two > P)
 constexpr int WAVE_NC = 16;     // rows of the coefficient ring (a power of two >= K + P + 2)
 constexpr int WAVE_TW = 128;    // strip width (columns per warp)
@@ -47,9 +47,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 // UCH: dt/(mu*dx) is the same in every cell (true for every material_init output, main.py:105,121): it comes as a
 // kernel argument and the map is neither fetched nor kept in the ring.
-template <int K, bool UCH>
+template <int K, bool UCH, int P>
 __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassParams<float> p, const WaveTask* tasks, const int n_tasks, int* ticket, const float ch_uniform) {
-    constexpr int TW = WAVE_TW, P = WAVE_P, NF = WAVE_NF, NC = WAVE_NC;
+    constexpr int TW = WAVE_TW, NF = WAVE_NF, NC = WAVE_NC;
     static_assert((NF & (NF - 1)) == 0 && NF > P && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_wave[];
@@ -154,6 +154,137 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassP
         if (i < i1) iter(X, Y, i);
         cp_async_wait<0>();
         __syncwarp();  // the ring is reused by the next run
+    }
+}
+
+// ---- packed variant: the same wavefront with Blackwell's two-wide fp32 instructions ------------------------------------
+// sm_100a has add/sub/fma.rn.f32x2 (SASS FADD2 / FFMA2): one instruction, two IEEE round-to-nearest results on an aligned
+// register pair.  They run at half the issue rate of FADD (measured, profiles/micro/f32x2_rate.cu: 0.50 against 0.96
+// warp-instructions per clock and scheduler), i.e. the same 128 lane-operations per clock and SM, but they take half the
+// ISSUE SLOTS -- and the scalar kernel above is bound by issue (79 %), its FP pipe only 63 % busy.  A lane's four columns
+// are two pairs (c, c+1), (c+2, c+3), exactly as the 16-byte loads deliver them; only the two column differences, whose
+// operands straddle the pairs, stay scalar (their results land in a pair directly, so no register moves).
+// A level is 18 packed + 8 scalar instructions + 2 shuffles instead of 44 + 2, which is what makes K = 12 levels pay.
+// Bit-exactness: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with --fmad false (scalar code is not
+// touched), so the product is written as fma.rn.f32x2(a, b, -0) with the -0 pair coming in as a kernel argument the
+// compiler cannot see through: rn(a*b + -0) = rn(a*b) for every input incl. signed zeros, and an FFMA2 that already
+// has an addend cannot absorb the add that follows.
+using u64 = unsigned long long;
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 c; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 c; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b, u64 negzero) { u64 c; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(c) : "l"(a), "l"(b), "l"(negzero)); return c; }
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 c; asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(lo), "f"(hi)); return c; }
+__device__ __forceinline__ float lo2(u64 a) { return __uint_as_float((uint32_t)a); }
+__device__ __forceinline__ float hi2(u64 a) { return __uint_as_float((uint32_t)(a >> 32)); }
+__device__ __forceinline__ void load22(const float* p, u64* a) { const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p); a[0] = v.x, a[1] = v.y; }
+__device__ __forceinline__ void store22(float* p, const u64* a) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a[0], a[1]); }
+
+template <int K, bool UCH, int P>
+__global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const PassParams<float> p, const WaveTask* tasks, const int n_tasks, int* ticket, const float ch_uniform, const u64 negzero) {
+    constexpr int TW = WAVE_TW, NF = WAVE_NF, NC = WAVE_NC;
+    static_assert((NF & (NF - 1)) == 0 && NF > P && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_wave[];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    float* fring = reinterpret_cast<float*>(smem_wave) + (size_t)w * (NF * 3 + NC * 2) * TW + 4 * l;  // [NF][3][TW], my 4 columns
+    float* cring = fring + NF * 3 * TW;                                                              // [NC][2][TW]
+    const bool core = 4 * l >= p.hx && 4 * l < p.hx + p.CW;
+    const u64 chu = pack2(ch_uniform, ch_uniform);
+
+    for (;;) {
+        int t = 0;
+        if (l == 0) t = atomicAdd(ticket, 1);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= n_tasks) break;
+        const WaveTask tk = tasks[t];
+        const long long base = (long long)tk.b * p.grid_stride + tk.x0 + 4 * l;
+        const int i0 = tk.y0 - K, i1 = tk.y1 + K;  // level-0 rows [i0, i1)
+        auto fetch = [&](int row, int fs, int cs) {
+            const long long o = base + (long long)row * p.pitch;
+            cp_async16(fring + (fs * 3 + 0) * TW, p.in[0] + o);
+            cp_async16(fring + (fs * 3 + 1) * TW, p.in[1] + o);
+            cp_async16(fring + (fs * 3 + 2) * TW, p.in[2] + o);
+            cp_async16(cring + (cs * 2 + 0) * TW, p.ce + o);
+            if (!UCH) cp_async16(cring + (cs * 2 + 1) * TW, p.ch + o);
+        };
+        // the window of strip_wave_kernel, every row as two column pairs
+        u64 X[K + 1][3][2], Y[K + 1][3][2];
+#pragma unroll
+        for (int s = 0; s <= K; ++s)
+#pragma unroll
+            for (int f = 0; f < 3; ++f) X[s][f][0] = X[s][f][1] = Y[s][f][0] = Y[s][f][1] = 0ull;
+        int fs = 0, cs = 1;
+        {
+            const float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            store4(cring + 0 * TW, z);
+            store4(cring + 1 * TW, z);
+        }
+#pragma unroll
+        for (int d = 0; d < P; ++d) {
+            fetch(i0 + d, fs, cs);
+            cp_async_commit();
+            fs = (fs + 1) & (NF - 1);
+            cs = (cs + 1) & (NC - 1);
+        }
+        int fr = 0, cr = 0;
+        auto iter = [&](u64 (&ST)[K + 1][3][2], u64 (&AR)[K + 1][3][2], const int i) {
+            if (i + P < i1) fetch(i + P, fs, cs);
+            cp_async_commit();
+            fs = (fs + 1) & (NF - 1);
+            cs = (cs + 1) & (NC - 1);
+            cp_async_wait<P>();
+            load22(fring + (fr * 3 + 0) * TW, AR[0][0]);
+            load22(fring + (fr * 3 + 1) * TW, AR[0][1]);
+            load22(fring + (fr * 3 + 2) * TW, AR[0][2]);
+            fr = (fr + 1) & (NF - 1);
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                u64 ce[2], ch[2];
+                const int c = (cr - s) & (NC - 1);  // coefficient slot of row i-s-1
+                load22(cring + (c * 2 + 0) * TW, ce);
+                if (UCH)
+                    ch[0] = ch[1] = chu;
+                else
+                    load22(cring + (c * 2 + 1) * TW, ch);
+                const u64 e0 = ST[s][0][0], e1 = ST[s][0][1];
+                // H half-step of the stored row (main.py:69-74).  The column differences straddle the pairs, so they
+                // are four scalar subtractions written straight into a pair (no register moves); the rest is two-wide.
+                const float right3 = __shfl_down_sync(FULL, lo2(e0), 1);
+                const u64 dx0 = pack2(sub_rn(hi2(e0), lo2(e0)), sub_rn(lo2(e1), hi2(e0)));
+                const u64 dx1 = pack2(sub_rn(hi2(e1), lo2(e1)), sub_rn(right3, hi2(e1)));
+                AR[s + 1][1][0] = sub2(ST[s][1][0], mul2(ch[0], sub2(AR[s][0][0], e0), negzero));
+                AR[s + 1][1][1] = sub2(ST[s][1][1], mul2(ch[1], sub2(AR[s][0][1], e1), negzero));
+                const u64 y0 = add2(ST[s][2][0], mul2(ch[0], dx0, negzero));
+                const u64 y1 = add2(ST[s][2][1], mul2(ch[1], dx1, negzero));
+                AR[s + 1][2][0] = y0;
+                AR[s + 1][2][1] = y1;
+                // its Ez update (main.py:21-27); Hx of the row above is one level up
+                const float left0 = __shfl_up_sync(FULL, hi2(y1), 1);
+                const u64 dy0 = pack2(sub_rn(lo2(y0), left0), sub_rn(hi2(y0), lo2(y0)));
+                const u64 dy1 = pack2(sub_rn(lo2(y1), hi2(y0)), sub_rn(hi2(y1), lo2(y1)));
+                const u64 curl0 = sub2(dy0, sub2(AR[s + 1][1][0], ST[s + 1][1][0]));
+                const u64 curl1 = sub2(dy1, sub2(AR[s + 1][1][1], ST[s + 1][1][1]));
+                AR[s + 1][0][0] = add2(e0, mul2(curl0, ce[0], negzero));
+                AR[s + 1][0][1] = add2(e1, mul2(curl1, ce[1], negzero));
+            }
+            cr = (cr + 1) & (NC - 1);
+            const int r = i - K;
+            if (core && r >= tk.y0 && r < tk.y1) {
+                const long long o = base + (long long)r * p.pitch;
+                store22(p.out[0] + o, AR[K][0]);
+                store22(p.out[1] + o, AR[K][1]);
+                store22(p.out[2] + o, AR[K][2]);
+            }
+        };
+        int i = i0;
+#pragma unroll 1
+        for (; i + 1 < i1; i += 2) {
+            iter(X, Y, i);
+            iter(Y, X, i + 1);
+        }
+        if (i < i1) iter(X, Y, i);
+        cp_async_wait<0>();
+        __syncwarp();
     }
 }
 

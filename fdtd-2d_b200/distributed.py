@@ -189,11 +189,12 @@ class SlabSimulation:
         (fdtd2d_pass_begin) and runs it on a side stream while the rest of the pass computes."""
         from . import DEFAULT_K
 
-        k = k or DEFAULT_K
         if self.world == 1:
-            self.sim.step(n_steps, k)
-            self.tile_launch_count += -(-n_steps // k)
+            before = self.sim.pass_count
+            self.sim.step(n_steps, k)  # k = 0: the library picks (8, or 12 for a large grid with uniform permeability)
+            self.tile_launch_count += self.sim.pass_count - before
             return
+        k = k or DEFAULT_K
         import torch
 
         k = min(k, self.halo)

@@ -255,6 +255,13 @@ class Simulation:
         check(lib().fdtd2d_set_kernel_variant(self._h, variant))
 
     @property
+    def pass_count(self) -> int:
+        """Stepping passes so far (HBM round trips of the fields)."""
+        v = ctypes.c_int64()
+        check(lib().fdtd2d_pass_count(self._h, ctypes.byref(v)))
+        return v.value
+
+    @property
     def launch_count(self) -> int:
         v = ctypes.c_int64()
         check(lib().fdtd2d_launch_count(self._h, ctypes.byref(v)))

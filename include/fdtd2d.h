@@ -127,8 +127,9 @@ int fdtd2d_read_probes(fdtd2d_sim* s, void* out, int64_t first_step, int n_steps
 /* ---- time stepping: replaces the loop body fdtd.py:31-34 ------------------------------------- */
 /* n_steps leapfrog steps (H -> Ez+Mur+corners -> source -> probe sample), k_temporal steps per HBM
  * round trip (1 <= k <= FDTD2D_MAX_K; for slabs k <= halo and the caller exchanges halos every k).
- * k_temporal = 0 picks the library default. */
-#define FDTD2D_MAX_K 8
+ * k_temporal = 0 picks the library default (fp64: 4; fp32: 8, or 12 for a large grid with uniform permeability,
+ * where the row-streaming wavefront kernel has a 12-level instance). */
+#define FDTD2D_MAX_K 12
 int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal);
 /* One pass applying only the phases in `phases` (FDTD2D_PHASE_*); with PHASE_H alone it is
  * update_Hx_Hy (main.py:66-76), with PHASE_E alone update_Ez (main.py:12-63).  Does not advance the
@@ -143,6 +144,9 @@ int fdtd2d_set_step_index(fdtd2d_sim* s, int64_t step);
  *     fdtd2d_step call, one thread-block cluster per grid; k_temporal does not apply) or FDTD2D_EINVAL.
  * Automatic = 4 when the grid is eligible, else 2. */
 int fdtd2d_set_kernel_variant(fdtd2d_sim* s, int variant);
+/* Number of stepping passes so far: one per HBM round trip of the fields (k leapfrog steps of the tile / wavefront
+ * kernels, or a whole fdtd2d_step call of the cluster-resident kernel).  bench.py's roofline divides by it. */
+int fdtd2d_pass_count(const fdtd2d_sim* s, int64_t* passes);
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 int fdtd2d_launch_count(const fdtd2d_sim* s, int64_t* launches);
 

@@ -1,4 +1,4 @@
-"""k sweep of the tile kernels on one GPU.  usage: [KS=8] [SIZES=4096,16384] [FDTD2D_FAST_CFG=n] python profiles/quick_bench.py"""
+"""k sweep of the tile kernels on one GPU (k = 0: library default).  usage: [KS=8] [SIZES=4096,16384] [FDTD2D_FAST_CFG=n] python profiles/quick_bench.py"""
 import os, sys, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fdtd2d_b200 as fd, torch
@@ -10,8 +10,8 @@ for R in [int(x) for x in os.environ.get("SIZES", "4096,16384").split(",")]:
             sim.set_stream(torch.cuda.current_stream().cuda_stream)
             sim.set_materials_random(1, 9.0)
             sim.set_point_source(R // 2, C // 2, 2000, 30e9)
-            sim.step(2 * k, k); torch.cuda.synchronize()
-            n = 16 * k
+            sim.step(2 * (k or 12), k); torch.cuda.synchronize()
+            n = 16 * (k or 12)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); sim.step(n, k); e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)

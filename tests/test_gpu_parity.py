@@ -306,7 +306,7 @@ def test_errors(fd):
         assert e.value.code == -4  # materials not set
         sim.set_materials(*fd.material_init(None, 32, 32))
         with pytest.raises(fd.Fdtd2dError):
-            sim.step(1, 9)  # k > FDTD2D_MAX_K
+            sim.step(1, 13)  # k > FDTD2D_MAX_K
         with pytest.raises(fd.Fdtd2dError):
             sim.set_sources([(0, 40, 3, 0)], np.zeros((1, 4)))  # outside the grid
         with pytest.raises(fd.Fdtd2dError):
@@ -377,15 +377,19 @@ def test_kernel_variants_agree(fd, variant):
 
 
 # --------------------------------------------------------------------------------------------
-# the row-streaming wavefront kernel (strip_wave.cuh): k = 8 passes of grids with many plain tiles
+# the row-streaming wavefront kernel (strip_wave.cuh): k = 8 / k = 12 passes of grids with many plain tiles
 # --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape,nsteps", [((300, 517), 40), ((1024, 1024), 24), ((203, 600), 17), ((2000, 260), 32),
                                           ((700, 1500), 8)])
 @pytest.mark.parametrize("uniform_mu", [False, True])
-def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, uniform_mu, monkeypatch):
+@pytest.mark.parametrize("k,x2", [(8, "1"), (8, "0"), (12, "1"), (12, "0")])
+def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, uniform_mu, k, x2, monkeypatch):
     """Forced onto small grids (FDTD2D_WAVE_MIN_TILES=0) so the oracle can check it: runs of plain tiles broken by
-    sources and probes, ragged sizes, the remainder pass (nsteps % 8) on the tile kernel."""
+    sources and probes, ragged sizes, the remainder pass (nsteps % k) on the tile kernel; the packed (FADD2 / FFMA2,
+    x2 = 1) and the scalar instantiations; 12 levels exist for uniform permeability (otherwise those passes run on the
+    tile kernels, which is checked all the same)."""
     monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", "0")
+    monkeypatch.setenv("FDTD2D_WAVE_X2", x2)
     c_oracle, npo = oracle
     R, C = shape
     rng = np.random.default_rng(R * 31 + C)
@@ -404,7 +408,7 @@ def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, uniform_mu, monke
         sim.set_state(Ez, Hx, Hy)
         sim.set_sources([(0, r, c, 0) for r, c in cells], amp[None, :])
         sim.set_probes(probes, nsteps)
-        sim.step(nsteps, 8)
+        sim.step(nsteps, k)
         gEz, gHx, gHy = sim.state()
         gtrace = sim.read_probes()
     assert_bits(gtrace, otrace, "probe trace")
@@ -414,18 +418,20 @@ def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, uniform_mu, monke
 
 
 def test_wavefront_equals_tile_kernel_large(fd, monkeypatch):
-    """6000 x 5000 fp32, 40 steps near the Ricker peak: the wavefront strips (default at this size) and the persistent
-    TMA tile kernel (FDTD2D_WAVE_MIN_TILES huge) must agree bit for bit, also for a 3-grid batch."""
+    """6000 x 5000 fp32, 40 steps near the Ricker peak: the wavefront strips (packed and scalar, 8 and 12 levels, and
+    whatever k = 0 picks) and the persistent TMA tile kernel (FDTD2D_WAVE_MIN_TILES huge) must agree bit for bit."""
     outs = []
-    for min_tiles in ("0", "100000000"):
+    for min_tiles, x2, k in (("100000000", "1", 8), ("0", "1", 8), ("0", "0", 8), ("0", "1", 12), ("0", "0", 12), ("0", "1", 0)):
         monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", min_tiles)
+        monkeypatch.setenv("FDTD2D_WAVE_X2", x2)
         with fd.Simulation(6000, 5000, np.float32, dt=DT, dx=DX) as sim:
             sim.set_materials_random(seed=5, span=9.0)
             sim.set_point_source(3000, 2500, 700, FC)
             sim.set_probes([(3000, 2510), (10, 10), (5990, 4990)], 700)
             sim.step_index = 640
-            sim.step(40, 8)
+            sim.step(40, k)
             outs.append(sim.state() + (sim.read_probes(640, 40),))
     assert np.abs(outs[0][0]).max() > 0.1
-    for a, b in zip(*outs):
-        assert_bits(a, b, "wavefront vs tile kernel")
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert_bits(a, b, "wavefront vs tile kernel")
