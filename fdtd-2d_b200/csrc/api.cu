@@ -473,6 +473,10 @@ static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask
         if (!uch) return fail(FDTD2D_EINVAL, "the 12-level wavefront kernel needs uniform permeability");
         return x2 ? launch_wave_t<12, true, 2, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<12, true, 2, false>(s, p, tasks, n_tasks, ticket, grid);
     }
+    if (k == 10) {
+        if (!uch) return fail(FDTD2D_EINVAL, "the 10-level wavefront kernel needs uniform permeability");
+        return launch_wave_t<10, true, WAVE_P, true>(s, p, tasks, n_tasks, ticket, grid);
+    }
     if (uch) return x2 ? launch_wave_t<8, true, WAVE_P, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<8, true, WAVE_P, false>(s, p, tasks, n_tasks, ticket, grid);
     return x2 ? launch_wave_t<8, false, WAVE_P, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<8, false, WAVE_P, false>(s, p, tasks, n_tasks, ticket, grid);
 }
@@ -637,40 +641,68 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
             }
         }
     // the wavefront kernel exists for k = 8 and, with uniform permeability, for k = 12
-    bool wave_k = kFastCfgs[s->fast_cfg].wave && (k == 8 || k == 12);
-    if (wave_k && k == 12) {
+    bool wave_k = kFastCfgs[s->fast_cfg].wave && (k == 8 || k == 10 || k == 12);
+    if (wave_k && k > 8) {
         if (int rc = check_ch_uniform(s)) return rc;
         wave_k = s->ch_uniform == 1;
     }
     if (wave_k) {
-        // vertical runs of plain tiles of one tile column -> wavefront tasks of at most WAVE_SEG tiles: long enough
-        // to amortise the 2k warm-up rows, short enough that every warp of the GPU gets several
+        // Vertical stretches of plain tiles of one tile column are cut into RUNS of rows, one wavefront task each.  A run
+        // costs 2k warm-up rows, and the GPU has W = SMs x 8 independent warps: the cut is chosen so that there are (at
+        // most) m x W runs of nearly the same length -- every warp gets m of them -- with m as small as a cap of
+        // ~WAVE_RUN_ROWS rows per run allows.  (With runs of whole tiles a 4096^2 grid gave 720 runs to 1184 warps.)
         if (!s->sm_count) CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
         const long long n_plain = (long long)fast.size() + (long long)fast_rest.size();
-        const int WAVE_SEG = (int)std::max<long long>(4, std::min<long long>(16, n_plain / (6LL * s->sm_count * WAVE_NW)));
         std::vector<unsigned char> is_plain((size_t)n_tiles, 0), is_band((size_t)n_tiles, 0);
         for (int id : fast) is_plain[id] = 1, is_band[id] = 1;
         for (int id : fast_rest) is_plain[id] = 1;
+        long long run_rows = 640;
+        if (const char* e = getenv("FDTD2D_WAVE_RUN_ROWS")) run_rows = std::max(1, atoi(e));
         std::vector<WaveTask> tasks;
         for (int pass = 0; pass < 2; ++pass) {  // pass 0: plain tiles outside the band; pass 1: all plain tiles
+            std::vector<WaveTask> segs;  // maximal stretches, in rows
+            long long total_rows = 0;
+            int longest = 1;
             for (int b = 0; b < s->batch; ++b)
                 for (int tx = 0; tx < tp.tiles_x; ++tx) {
                     int run = 0;
                     for (int ty = 0; ty <= tp.tiles_y; ++ty) {
                         const int id = b * per_grid + ty * tp.tiles_x + tx;
                         const bool ok = ty < tp.tiles_y && is_plain[id] && (pass == 1 || !is_band[id]);
-                        if (ok && run < WAVE_SEG) {
+                        if (ok) {
                             ++run;
                             continue;
                         }
                         if (run) {
                             WaveTask t;
                             t.b = b, t.x0 = tx * tp.CW - tp.hx, t.y0 = (ty - run) * tp.CH, t.y1 = ty * tp.CH;
-                            tasks.push_back(t);
+                            segs.push_back(t);
+                            total_rows += t.y1 - t.y0;
+                            longest = std::max(longest, t.y1 - t.y0);
                         }
-                        run = ok ? 1 : 0;
+                        run = 0;
                     }
                 }
+            const long long W = (long long)s->sm_count * WAVE_NW;
+            const long long m = std::max<long long>(1, (total_rows + W * run_rows - 1) / (W * run_rows));
+            auto count_runs = [&](int len) {
+                long long c = 0;
+                for (const WaveTask& g : segs) c += (g.y1 - g.y0 + len - 1) / len;
+                return c;
+            };
+            int lo = std::min(longest, 4 * k), hi = longest;  // shortest run length that gives at most m x W runs
+            while (lo < hi) {
+                const int mid = (lo + hi) / 2;
+                if (count_runs(mid) <= m * W) hi = mid; else lo = mid + 1;
+            }
+            for (const WaveTask& g : segs) {
+                const int rows = g.y1 - g.y0, parts = (rows + lo - 1) / lo;
+                for (int q = 0; q < parts; ++q) {
+                    WaveTask t = g;
+                    t.y0 = g.y0 + (int)((long long)rows * q / parts), t.y1 = g.y0 + (int)((long long)rows * (q + 1) / parts);
+                    tasks.push_back(t);
+                }
+            }
             // hand the runs out row band by row band: warps that work at the same time then hold neighbouring strips of
             // the same rows, so the 8 halo columns they share are read from DRAM once and from L2 the second time
             std::stable_sort(tasks.begin() + (pass == 0 ? 0 : pl->n_wave_rest), tasks.end(), [](const WaveTask& a, const WaveTask& b) {

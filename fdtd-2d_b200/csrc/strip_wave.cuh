@@ -197,10 +197,13 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const Pa
         t = __shfl_sync(FULL, t, 0);
         if (t >= n_tasks) break;
         const WaveTask tk = tasks[t];
-        const long long base = (long long)tk.b * p.grid_stride + tk.x0 + 4 * l;
-        const int i0 = tk.y0 - K, i1 = tk.y1 + K;  // level-0 rows [i0, i1)
-        auto fetch = [&](int row, int fs, int cs) {
-            const long long o = base + (long long)row * p.pitch;
+        // Loop state is kept small (the window takes 13 x 12 registers at K = 12): j counts the level-0 rows of the run,
+        // `of` is the element offset of the next row to fetch and moves one row per iteration; the row that leaves
+        // level K-1 in iteration j is K rows behind the arriving one, i.e. P + 1 + K rows behind `of`.
+        const int n = tk.y1 - tk.y0 + 2 * K;  // level-0 rows [y0 - K, y1 + K)
+        long long of = (long long)tk.b * p.grid_stride + tk.x0 + 4 * l + (long long)(tk.y0 - K) * p.pitch;
+        auto fetch = [&](int fs, int cs) {
+            const long long o = of;
             cp_async16(fring + (fs * 3 + 0) * TW, p.in[0] + o);
             cp_async16(fring + (fs * 3 + 1) * TW, p.in[1] + o);
             cp_async16(fring + (fs * 3 + 2) * TW, p.in[2] + o);
@@ -221,14 +224,16 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const Pa
         }
 #pragma unroll
         for (int d = 0; d < P; ++d) {
-            fetch(i0 + d, fs, cs);
+            fetch(fs, cs);
+            of += p.pitch;
             cp_async_commit();
             fs = (fs + 1) & (NF - 1);
             cs = (cs + 1) & (NC - 1);
         }
         int fr = 0, cr = 0;
-        auto iter = [&](u64 (&ST)[K + 1][3][2], u64 (&AR)[K + 1][3][2], const int i) {
-            if (i + P < i1) fetch(i + P, fs, cs);
+        auto iter = [&](u64 (&ST)[K + 1][3][2], u64 (&AR)[K + 1][3][2], const int j) {
+            if (j + P < n) fetch(fs, cs);
+            of += p.pitch;
             cp_async_commit();
             fs = (fs + 1) & (NF - 1);
             cs = (cs + 1) & (NC - 1);
@@ -268,21 +273,20 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const Pa
                 AR[s + 1][0][1] = add2(e1, mul2(curl1, ce[1], negzero));
             }
             cr = (cr + 1) & (NC - 1);
-            const int r = i - K;
-            if (core && r >= tk.y0 && r < tk.y1) {
-                const long long o = base + (long long)r * p.pitch;
+            if (core && j >= 2 * K) {  // row y0 + (j - 2K) < y1 has left level K-1, K steps on
+                const long long o = of - (long long)(P + 1 + K) * p.pitch;
                 store22(p.out[0] + o, AR[K][0]);
                 store22(p.out[1] + o, AR[K][1]);
                 store22(p.out[2] + o, AR[K][2]);
             }
         };
-        int i = i0;
+        int j = 0;
 #pragma unroll 1
-        for (; i + 1 < i1; i += 2) {
-            iter(X, Y, i);
-            iter(Y, X, i + 1);
+        for (; j + 1 < n; j += 2) {
+            iter(X, Y, j);
+            iter(Y, X, j + 1);
         }
-        if (i < i1) iter(X, Y, i);
+        if (j < n) iter(X, Y, j);
         cp_async_wait<0>();
         __syncwarp();
     }
