@@ -712,10 +712,10 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
             });
             (pass == 0 ? pl->n_wave_rest : pl->n_wave_all) = (int)tasks.size() - (pass == 0 ? 0 : pl->n_wave_rest);
         }
-        // small grids do not have enough runs to balance ~1200 independent warps: they stay on the tile kernel
-        // measured on B200 (profiles/): from ~2 plain tiles per warp of the GPU (4096^2) the wavefront wins, below the
-        // persistent tile kernel does (3000^2: 592 vs 496 Gcell/s)
-        long long min_tiles = 2LL * s->sm_count * WAVE_NW;
+        // small grids: one run per warp gets too short against its 2k warm-up rows, and the persistent tile kernel wins.
+        // Measured on B200 with balanced runs (profiles/): 3000^2 696 vs 593, 2048^2 548 vs 491, 1536^2 364 vs 390 Gcell/s
+        // (wavefront vs tiles) -> the wavefront takes over from ~0.4 plain tiles per warp of the GPU
+        long long min_tiles = 2LL * s->sm_count * WAVE_NW / 5;
         if (const char* e = getenv("FDTD2D_WAVE_MIN_TILES")) min_tiles = std::max(0, atoi(e));
         if (n_plain < min_tiles) tasks.clear(), pl->n_wave_rest = pl->n_wave_all = 0;
         if (!tasks.empty()) {

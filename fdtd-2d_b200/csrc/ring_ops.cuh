@@ -19,7 +19,8 @@ template <typename T> struct TileCtx {
     int src_lo, src_hi, prb_lo, prb_hi;   // this grid's ranges in the sorted source / probe lists
 };
 
-template <typename T, int TH, int TW, int NT>
+// S2_DONE: the caller has already applied S2 to nxt (tile_edge_kernel does it in registers).
+template <typename T, int TH, int TW, int NT, bool S2_DONE = false>
 __device__ __forceinline__ void ring_stages(const T* cur, T* nxt, const TileCtx<T>& tc, const int tid) {
     const int gr0 = tc.gr0, lc0 = tc.lc0, Rg = tc.Rg, C = tc.C;
     const T coef = tc.coef;
@@ -27,7 +28,7 @@ __device__ __forceinline__ void ring_stages(const T* cur, T* nxt, const TileCtx<
                 // ---- S2: Mur left/right, main.py:33-41. One thread per (row, side) runs the
                 // reference's five column updates in the reference's order (outermost first), so every
                 // read of the inward neighbour sees the value S1 left there. -----------------------
-                if (touchL || touchR) {
+                if (!S2_DONE && (touchL || touchR)) {
                     for (int w = tid; w < 2 * TH; w += NT) {
                         const int side = w / TH, li = w - side * TH;
                         const int gi = gr0 + li;

@@ -109,7 +109,28 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
         const Cell c = p.probes[q];
         mine |= (c.row >= gr0 && c.row < gr0 + TH && c.col >= lc0 && c.col < lc0 + TW);
     }
-    const bool staged = __syncthreads_or(mine) || tc.touchL || tc.touchR || tc.touchT || tc.touchB;
+    // Sources / probes anywhere in the tile: every step parks the whole field in shared memory.  Top / bottom ring:
+    // only the warps that hold ring rows (global rows 0..5, Rg-6..Rg-1) park theirs.  Left / right ring: nothing is
+    // parked, S2 runs in registers below.
+    const bool full = __syncthreads_or(mine);
+    const bool staged = full || tc.touchT || tc.touchB;
+    const int gw0 = gr0 + li0, gw1 = gw0 + MR - 1;  // global rows of this warp
+    const bool park = full || (staged && ((gw0 <= RING && gw1 >= 0) || (gw1 >= Rg - 1 - RING && gw0 <= Rg - 1)));
+    const bool lr = tc.touchL || tc.touchR;
+    // Mur left / right (main.py:33-41) on registers: in the reference's order every column reads its inward neighbour
+    // before that one is overwritten, so for rows 1..Rg-2
+    //   Ez[i, q]     = S0[i, q+1]   + coef * (S1[i, q+1]   - S0[i, q])      q = 0..4
+    //   Ez[i, C-1-q] = S0[i, C-2-q] + coef * (S1[i, C-2-q] - S0[i, C-1-q])
+    // with S0 the field before the step and S1 the field after the interior update: both are in this thread or one
+    // lane away.  (Left and right do not interact for C >= 11, the smallest grid the library accepts.)
+    bool lcol[4], rcol[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int gj = lc0 + lj + q;
+        lcol[q] = gj >= 0 && gj < RING;
+        rcol[q] = gj >= C - RING && gj <= C - 1;
+    }
+    const T coef = tc.coef;
 
     const int wb = (w + 1 < NW ? w + 1 : NW - 1) * TW + lj;
     const int wa = (w > 0 ? w - 1 : 0) * TW + lj;
@@ -134,9 +155,9 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
                 hy[r][q] = ok ? ny : hy[r][q];
             }
         }
-        // ---- interior Ez update (S1) ----------------------------------------------------------
+        // ---- interior Ez update (S1), Mur left/right (S2) -------------------------------------------
         store4(sHx + w * TW + lj, hx[MR - 1]);
-        if (staged) {
+        if (park) {
 #pragma unroll
             for (int r = 0; r < MR; ++r) store4(s0 + (li0 + r) * TW + lj, e[r]);
         }
@@ -146,24 +167,47 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
 #pragma unroll
         for (int r = 0; r < MR; ++r) {
             const T left0 = __shfl_up_sync(0xffffffffu, hy[r][3], 1);
+            T nv[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const T up = (r > 0) ? hx[r > 0 ? r - 1 : 0][q] : above[q];
                 const T left = (q > 0) ? hy[r][q > 0 ? q - 1 : 0] : left0;
                 const T curl = sub_rn(sub_rn(hy[r][q], left), sub_rn(hx[r][q], up));
-                const T nv = add_rn(e[r][q], mul_rn(curl, ce[r][q]));
-                e[r][q] = (erow[r] && ecol[q]) ? nv : e[r][q];
+                const T v = add_rn(e[r][q], mul_rn(curl, ce[r][q]));
+                nv[q] = (erow[r] && ecol[q]) ? v : e[r][q];
+            }
+            if (lr) {
+                const T s0r = __shfl_down_sync(0xffffffffu, e[r][0], 1), s1r = __shfl_down_sync(0xffffffffu, nv[0], 1);
+                const T s0l = __shfl_up_sync(0xffffffffu, e[r][3], 1), s1l = __shfl_up_sync(0xffffffffu, nv[3], 1);
+                T out[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const T a0 = (q < 3) ? e[r][q < 3 ? q + 1 : 3] : s0r, a1 = (q < 3) ? nv[q < 3 ? q + 1 : 3] : s1r;
+                    const T b0 = (q > 0) ? e[r][q > 0 ? q - 1 : 0] : s0l, b1 = (q > 0) ? nv[q > 0 ? q - 1 : 0] : s1l;
+                    const T ml = add_rn(a0, mul_rn(coef, sub_rn(a1, e[r][q])));
+                    const T mr = add_rn(b0, mul_rn(coef, sub_rn(b1, e[r][q])));
+                    out[q] = (erow[r] && lcol[q]) ? ml : ((erow[r] && rcol[q]) ? mr : nv[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) e[r][q] = out[q];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) e[r][q] = nv[q];
             }
         }
-        // ---- boundary stages through shared memory (S2, S3, S4, source, probes) -------------------
+        // ---- the other boundary stages through shared memory (S3, S4, source, probes) ----------------
         if (staged) {
+            if (park) {
 #pragma unroll
-            for (int r = 0; r < MR; ++r) store4(s1 + (li0 + r) * TW + lj, e[r]);
+                for (int r = 0; r < MR; ++r) store4(s1 + (li0 + r) * TW + lj, e[r]);
+            }
             __syncthreads();
-            ring_stages<T, TH, TW, NT>(s0, s1, tc, tid);
-            source_and_probes<T, TH, TW, NT>(s1, p, tc, p.step0 + s, tid);
+            ring_stages<T, TH, TW, NT, true>(s0, s1, tc, tid);
+            if (full) source_and_probes<T, TH, TW, NT>(s1, p, tc, p.step0 + s, tid);
+            if (park) {
 #pragma unroll
-            for (int r = 0; r < MR; ++r) load4(s1 + (li0 + r) * TW + lj, e[r]);
+                for (int r = 0; r < MR; ++r) load4(s1 + (li0 + r) * TW + lj, e[r]);
+            }
         }
     }
 
