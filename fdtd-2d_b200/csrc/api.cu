@@ -86,6 +86,7 @@ struct PassPlan {
     // cover every plain tile
     int n_wave_rest = 0, n_wave_all = 0;
     WaveTask* d_wave = nullptr;
+    bool wave_ring = false;   // both task lists start with the runs of the strips that hold the left / right Mur ring
     int* d_ticket = nullptr;  // next run to hand out (reset before every launch)
 };
 
@@ -438,15 +439,15 @@ static int check_ch_uniform(fdtd2d_sim* s) {
 
 // One instantiation of the wavefront kernel: K levels, scalar or uniform dt/(mu*dx), P rows of prefetch, X2 = packed
 // two-wide fp32 instructions (strip_wave_x2_kernel).
-template <int K, bool UCH, int P, bool X2>
+template <int K, bool UCH, int P, bool X2, bool RING = false>
 static int launch_wave_t(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, int grid) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[s->device % MAX_DEVICES];
-    const size_t smem = wave_smem_bytes();
+    const size_t smem = wave_smem_bytes(WAVE_NW, X2 && UCH);
     const float chv = UCH ? s->ch_value : 0.0f;
     if (X2) {
-        if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_x2_kernel<K, UCH, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        strip_wave_x2_kernel<K, UCH, P><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, chv, 0x8000000080000000ull);
+        if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_x2_kernel<K, UCH, P, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        strip_wave_x2_kernel<K, UCH, P, RING><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, chv, 0x8000000080000000ull);
     } else {
         if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_kernel<K, UCH, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         strip_wave_kernel<K, UCH, P><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, chv);
@@ -462,7 +463,7 @@ static bool wave_x2() {
     return e ? atoi(e) != 0 : true;
 }
 
-static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k) {
+static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k, bool ring) {
     if (int rc = check_ch_uniform(s)) return rc;
     if (!s->sm_count) CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
     const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, s->sm_count);
@@ -477,6 +478,8 @@ static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask
         if (!uch) return fail(FDTD2D_EINVAL, "the 10-level wavefront kernel needs uniform permeability");
         return launch_wave_t<10, true, WAVE_P, true>(s, p, tasks, n_tasks, ticket, grid);
     }
+    if (ring)  // the task list starts with ring-strip runs (built only for k = 8 with the packed kernel)
+        return uch ? launch_wave_t<8, true, WAVE_P, true, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<8, false, WAVE_P, true, true>(s, p, tasks, n_tasks, ticket, grid);
     if (uch) return x2 ? launch_wave_t<8, true, WAVE_P, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<8, true, WAVE_P, false>(s, p, tasks, n_tasks, ticket, grid);
     return x2 ? launch_wave_t<8, false, WAVE_P, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<8, false, WAVE_P, false>(s, p, tasks, n_tasks, ticket, grid);
 }
@@ -487,6 +490,7 @@ template <typename T, int MR, int NW> static int launch_edge_tt(int dev, const P
     const size_t smem = (size_t)(2 * MR * NW * FAST_TW + 2 * NW * FAST_TW) * sizeof(T);
     if (!done) {
         CUDA_TRY(cudaFuncSetAttribute(tile_edge_kernel<T, MR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(tile_edge_kernel<T, MR, NW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         done = true;
     }
     tile_edge_kernel<T, MR, NW><<<(unsigned)n_tiles, NW * 32, smem, st>>>(p);
@@ -626,7 +630,26 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
         if (s->has_bot_nb && r1 > own_last - s->halo) return true;
         return false;
     };
-    std::vector<int> gen, fast, gen_rest, fast_rest;
+    // Ring strips: tiles of the first / last tile column whose ROWS are plain go to the ring instantiation of the
+    // wavefront kernel (8 levels, packed) when the plain tiles do; the band tiles of a slab stay on the tile kernels.
+    // The right strip is the last 128 columns of the padded row, so a source / probe must be re-checked against it.
+    const bool lr_ok = kFastCfgs[s->fast_cfg].wave && k == 8 && wave_x2() && s->C >= 4 * FAST_TW && !getenv("FDTD2D_NO_RING_STRIPS");
+    const int lr_x0[2] = {0, (s->C + 3) / 4 * 4 - FAST_TW};
+    std::vector<unsigned char> lr_special((size_t)n_tiles, 0);
+    if (lr_ok) {
+        auto mark_lr = [&](const Cell& c, int row_pad_lo, int row_pad_hi) {
+            for (int side = 0; side < 2; ++side) {
+                if (c.col < lr_x0[side] || c.col >= lr_x0[side] + FAST_TW) continue;
+                const int tx = side ? tp.tiles_x - 1 : 0, lrow = c.row - s->row0;
+                for (int ty = 0; ty < tp.tiles_y; ++ty)
+                    if (lrow >= ty * tp.CH - row_pad_lo && lrow < ty * tp.CH + tp.CH + row_pad_hi)
+                        lr_special[(size_t)c.grid * per_grid + (size_t)ty * tp.tiles_x + tx] = 1;
+            }
+        };
+        for (const Cell& c : s->h_src) mark_lr(c, k, k);
+        for (const Cell& c : s->h_probe) mark_lr(c, 0, 0);
+    }
+    std::vector<int> gen, fast, gen_rest, fast_rest, lr_tiles;
     for (int b = 0; b < s->batch; ++b)
         for (int ty = 0; ty < tp.tiles_y; ++ty) {
             const int lr0 = ty * tp.CH - k, gr0 = lr0 + s->row0;
@@ -637,7 +660,10 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
                 const bool cols_plain = lc0 >= RING && lc0 + FAST_TW <= s->C - RING;
                 const int id = b * per_grid + ty * tp.tiles_x + tx;
                 const bool plain = rows_plain && cols_plain && !special[id];
-                (plain ? (band ? fast : fast_rest) : (band ? gen : gen_rest)).push_back(id);
+                if (lr_ok && !plain && !band && rows_plain && !special[id] && !lr_special[id] && (tx == 0 || tx == tp.tiles_x - 1))
+                    lr_tiles.push_back(id);  // decided below: ring strip or edge tile
+                else
+                    (plain ? (band ? fast : fast_rest) : (band ? gen : gen_rest)).push_back(id);
             }
         }
     // the wavefront kernel exists for k = 8 and, with uniform permeability, for k = 12
@@ -658,11 +684,51 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
         for (int id : fast_rest) is_plain[id] = 1;
         long long run_rows = 640;
         if (const char* e = getenv("FDTD2D_WAVE_RUN_ROWS")) run_rows = std::max(1, atoi(e));
+        // small grids: one run per warp gets too short against its 2k warm-up rows, and the persistent tile kernel wins.
+        // Measured on B200 with balanced runs (profiles/): 3000^2 696 vs 593, 2048^2 548 vs 491, 1536^2 364 vs 390 Gcell/s
+        // (wavefront vs tiles) -> the wavefront takes over from ~0.4 plain tiles per warp of the GPU
+        long long min_tiles = 2LL * s->sm_count * WAVE_NW / 5;
+        if (const char* e = getenv("FDTD2D_WAVE_MIN_TILES")) min_tiles = std::max(0, atoi(e));
+        const bool use_wave = n_plain >= min_tiles && n_plain > 0;
+        // stretches of ring-strip tiles (first / last tile column): a row of them costs about twice a plain row, so they
+        // are cut to half the run length, counted in the same budget of runs and handed out first
+        std::vector<WaveTask> lr_segs;
+        if (use_wave && !lr_tiles.empty()) {
+            std::vector<unsigned char> is_lr((size_t)n_tiles, 0);
+            for (int id : lr_tiles) is_lr[id] = 1;
+            for (int b = 0; b < s->batch; ++b)
+                for (int side = 0; side < 2; ++side) {
+                    const int tx = side ? tp.tiles_x - 1 : 0;
+                    if (side && tp.tiles_x == 1) continue;
+                    int run = 0;
+                    for (int ty = 0; ty <= tp.tiles_y; ++ty) {
+                        const bool ok = ty < tp.tiles_y && is_lr[b * per_grid + ty * tp.tiles_x + tx];
+                        if (ok) {
+                            ++run;
+                            continue;
+                        }
+                        if (run) {
+                            WaveTask t;
+                            t.b = b, t.x0 = lr_x0[side], t.side = side + 1, t.pad = 0;
+                            t.y0 = (ty - run) * tp.CH, t.y1 = ty * tp.CH;
+                            // stored columns: the tile's core, in strip coordinates (whole 16-byte groups; the last group
+                            // may reach into the pad columns, which keep their zeros)
+                            t.c0 = side ? tx * tp.CW - t.x0 : 0;
+                            t.c1 = side ? FAST_TW : tp.CW;
+                            lr_segs.push_back(t);
+                        }
+                        run = 0;
+                    }
+                }
+            lr_tiles.clear();
+            pl->wave_ring = true;
+        }
         std::vector<WaveTask> tasks;
-        for (int pass = 0; pass < 2; ++pass) {  // pass 0: plain tiles outside the band; pass 1: all plain tiles
-            std::vector<WaveTask> segs;  // maximal stretches, in rows
+        for (int pass = 0; use_wave && pass < 2; ++pass) {  // pass 0: plain tiles outside the band; pass 1: all plain tiles
+            std::vector<WaveTask> segs = lr_segs;  // maximal stretches, in rows
             long long total_rows = 0;
             int longest = 1;
+            for (const WaveTask& g : lr_segs) total_rows += 2 * (g.y1 - g.y0), longest = std::max(longest, g.y1 - g.y0);
             for (int b = 0; b < s->batch; ++b)
                 for (int tx = 0; tx < tp.tiles_x; ++tx) {
                     int run = 0;
@@ -676,6 +742,7 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
                         if (run) {
                             WaveTask t;
                             t.b = b, t.x0 = tx * tp.CW - tp.hx, t.y0 = (ty - run) * tp.CH, t.y1 = ty * tp.CH;
+                            t.c0 = tp.hx, t.c1 = tp.hx + tp.CW, t.side = 0, t.pad = 0;
                             segs.push_back(t);
                             total_rows += t.y1 - t.y0;
                             longest = std::max(longest, t.y1 - t.y0);
@@ -685,45 +752,43 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
                 }
             const long long W = (long long)s->sm_count * WAVE_NW;
             const long long m = std::max<long long>(1, (total_rows + W * run_rows - 1) / (W * run_rows));
+            auto run_len = [&](const WaveTask& g, int len) { return g.side ? std::max(4 * k, len / 2) : len; };
             auto count_runs = [&](int len) {
                 long long c = 0;
-                for (const WaveTask& g : segs) c += (g.y1 - g.y0 + len - 1) / len;
+                for (const WaveTask& g : segs) c += (g.y1 - g.y0 + run_len(g, len) - 1) / run_len(g, len);
                 return c;
             };
-            int lo = std::min(longest, 4 * k), hi = longest;  // shortest run length that gives at most m x W runs
+            int lo = std::min(longest, 4 * k), hi = std::max(longest, 8 * k);  // shortest run length that gives at most m x W runs
             while (lo < hi) {
                 const int mid = (lo + hi) / 2;
                 if (count_runs(mid) <= m * W) hi = mid; else lo = mid + 1;
             }
             for (const WaveTask& g : segs) {
-                const int rows = g.y1 - g.y0, parts = (rows + lo - 1) / lo;
+                const int rows = g.y1 - g.y0, len = run_len(g, lo), parts = (rows + len - 1) / len;
                 for (int q = 0; q < parts; ++q) {
                     WaveTask t = g;
                     t.y0 = g.y0 + (int)((long long)rows * q / parts), t.y1 = g.y0 + (int)((long long)rows * (q + 1) / parts);
                     tasks.push_back(t);
                 }
             }
-            // hand the runs out row band by row band: warps that work at the same time then hold neighbouring strips of
-            // the same rows, so the 8 halo columns they share are read from DRAM once and from L2 the second time
+            // ring-strip runs first; then row band by row band: warps that work at the same time then hold neighbouring
+            // strips of the same rows, so the 8 halo columns they share are read from DRAM once and from L2 the second time
             std::stable_sort(tasks.begin() + (pass == 0 ? 0 : pl->n_wave_rest), tasks.end(), [](const WaveTask& a, const WaveTask& b) {
+                if ((a.side != 0) != (b.side != 0)) return a.side != 0;
                 if (a.b != b.b) return a.b < b.b;
                 if (a.y0 != b.y0) return a.y0 < b.y0;
                 return a.x0 < b.x0;
             });
             (pass == 0 ? pl->n_wave_rest : pl->n_wave_all) = (int)tasks.size() - (pass == 0 ? 0 : pl->n_wave_rest);
         }
-        // small grids: one run per warp gets too short against its 2k warm-up rows, and the persistent tile kernel wins.
-        // Measured on B200 with balanced runs (profiles/): 3000^2 696 vs 593, 2048^2 548 vs 491, 1536^2 364 vs 390 Gcell/s
-        // (wavefront vs tiles) -> the wavefront takes over from ~0.4 plain tiles per warp of the GPU
-        long long min_tiles = 2LL * s->sm_count * WAVE_NW / 5;
-        if (const char* e = getenv("FDTD2D_WAVE_MIN_TILES")) min_tiles = std::max(0, atoi(e));
-        if (n_plain < min_tiles) tasks.clear(), pl->n_wave_rest = pl->n_wave_all = 0;
         if (!tasks.empty()) {
             CUDA_TRY(cudaMalloc(&pl->d_ticket, sizeof(int)));
             CUDA_TRY(cudaMalloc(&pl->d_wave, sizeof(WaveTask) * tasks.size()));
             CUDA_TRY(cudaMemcpy(pl->d_wave, tasks.data(), sizeof(WaveTask) * tasks.size(), cudaMemcpyHostToDevice));
         }
     }
+    gen_rest.insert(gen_rest.end(), lr_tiles.begin(), lr_tiles.end());  // no ring strips: they are ordinary edge tiles
+    std::sort(gen_rest.begin(), gen_rest.end());
     pl->n_generic_band = (int)gen.size();
     pl->n_fast_band = (int)fast.size();
     gen.insert(gen.end(), gen_rest.begin(), gen_rest.end());
@@ -798,7 +863,7 @@ static int launch_hybrid(fdtd2d_sim* s, int k, int part) {
         const int n_tasks = part == 2 ? pl.n_wave_rest : pl.n_wave_all;
         p.tile_list = nullptr;
         if (n_tasks)
-            if (int rc = launch_wave(s, p, tasks, n_tasks, pl.d_ticket, k)) return rc;
+            if (int rc = launch_wave(s, p, tasks, n_tasks, pl.d_ticket, k, pl.wave_ring)) return rc;
         s->launches += n_tasks ? 1 : 0;
     } else if (n_fst) {
         p.tile_list = pl.d_fast + f_off;

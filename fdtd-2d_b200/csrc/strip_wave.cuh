@@ -29,13 +29,17 @@ constexpr int WAVE_NF = 4;      // rows of the field ring (a power of two > P)
 constexpr int WAVE_NC = 16;     // rows of the coefficient ring (a power of two >= K + P + 2)
 constexpr int WAVE_TW = 128;    // strip width (columns per warp)
 
-// one run of rows of one strip: grid b, haloed strip starts at column x0, rows [y0, y1) are stored
+// one run of rows of one strip: grid b, haloed strip starts at column x0, rows [y0, y1) are stored.
+// Ring strips (side != 0, strip_wave_x2_kernel<.., LR = true>) also say which of their 128 columns they store: [c0, c1).
 struct WaveTask {
     int32_t b, x0, y0, y1;
+    int32_t c0, c1, side, pad;  // side: 0 plain strip, 1 holds the left Mur ring (columns 0..4), 2 the right one
 };
 
-__host__ __device__ constexpr size_t wave_smem_bytes() {
-    return (size_t)WAVE_NW * (WAVE_NF * 3 + WAVE_NC * 2) * WAVE_TW * sizeof(float);
+// per warp: NF rows of the three fields + NC rows of dt/(eps*dx) (+ NC rows of dt/(mu*dx) unless that is a scalar:
+// the packed kernel then leaves the second ring out, which is what lets a ring-strip CTA fit beside a plain-strip CTA)
+__host__ __device__ constexpr size_t wave_smem_bytes(int warps = WAVE_NW, bool no_ch_ring = false) {
+    return (size_t)warps * (WAVE_NF * 3 + WAVE_NC * (no_ch_ring ? 1 : 2)) * WAVE_TW * sizeof(float);
 }
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
@@ -179,24 +183,45 @@ __device__ __forceinline__ float hi2(u64 a) { return __uint_as_float((uint32_t)(
 __device__ __forceinline__ void load22(const float* p, u64* a) { const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p); a[0] = v.x, a[1] = v.y; }
 __device__ __forceinline__ void store22(float* p, const u64* a) { *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a[0], a[1]); }
 
-template <int K, bool UCH, int P>
-__global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const PassParams<float> p, const WaveTask* tasks, const int n_tasks, int* ticket, const float ch_uniform, const u64 negzero) {
-    constexpr int TW = WAVE_TW, NF = WAVE_NF, NC = WAVE_NC;
-    static_assert((NF & (NF - 1)) == 0 && NF > P && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
+// One run of rows of one strip, K levels deep (the body of strip_wave_x2_kernel).
+// LR = true: the strip holds the left or right Mur ring (main.py:33-41) over rows that are plain (no top / bottom ring,
+// no source, no probe in reach).  The ring rides along the wavefront: at every level the five ring columns are set from
+// the row's own values before (S0) and after (S1) the interior update,
+//   Ez[i, q] = S0[i, q+1] + coef * (S1[i, q+1] - S0[i, q])   (left; mirrored on the right),
+// which is the reference's column-by-column loop with every read resolved (each column reads its inward neighbour
+// before that one is overwritten).  The reference's slice bounds (H: columns 0..C-2, Ez: 1..C-2) are imposed by selects
+// on the right strip, which also covers the pad columns >= C (kept as loaded: zero).
+template <int K, bool UCH, int P, bool LR>
+__device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const WaveTask& tk, float* fring, float* cring, const int l, const u64 chu, const u64 negzero) {
+    constexpr int TW = WAVE_TW, NF = WAVE_NF, NC = WAVE_NC, CS = UCH ? 1 : 2;
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ __align__(16) unsigned char smem_wave[];
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    float* fring = reinterpret_cast<float*>(smem_wave) + (size_t)w * (NF * 3 + NC * 2) * TW + 4 * l;  // [NF][3][TW], my 4 columns
-    float* cring = fring + NF * 3 * TW;                                                              // [NC][2][TW]
-    const bool core = 4 * l >= p.hx && 4 * l < p.hx + p.CW;
-    const u64 chu = pack2(ch_uniform, ch_uniform);
-
-    for (;;) {
-        int t = 0;
-        if (l == 0) t = atomicAdd(ticket, 1);
-        t = __shfl_sync(FULL, t, 0);
-        if (t >= n_tasks) break;
-        const WaveTask tk = tasks[t];
+    bool core = 4 * l >= p.hx && 4 * l < p.hx + p.CW;
+    {
+        // ring strips: which of my four columns are ring columns / beyond the reference's slices, as all-ones masks for
+        // bitwise selects (one LOP3 each; predicates would have to be recomputed at every use)
+        uint32_t ringm[4] = {0, 0, 0, 0}, hoffm[4] = {0, 0, 0, 0}, padm[4] = {0, 0, 0, 0};
+        float coef = 0.0f;
+        if (LR) {
+            core = 4 * l >= tk.c0 && 4 * l < tk.c1;
+            coef = p.mur[tk.b];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int gj = tk.x0 + 4 * l + q;
+                // (sign bits smeared by an arithmetic shift: written as a comparison the compiler turns the masks
+                // back into predicates)
+                auto lt = [](int a, int b) {  // a < b ? ~0 : 0
+                    uint32_t m;
+                    asm("shr.s32 %0, %1, 31;" : "=r"(m) : "r"(a - b));
+                    return m;
+                };
+                ringm[q] = tk.side == 1 ? lt(gj, RING) : (lt(p.C - RING - 1, gj) & lt(gj, p.C));
+                hoffm[q] = lt(p.C - 2, gj);  // H is updated in columns 0..C-2 (main.py:70,74)
+                padm[q] = lt(p.C - 1, gj);
+            }
+        }
+        auto bsel = [](uint32_t m, float a, float b) {  // m ? a : b
+            return __uint_as_float((__float_as_uint(a) & m) | (__float_as_uint(b) & ~m));
+        };
         // Loop state is kept small (the window takes 13 x 12 registers at K = 12): j counts the level-0 rows of the run,
         // `of` is the element offset of the next row to fetch and moves one row per iteration; the row that leaves
         // level K-1 in iteration j is K rows behind the arriving one, i.e. P + 1 + K rows behind `of`.
@@ -207,8 +232,8 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const Pa
             cp_async16(fring + (fs * 3 + 0) * TW, p.in[0] + o);
             cp_async16(fring + (fs * 3 + 1) * TW, p.in[1] + o);
             cp_async16(fring + (fs * 3 + 2) * TW, p.in[2] + o);
-            cp_async16(cring + (cs * 2 + 0) * TW, p.ce + o);
-            if (!UCH) cp_async16(cring + (cs * 2 + 1) * TW, p.ch + o);
+            cp_async16(cring + (cs * CS + 0) * TW, p.ce + o);
+            if (!UCH) cp_async16(cring + (cs * CS + 1) * TW, p.ch + o);
         };
         // the window of strip_wave_kernel, every row as two column pairs
         u64 X[K + 1][3][2], Y[K + 1][3][2];
@@ -220,7 +245,7 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const Pa
         {
             const float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             store4(cring + 0 * TW, z);
-            store4(cring + 1 * TW, z);
+            if (!UCH) store4(cring + 1 * TW, z);
         }
 #pragma unroll
         for (int d = 0; d < P; ++d) {
@@ -246,11 +271,11 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const Pa
             for (int s = 0; s < K; ++s) {
                 u64 ce[2], ch[2];
                 const int c = (cr - s) & (NC - 1);  // coefficient slot of row i-s-1
-                load22(cring + (c * 2 + 0) * TW, ce);
+                load22(cring + (c * CS + 0) * TW, ce);
                 if (UCH)
                     ch[0] = ch[1] = chu;
                 else
-                    load22(cring + (c * 2 + 1) * TW, ch);
+                    load22(cring + (c * CS + 1) * TW, ch);
                 const u64 e0 = ST[s][0][0], e1 = ST[s][0][1];
                 // H half-step of the stored row (main.py:69-74).  The column differences straddle the pairs, so they
                 // are four scalar subtractions written straight into a pair (no register moves); the rest is two-wide.
@@ -271,6 +296,38 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const Pa
                 const u64 curl1 = sub2(dy1, sub2(AR[s + 1][1][1], ST[s + 1][1][1]));
                 AR[s + 1][0][0] = add2(e0, mul2(curl0, ce[0], negzero));
                 AR[s + 1][0][1] = add2(e1, mul2(curl1, ce[1], negzero));
+                if (LR && tk.side != 0) {
+                    const float s0[4] = {lo2(e0), hi2(e0), lo2(e1), hi2(e1)};
+                    const float s1[4] = {lo2(AR[s + 1][0][0]), hi2(AR[s + 1][0][0]), lo2(AR[s + 1][0][1]), hi2(AR[s + 1][0][1])};
+                    float out[4];
+                    if (tk.side == 1) {
+                        const float s1r = __shfl_down_sync(FULL, s1[0], 1);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float a0 = q < 3 ? s0[q < 3 ? q + 1 : 3] : right3, a1 = q < 3 ? s1[q < 3 ? q + 1 : 3] : s1r;
+                            const float m = add_rn(a0, mul_rn(coef, sub_rn(a1, s0[q])));
+                            out[q] = bsel(ringm[q], m, s1[q]);
+                        }
+                    } else {
+                        const float s0l = __shfl_up_sync(FULL, s0[3], 1), s1l = __shfl_up_sync(FULL, s1[3], 1);
+                        const float hxo[4] = {lo2(ST[s][1][0]), hi2(ST[s][1][0]), lo2(ST[s][1][1]), hi2(ST[s][1][1])};
+                        const float hyo[4] = {lo2(ST[s][2][0]), hi2(ST[s][2][0]), lo2(ST[s][2][1]), hi2(ST[s][2][1])};
+                        const float hxn[4] = {lo2(AR[s + 1][1][0]), hi2(AR[s + 1][1][0]), lo2(AR[s + 1][1][1]), hi2(AR[s + 1][1][1])};
+                        const float hyn[4] = {lo2(y0), hi2(y0), lo2(y1), hi2(y1)};
+                        float hx2[4], hy2[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float b0 = q > 0 ? s0[q > 0 ? q - 1 : 0] : s0l, b1 = q > 0 ? s1[q > 0 ? q - 1 : 0] : s1l;
+                            const float m = add_rn(b0, mul_rn(coef, sub_rn(b1, s0[q])));
+                            out[q] = bsel(padm[q], s0[q], bsel(ringm[q], m, s1[q]));
+                            hx2[q] = bsel(hoffm[q], hxo[q], hxn[q]);
+                            hy2[q] = bsel(hoffm[q], hyo[q], hyn[q]);
+                        }
+                        AR[s + 1][1][0] = pack2(hx2[0], hx2[1]), AR[s + 1][1][1] = pack2(hx2[2], hx2[3]);
+                        AR[s + 1][2][0] = pack2(hy2[0], hy2[1]), AR[s + 1][2][1] = pack2(hy2[2], hy2[3]);
+                    }
+                    AR[s + 1][0][0] = pack2(out[0], out[1]), AR[s + 1][0][1] = pack2(out[2], out[3]);
+                }
             }
             cr = (cr + 1) & (NC - 1);
             if (core && j >= 2 * K) {  // row y0 + (j - 2K) < y1 has left level K-1, K steps on
@@ -288,7 +345,32 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const Pa
         }
         if (j < n) iter(X, Y, j);
         cp_async_wait<0>();
-        __syncwarp();
+        __syncwarp();  // the ring is reused by the next run
+    }
+}
+
+// The kernel: warps take runs from one ticket; with RING the ring-strip runs come first in the task list (they are the
+// heavier ones) and go through the LR instantiation of the run, everything else through the plain one -- two separate
+// loops in one kernel, so the plain strips pay nothing for the ring code and one launch balances both.
+template <int K, bool UCH, int P, bool RING = false>
+__global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const PassParams<float> p, const WaveTask* tasks, const int n_tasks, int* ticket, const float ch_uniform, const u64 negzero) {
+    constexpr int TW = WAVE_TW, NF = WAVE_NF, NC = WAVE_NC, CS = UCH ? 1 : 2;  // CS: coefficient maps kept in the ring
+    static_assert((NF & (NF - 1)) == 0 && NF > P && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
+    extern __shared__ __align__(16) unsigned char smem_wave[];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    float* fring = reinterpret_cast<float*>(smem_wave) + (size_t)w * (NF * 3 + NC * CS) * TW + 4 * l;  // [NF][3][TW], my 4 columns
+    float* cring = fring + NF * 3 * TW;                                                               // [NC][CS][TW]
+    const u64 chu = pack2(ch_uniform, ch_uniform);
+    for (;;) {
+        int t = 0;
+        if (l == 0) t = atomicAdd(ticket, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tasks) break;
+        const WaveTask tk = tasks[t];
+        if (RING && tk.side != 0)
+            wave_run_x2<K, UCH, P, true>(p, tk, fring, cring, l, chu, negzero);
+        else
+            wave_run_x2<K, UCH, P, false>(p, tk, fring, cring, l, chu, negzero);
     }
 }
 
