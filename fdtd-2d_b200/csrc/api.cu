@@ -693,7 +693,8 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
         // stretches of ring-strip tiles (first / last tile column): a row of them costs about twice a plain row, so they
         // are cut to half the run length, counted in the same budget of runs and handed out first
         std::vector<WaveTask> lr_segs;
-        if (use_wave && !lr_tiles.empty()) {
+        // (on small grids the ring strips do not pay: 2048^2 539 with, 590 Gcell/s without)
+        if (use_wave && !lr_tiles.empty() && n_plain >= 2LL * s->sm_count * WAVE_NW) {
             std::vector<unsigned char> is_lr((size_t)n_tiles, 0);
             for (int id : lr_tiles) is_lr[id] = 1;
             for (int b = 0; b < s->batch; ++b)

@@ -64,23 +64,24 @@ __device__ __forceinline__ void ring_stages(const T* cur, T* nxt, const TileCtx<
                     }
                     __syncthreads();
                 }
-                // ---- S4: 5x5 corner means, main.py:54-61. One thread per corner, reference order. ---
+                // ---- S4: 5x5 corner means, main.py:54-61.  In the reference's order every cell reads its right / lower
+                // (mirrored: inward) neighbours before they are overwritten, so all 100 means are functions of the
+                // post-S3 field: one thread per cell reads, the CTA synchronises, then the cells are written. ---------
                 if ((touchL || touchR) && (touchT || touchB)) {
-                    if (tid < 4) {
-                        const bool top = tid < 2, left = (tid & 1) == 0;
-                        for (int a = 0; a < RING; ++a) {
-                            const int gi = top ? a : Rg - 1 - a;
-                            const int li = gi - gr0, lin = top ? li + 1 : li - 1;
-                            if (li < 0 || li >= TH || lin < 0 || lin >= TH) continue;
-                            for (int c = 0; c < RING; ++c) {
-                                const int gj = left ? c : C - 1 - c;
-                                const int lj = gj - lc0, ljn = left ? lj + 1 : lj - 1;
-                                if (lj < 0 || lj >= TW || ljn < 0 || ljn >= TW) continue;
-                                const T sum = add_rn(nxt[li * TW + ljn], nxt[lin * TW + lj]);
-                                nxt[li * TW + lj] = mul_rn(sum, (T)0.5);  // == sum / 2 exactly
-                            }
+                    T val = (T)0;
+                    int dst = -1;
+                    if (tid < 4 * RING * RING) {
+                        const int corner = tid / (RING * RING), a = (tid / RING) % RING, c = tid % RING;
+                        const bool top = corner < 2, left = (corner & 1) == 0;
+                        const int gi = top ? a : Rg - 1 - a, li = gi - gr0, lin = top ? li + 1 : li - 1;
+                        const int gj = left ? c : C - 1 - c, lj = gj - lc0, ljn = left ? lj + 1 : lj - 1;
+                        if (li >= 0 && li < TH && lin >= 0 && lin < TH && lj >= 0 && lj < TW && ljn >= 0 && ljn < TW) {
+                            val = mul_rn(add_rn(nxt[li * TW + ljn], nxt[lin * TW + lj]), (T)0.5);  // == sum / 2 exactly
+                            dst = li * TW + lj;
                         }
                     }
+                    __syncthreads();
+                    if (dst >= 0) nxt[dst] = val;
                     __syncthreads();
                 }
 }

@@ -99,23 +99,29 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
     tc.src_hi = p.src_range ? p.src_range[b + 1] : 0;
     tc.prb_lo = p.probe_range ? p.probe_range[b] : 0;
     tc.prb_hi = p.probe_range ? p.probe_range[b + 1] : 0;
-    // does any source / probe of this grid fall inside this tile?
-    int mine = 0;
+    // does any source / probe of this grid fall inside this tile, and in which warps' rows?
+    __shared__ unsigned cell_warps;
+    if (tid == 0) cell_warps = 0u;
+    __syncthreads();
     for (int q = tc.src_lo + tid; q < tc.src_hi; q += NT) {
         const Cell c = p.src[q];
-        mine |= (c.row >= gr0 && c.row < gr0 + TH && c.col >= lc0 && c.col < lc0 + TW);
+        if (c.row >= gr0 && c.row < gr0 + TH && c.col >= lc0 && c.col < lc0 + TW) atomicOr(&cell_warps, 1u << ((c.row - gr0) / MR));
     }
     for (int q = tc.prb_lo + tid; q < tc.prb_hi; q += NT) {
         const Cell c = p.probes[q];
-        mine |= (c.row >= gr0 && c.row < gr0 + TH && c.col >= lc0 && c.col < lc0 + TW);
+        if (c.row >= gr0 && c.row < gr0 + TH && c.col >= lc0 && c.col < lc0 + TW) atomicOr(&cell_warps, 1u << ((c.row - gr0) / MR));
     }
-    // Sources / probes anywhere in the tile: every step parks the whole field in shared memory.  Top / bottom ring:
-    // only the warps that hold ring rows (global rows 0..5, Rg-6..Rg-1) park theirs.  Left / right ring: nothing is
-    // parked, S2 runs in registers below.
-    const bool full = __syncthreads_or(mine);
-    const bool staged = full || tc.touchT || tc.touchB;
+    __syncthreads();
+    // Sources / probes in the tile: the warps that hold their rows park the field after the interior update (s1), the
+    // source is added and the probes are read there.  Top / bottom ring: the warps that hold ring rows (global rows 0..5,
+    // Rg-6..Rg-1) park the field before (s0) and after (s1) the update for S3 / S4.  Left / right ring: nothing is parked,
+    // S2 runs in registers below.
+    const bool full = cell_warps != 0u;
+    const bool tb = tc.touchT || tc.touchB;
+    const bool staged = full || tb;
     const int gw0 = gr0 + li0, gw1 = gw0 + MR - 1;  // global rows of this warp
-    const bool park = full || (staged && ((gw0 <= RING && gw1 >= 0) || (gw1 >= Rg - 1 - RING && gw0 <= Rg - 1)));
+    const bool park0 = tb && ((gw0 <= RING && gw1 >= 0) || (gw1 >= Rg - 1 - RING && gw0 <= Rg - 1));
+    const bool park = park0 || ((cell_warps >> w) & 1u);
     const bool lr = tc.touchL || tc.touchR;
     // Mur left / right (main.py:33-41) on registers: in the reference's order every column reads its inward neighbour
     // before that one is overwritten, so for rows 1..Rg-2
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
         }
         // ---- interior Ez update (S1), Mur left/right (S2) -------------------------------------------
         store4(sHx + w * TW + lj, hx[MR - 1]);
-        if (park) {
+        if (park0) {
 #pragma unroll
             for (int r = 0; r < MR; ++r) store4(s0 + (li0 + r) * TW + lj, e[r]);
         }
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
                 for (int r = 0; r < MR; ++r) store4(s1 + (li0 + r) * TW + lj, e[r]);
             }
             __syncthreads();
-            ring_stages<T, TH, TW, NT, true>(s0, s1, tc, tid);
+            if (tb) ring_stages<T, TH, TW, NT, true>(s0, s1, tc, tid);
             if (full) source_and_probes<T, TH, TW, NT>(s1, p, tc, p.step0 + s, tid);
             if (park) {
 #pragma unroll
