@@ -785,7 +785,11 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
         if (!tasks.empty()) {
             CUDA_TRY(cudaMalloc(&pl->d_ticket, sizeof(int)));
             CUDA_TRY(cudaMalloc(&pl->d_wave, sizeof(WaveTask) * tasks.size()));
-            CUDA_TRY(cudaMemcpy(pl->d_wave, tasks.data(), sizeof(WaveTask) * tasks.size(), cudaMemcpyHostToDevice));
+            // on the handle's own stream: a plain cudaMemcpy goes through the legacy default stream, which a non-blocking
+            // stream does not wait for -- with another handle keeping the GPU busy the kernel could read the list before it
+            // had landed (seen as an illegal address with two handles in two host threads)
+            CUDA_TRY(cudaMemcpyAsync(pl->d_wave, tasks.data(), sizeof(WaveTask) * tasks.size(), cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));  // `tasks` dies with this block
         }
     }
     gen_rest.insert(gen_rest.end(), lr_tiles.begin(), lr_tiles.end());  // no ring strips: they are ordinary edge tiles
@@ -1482,9 +1486,11 @@ int fdtd2d_set_sources(fdtd2d_sim* s, int n_cells, const int32_t* grid, const in
     CUDA_TRY(cudaMalloc(&s->d_src, sizeof(Cell) * n_cells));
     CUDA_TRY(cudaMalloc(&s->d_src_range, sizeof(int) * range.size()));
     CUDA_TRY(cudaMalloc(&s->d_amp, sizeof(double) * (size_t)n_waves * n_steps));
-    CUDA_TRY(cudaMemcpy(s->d_src, cells.data(), sizeof(Cell) * n_cells, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(s->d_src_range, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(s->d_amp, tables, sizeof(double) * (size_t)n_waves * n_steps, cudaMemcpyHostToDevice));
+    // (stream-ordered copies, then a wait: see the note at the wavefront task list)
+    CUDA_TRY(cudaMemcpyAsync(s->d_src, cells.data(), sizeof(Cell) * n_cells, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->d_src_range, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->d_amp, tables, sizeof(double) * (size_t)n_waves * n_steps, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->h_src = cells;
     s->n_src = n_cells;
     s->n_waves = n_waves;
@@ -1517,9 +1523,10 @@ int fdtd2d_set_probes(fdtd2d_sim* s, int n_probes, const int32_t* grid, const in
     CUDA_TRY(cudaMalloc(&s->d_probe, sizeof(Cell) * n_probes));
     CUDA_TRY(cudaMalloc(&s->d_probe_range, sizeof(int) * range.size()));
     CUDA_TRY(cudaMalloc(&s->d_trace, tbytes));
-    CUDA_TRY(cudaMemcpy(s->d_probe, cells.data(), sizeof(Cell) * n_probes, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(s->d_probe_range, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemset(s->d_trace, 0, tbytes));
+    CUDA_TRY(cudaMemcpyAsync(s->d_probe, cells.data(), sizeof(Cell) * n_probes, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->d_probe_range, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->d_trace, 0, tbytes, s->stream));
     s->h_probe = cells;
     s->n_probe = n_probes;
     s->trace_cap = capacity_steps;

@@ -435,3 +435,51 @@ def test_wavefront_equals_tile_kernel_large(fd, monkeypatch):
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
             assert_bits(a, b, "wavefront vs tile kernel")
+
+
+def test_two_handles_in_two_host_threads(fd, monkeypatch):
+    """Two handles driven from two host threads at the same time (what bench.py's e2e does: one job's copies overlap
+    the other's kernels): upload, step, download in a loop; both must give what a single handle gives alone.  The
+    wavefront kernel is forced on so that its task list (uploaded when the plan is built) is in play."""
+    import threading
+
+    monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", "0")
+    R, C, n = 1500, 2100, 400
+    rng = np.random.default_rng(11)
+    eps, mu, Ez, Hx, Hy = _random_problem(rng, R, C, "float32")
+    mu[...] = np.float32(4 * np.pi * 1e-7)
+
+    def job(sim):
+        sim.step_index = 0
+        sim.set_materials(eps, mu)
+        sim.set_state(Ez, Hx, Hy)
+        sim.step(n, 0)
+        return sim.state() + (sim.read_probes(0, n),)
+
+    def make():
+        sim = fd.Simulation(R, C, np.float32, dt=DT, dx=DX)
+        sim.set_kernel_variant(2)
+        sim.set_point_source(R // 2, C // 2, n, FC)
+        sim.set_probes([(R // 2, C // 2 + 16), (R // 4, C // 4), (R // 2, 8)], n)
+        return sim
+
+    with make() as sim:
+        ref = job(sim)
+    sims, res, errs = [make(), make()], [None, None], []
+
+    def work(w):
+        try:
+            for _ in range(4):
+                res[w] = job(sims[w])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(w,)) for w in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for s_ in sims:
+        s_.close()
+    assert not errs, errs
+    for r in res:
+        for a, b in zip(r, ref):
+            assert_bits(a, b, "two threads vs one handle alone")
