@@ -300,7 +300,7 @@ def main():
     cols = wl["cols"]
     grows = wl["rows"] if (strong or batch) else wl["rows"] * world  # weak scaling: fixed rows per GPU
     inner = wl["inner"]
-    k = args.k  # 0: the library picks (fp32: 8, or 12 for a large single-GPU grid with uniform permeability)
+    k = args.k  # 0: the library picks (fp32: 8)
     stream = torch.cuda.current_stream().cuda_stream
 
     sim = make_sim(fd, wl, grows, cols, rank, world, local_rank, k)
@@ -380,8 +380,9 @@ def main():
                        "batch_per_gpu": batch or 1, "inner_leapfrog_steps_per_step": inner,
                        "k_temporal": k_eff,
                        "kernel": ("cluster-resident (grid on chip for the whole step call, 1 launch per bench step)" if resident
-                                  else f"{k_eff} leapfrog steps per HBM round trip: row-streaming wavefront strips on the plain regions (k = 8 or 12, "
-                                       "large grids) or persistent TMA-fed tiles, edge-capable tiles on the ring / sources / probes"),
+                                  else f"{k_eff} leapfrog steps per HBM round trip: row-streaming wavefront strips (packed fp32x2 arithmetic; the "
+                                       "left / right Mur ring rides along) from ~2000^2, else persistent TMA-fed tiles; "
+                                       "edge-capable tiles on the top / bottom ring, corners, sources, probes"),
                        "parallelism": ("independent grids per rank" if batch else f"y-slabs x{world}") if world > 1 else "single GPU",
                        "l2": "state is larger than L2 (inputs larger than L2; no flush needed)",
                        "seed": 2026, "source": "ricker fc=30e9 at centre", "probes": len(probes)},

@@ -191,7 +191,7 @@ class SlabSimulation:
 
         if self.world == 1:
             before = self.sim.pass_count
-            self.sim.step(n_steps, k)  # k = 0: the library picks (8, or 12 for a large grid with uniform permeability)
+            self.sim.step(n_steps, k)  # k = 0: the library picks (fp32: 8)
             self.tile_launch_count += self.sim.pass_count - before
             return
         k = k or DEFAULT_K

@@ -127,8 +127,9 @@ int fdtd2d_read_probes(fdtd2d_sim* s, void* out, int64_t first_step, int n_steps
 /* ---- time stepping: replaces the loop body fdtd.py:31-34 ------------------------------------- */
 /* n_steps leapfrog steps (H -> Ez+Mur+corners -> source -> probe sample), k_temporal steps per HBM
  * round trip (1 <= k <= FDTD2D_MAX_K; for slabs k <= halo and the caller exchanges halos every k).
- * k_temporal = 0 picks the library default (fp64: 4; fp32: 8, or 12 for a large grid with uniform permeability,
- * where the row-streaming wavefront kernel has a 12-level instance). */
+ * k_temporal = 0 picks the library default (fp64: 4; fp32: 8).  k = 12 has a row-streaming wavefront instance for
+ * grids with uniform permeability; on B200 it is no faster than k = 8 (latency-bound at 255 registers), so it is not
+ * chosen automatically. */
 #define FDTD2D_MAX_K 12
 int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal);
 /* One pass applying only the phases in `phases` (FDTD2D_PHASE_*); with PHASE_H alone it is
