@@ -694,7 +694,9 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
         // are cut to half the run length, counted in the same budget of runs and handed out first
         std::vector<WaveTask> lr_segs;
         // (on small grids the ring strips do not pay: 2048^2 539 with, 590 Gcell/s without)
-        if (use_wave && !lr_tiles.empty() && n_plain >= 2LL * s->sm_count * WAVE_NW) {
+        long long ring_min_tiles = 2LL * s->sm_count * WAVE_NW;
+        if (const char* e = getenv("FDTD2D_RING_MIN_TILES")) ring_min_tiles = std::max(0, atoi(e));
+        if (use_wave && !lr_tiles.empty() && n_plain >= ring_min_tiles) {
             std::vector<unsigned char> is_lr((size_t)n_tiles, 0);
             for (int id : lr_tiles) is_lr[id] = 1;
             for (int b = 0; b < s->batch; ++b)

@@ -389,6 +389,7 @@ def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, uniform_mu, k, x2
     x2 = 1) and the scalar instantiations; 12 levels exist for uniform permeability (otherwise those passes run on the
     tile kernels, which is checked all the same)."""
     monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", "0")
+    monkeypatch.setenv("FDTD2D_RING_MIN_TILES", "0")  # ring strips (left / right Mur ring on the wavefront) where C >= 512
     monkeypatch.setenv("FDTD2D_WAVE_X2", x2)
     c_oracle, npo = oracle
     R, C = shape
@@ -444,6 +445,7 @@ def test_two_handles_in_two_host_threads(fd, monkeypatch):
     import threading
 
     monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", "0")
+    monkeypatch.setenv("FDTD2D_RING_MIN_TILES", "0")
     R, C, n = 1500, 2100, 400
     rng = np.random.default_rng(11)
     eps, mu, Ez, Hx, Hy = _random_problem(rng, R, C, "float32")

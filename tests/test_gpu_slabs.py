@@ -20,6 +20,7 @@ def plain_tile_kernel(request, monkeypatch):
     grids (in a slab pass the band tiles stay on the tile kernel, the rest of the plain tiles become strip runs)."""
     if request.param == "wavefront":
         monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", "0")
+        monkeypatch.setenv("FDTD2D_RING_MIN_TILES", "0")
     return request.param
 
 
