@@ -490,7 +490,6 @@ template <typename T, int MR, int NW> static int launch_edge_tt(int dev, const P
     const size_t smem = (size_t)(2 * MR * NW * FAST_TW + 2 * NW * FAST_TW) * sizeof(T);
     if (!done) {
         CUDA_TRY(cudaFuncSetAttribute(tile_edge_kernel<T, MR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(tile_edge_kernel<T, MR, NW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         done = true;
     }
     tile_edge_kernel<T, MR, NW><<<(unsigned)n_tiles, NW * 32, smem, st>>>(p);

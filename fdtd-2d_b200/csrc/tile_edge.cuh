@@ -116,13 +116,17 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
     // source is added and the probes are read there.  Top / bottom ring: the warps that hold ring rows (global rows 0..5,
     // Rg-6..Rg-1) park the field before (s0) and after (s1) the update for S3 / S4.  Left / right ring: nothing is parked,
     // S2 runs in registers below.
+    // (fp64 keeps S2 in shared memory with every row parked: its kernel sits at the 128-register limit of a 512-thread
+    // CTA and the register form cost it a third of its speed)
+    constexpr bool S2REG = sizeof(T) == 4;
     const bool full = cell_warps != 0u;
     const bool tb = tc.touchT || tc.touchB;
-    const bool staged = full || tb;
+    const bool ring_smem = S2REG ? tb : (tb || tc.touchL || tc.touchR);  // ring stages that run in shared memory
+    const bool staged = full || ring_smem;
     const int gw0 = gr0 + li0, gw1 = gw0 + MR - 1;  // global rows of this warp
-    const bool park0 = tb && ((gw0 <= RING && gw1 >= 0) || (gw1 >= Rg - 1 - RING && gw0 <= Rg - 1));
+    const bool park0 = S2REG ? (tb && ((gw0 <= RING && gw1 >= 0) || (gw1 >= Rg - 1 - RING && gw0 <= Rg - 1))) : ring_smem;
     const bool park = park0 || ((cell_warps >> w) & 1u);
-    const bool lr = tc.touchL || tc.touchR;
+    const bool lr = S2REG && (tc.touchL || tc.touchR);
     // Mur left / right (main.py:33-41) on registers: in the reference's order every column reads its inward neighbour
     // before that one is overwritten, so for rows 1..Rg-2
     //   Ez[i, q]     = S0[i, q+1]   + coef * (S1[i, q+1]   - S0[i, q])      q = 0..4
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
                 for (int r = 0; r < MR; ++r) store4(s1 + (li0 + r) * TW + lj, e[r]);
             }
             __syncthreads();
-            if (tb) ring_stages<T, TH, TW, NT, true>(s0, s1, tc, tid);
+            if (ring_smem) ring_stages<T, TH, TW, NT, S2REG>(s0, s1, tc, tid);
             if (full) source_and_probes<T, TH, TW, NT>(s1, p, tc, p.step0 + s, tid);
             if (park) {
 #pragma unroll
