@@ -1,5 +1,6 @@
-// Row-streaming wavefront kernel (fp32, plain regions): K leapfrog steps per HBM round trip with redundancy only in
-// the COLUMN halo.
+// Row-streaming wavefront kernels (fp32): K leapfrog steps per HBM round trip with redundancy only in the COLUMN halo.
+// Two forms: strip_wave_kernel (scalar arithmetic, plain regions only) and, further down, strip_wave_x2_kernel -- the
+// default -- with sm_100a's two-wide fp32 instructions and, in its LR form, the left / right Mur ring riding along.
 //
 // The overlapped tiles of tile_tma.cuh recompute a halo of K rows above and below every 64-row tile (core 48 x 112 of
 // 64 x 128: 34 % of the arithmetic is thrown away at K = 8).  Here one WARP owns a strip of 128 columns (core 112) and
@@ -30,14 +31,14 @@ constexpr int WAVE_NC = 16;     // rows of the coefficient ring (a power of two 
 constexpr int WAVE_TW = 128;    // strip width (columns per warp)
 
 // one run of rows of one strip: grid b, haloed strip starts at column x0, rows [y0, y1) are stored.
-// Ring strips (side != 0, strip_wave_x2_kernel<.., LR = true>) also say which of their 128 columns they store: [c0, c1).
+// Ring strips (side != 0, wave_run_x2<.., LR = true>) also say which of their 128 columns they store: [c0, c1).
 struct WaveTask {
     int32_t b, x0, y0, y1;
     int32_t c0, c1, side, pad;  // side: 0 plain strip, 1 holds the left Mur ring (columns 0..4), 2 the right one
 };
 
 // per warp: NF rows of the three fields + NC rows of dt/(eps*dx) (+ NC rows of dt/(mu*dx) unless that is a scalar:
-// the packed kernel then leaves the second ring out, which is what lets a ring-strip CTA fit beside a plain-strip CTA)
+// the packed kernel then leaves the second ring out)
 __host__ __device__ constexpr size_t wave_smem_bytes(int warps = WAVE_NW, bool no_ch_ring = false) {
     return (size_t)warps * (WAVE_NF * 3 + WAVE_NC * (no_ch_ring ? 1 : 2)) * WAVE_TW * sizeof(float);
 }
@@ -168,7 +169,9 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassP
 // ISSUE SLOTS -- and the scalar kernel above is bound by issue (79 %), its FP pipe only 63 % busy.  A lane's four columns
 // are two pairs (c, c+1), (c+2, c+3), exactly as the 16-byte loads deliver them; only the two column differences, whose
 // operands straddle the pairs, stay scalar (their results land in a pair directly, so no register moves).
-// A level is 18 packed + 8 scalar instructions + 2 shuffles instead of 44 + 2, which is what makes K = 12 levels pay.
+// A level is 18 packed + 8 scalar instructions + 2 shuffles instead of 44 + 2 (437 -> 362 instructions per row at K = 8).
+// At K = 8 the kernel is DRAM-bound either way (94 % of the copy bandwidth); the 12-level instance, which moves a third
+// less, needs the packed form to get level with it (1586 vs 1571 Gcell/s at 16384^2; scalar 1366) and stays opt-in.
 // Bit-exactness: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with --fmad false (scalar code is not
 // touched), so the product is written as fma.rn.f32x2(a, b, -0) with the -0 pair coming in as a kernel argument the
 // compiler cannot see through: rn(a*b + -0) = rn(a*b) for every input incl. signed zeros, and an FFMA2 that already

@@ -418,6 +418,43 @@ def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, uniform_mu, k, x2
     assert_bits(gHy, oHy, "Hy")
 
 
+def test_wavefront_batched_grids_vs_oracle(fd, oracle, monkeypatch):
+    """Three independent 400 x 900 grids in one handle on the wavefront kernel (ring strips included): per-grid media and
+    Mur coefficient, sources and probes in different places, each grid against the oracle."""
+    monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", "0")
+    monkeypatch.setenv("FDTD2D_RING_MIN_TILES", "0")
+    c_oracle, npo = oracle
+    B, R, C, nsteps = 3, 400, 900, 24
+    rng = np.random.default_rng(21)
+    probs = [_random_problem(rng, R, C, "float32") for _ in range(B)]
+    for p_ in probs:
+        p_[1][...] = np.float32(4 * np.pi * 1e-7)
+    eps, mu, Ez, Hx, Hy = (np.stack([p_[i] for p_ in probs]) for i in range(5))
+    tables = np.stack([npo.source_table("ricker", nsteps, DT, FC + 1e9 * b) + 0.25 for b in range(B)])
+    per_grid = [[(R // 2 + 10 * b, C // 2 - 50 * b)] for b in range(B)]
+    cells = [(b, r, c, b) for b in range(B) for r, c in per_grid[b]]
+    pcell = [(R // 3, C // 3 + 7), (R // 2, 6)]
+    probes = [(b, r, c) for r, c in pcell for b in range(B)]
+    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX, batch=B) as sim:
+        sim.set_kernel_variant(2)
+        sim.set_materials(eps, mu)
+        sim.set_state(Ez, Hx, Hy)
+        sim.set_sources(cells, tables)
+        sim.set_probes(probes, nsteps)
+        sim.step(nsteps, 8)
+        gEz, gHx, gHy = sim.state()
+        gtrace = sim.read_probes()
+    for b in range(B):
+        ce, ch, coef = c_oracle.coefficients(eps[b], mu[b], DT, DX, np.dtype(np.float32))
+        oEz, oHx, oHy = Ez[b].copy(), Hx[b].copy(), Hy[b].copy()
+        otr = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, nsteps, tables[b], per_grid[b], pcell, omp=True)
+        assert_bits(gEz[b], oEz, f"Ez grid {b}")
+        assert_bits(gHx[b], oHx, f"Hx grid {b}")
+        assert_bits(gHy[b], oHy, f"Hy grid {b}")
+        assert_bits(gtrace[:, b], otr[:, 0], f"probe A grid {b}")
+        assert_bits(gtrace[:, B + b], otr[:, 1], f"probe B grid {b}")
+
+
 def test_wavefront_equals_tile_kernel_large(fd, monkeypatch):
     """6000 x 5000 fp32, 40 steps near the Ricker peak: the wavefront strips (packed and scalar, 8 and 12 levels, and
     whatever k = 0 picks) and the persistent TMA tile kernel (FDTD2D_WAVE_MIN_TILES huge) must agree bit for bit."""
