@@ -382,7 +382,7 @@ def test_kernel_variants_agree(fd, variant):
 @pytest.mark.parametrize("shape,nsteps", [((300, 517), 40), ((1024, 1024), 24), ((203, 600), 17), ((2000, 260), 32),
                                           ((700, 1500), 8)])
 @pytest.mark.parametrize("uniform_mu", [False, True])
-@pytest.mark.parametrize("k,x2", [(8, "1"), (8, "0"), (12, "1"), (12, "0")])
+@pytest.mark.parametrize("k,x2", [(8, "1"), (8, "0"), (10, "1"), (12, "1"), (12, "0")])
 def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, uniform_mu, k, x2, monkeypatch):
     """Forced onto small grids (FDTD2D_WAVE_MIN_TILES=0) so the oracle can check it: runs of plain tiles broken by
     sources and probes, ragged sizes, the remainder pass (nsteps % k) on the tile kernel; the packed (FADD2 / FFMA2,
