@@ -292,6 +292,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # the halo exchange must not queue behind the persistent stepping kernel of the same pass: NCCL's stream gets
+        # high priority, so its few CTAs are placed first when the band tiles are done (SlabSimulation's side stream too)
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
 

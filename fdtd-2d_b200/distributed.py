@@ -11,10 +11,19 @@ anywhere, so the result is bit-identical to the single-GPU run.
 The exchange is one batched group of NCCL send/recv over NVLink (torch.distributed P2P ops on tensors
 that alias the library's device buffers -- no staging copy).  The exchange plumbing (`HaloExchange`) is
 independent of CUDA so that it is covered by world_size-2 gloo tests on CPU.
+
+Priority: the stepping kernel of a pass is persistent (one CTA per SM until the pass is done), so an exchange kernel
+that becomes ready at the same moment would wait for the whole pass.  NCCL's stream therefore has to be a high-priority
+one -- `TORCH_NCCL_HIGH_PRIORITY=1`, read by torch when the process group is created; importing this module sets it
+unless the caller already chose -- and the side stream the exchange is issued from is high-priority too.  Measured on
+2 x B200, 16384^2 per GPU: 3031 -> 3198 Gcell/s (92 % -> 97 % of 2 x one GPU).
 """
 from __future__ import annotations
 
+import os
 from typing import Callable
+
+os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
 
 import numpy as np
 
@@ -94,7 +103,7 @@ class SlabSimulation:
             self._xchg_next = HaloExchange(rank, world, lambda f, side: self._blocks(f, side, True), group)
             # kernels and the exchange are ordered through torch streams: adopt the current one
             self.set_stream(torch.cuda.current_stream(device).cuda_stream)
-            self._comm = torch.cuda.Stream(device)
+            self._comm = torch.cuda.Stream(device, priority=-1)  # the exchange goes ahead of the rest of the pass
 
     # -- halo plumbing ------------------------------------------------------------------------
     def _blocks(self, field, side, next_state=False):
