@@ -3,6 +3,7 @@ logic of the Python surface, and hygiene rules (no oracle / CPU fallback in the 
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -136,3 +137,31 @@ def test_seismic_lut_construction():
     g = fd.eps_background(np.array([[8.85418e-12, 2 * 8.85418e-12], [10 * 8.85418e-12, 8.85418e-12]]))
     assert g.dtype == np.uint8 and g[0, 0] == 255 and g[1, 0] == 128
     assert (fd.eps_background(np.full((3, 3), 8.85418e-12)) == 255).all()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path, here the bit-identical numpy port) needs no GPU and prints
+    one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "small",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Gcell-updates/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 2 and line["warmup"] == 1 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_bench_fails_loudly_without_a_gpu():
+    import subprocess
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "small", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
