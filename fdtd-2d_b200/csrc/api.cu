@@ -591,6 +591,34 @@ static void free_plans(fdtd2d_sim* s) {
 
 static int check_ch_uniform(fdtd2d_sim* s);
 
+// Run lengths of the wavefront kernel (host only, no CUDA; exported as fdtd2d_plan_wave_runs for the CPU tests).
+// rows[i] is the height of stretch i (a vertical sequence of plain tiles of one strip), ring[i] != 0 marks a ring strip,
+// whose rows cost about twice a plain row: its runs are half as long and its rows count double.  The result is the
+// shortest plain run length L (>= 4k rows: a run spends 2k rows warming up) for which the stretches fall into at most
+// m x `warps` runs, m = the smallest count of runs per warp that keeps a run under ~cap_rows rows; parts[i] runs of
+// (nearly) equal height then cover stretch i.
+static int plan_wave_runs(const std::vector<int>& rows, const std::vector<unsigned char>& ring, long long warps, long long cap_rows, int k,
+                          std::vector<int>* parts) {
+    long long total = 0;
+    int longest = 1;
+    for (size_t i = 0; i < rows.size(); ++i) total += (ring[i] ? 2LL : 1LL) * rows[i], longest = std::max(longest, rows[i]);
+    const long long m = std::max<long long>(1, (total + warps * cap_rows - 1) / (warps * cap_rows));
+    auto run_len = [&](size_t i, int len) { return ring[i] ? std::max(4 * k, len / 2) : len; };
+    auto count_runs = [&](int len) {
+        long long c = 0;
+        for (size_t i = 0; i < rows.size(); ++i) c += (rows[i] + run_len(i, len) - 1) / run_len(i, len);
+        return c;
+    };
+    int lo = std::min(longest, 4 * k), hi = std::max(longest, 8 * k);
+    while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if (count_runs(mid) <= m * warps) hi = mid; else lo = mid + 1;
+    }
+    parts->resize(rows.size());
+    for (size_t i = 0; i < rows.size(); ++i) (*parts)[i] = (rows[i] + run_len(i, lo) - 1) / run_len(i, lo);
+    return lo;
+}
+
 // Split the TH x 128 tile grid into plain tiles (fast kernel) and the rest (generic kernel).
 static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
     TilePlan& tp = pl->tp;
@@ -728,9 +756,6 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
         std::vector<WaveTask> tasks;
         for (int pass = 0; use_wave && pass < 2; ++pass) {  // pass 0: plain tiles outside the band; pass 1: all plain tiles
             std::vector<WaveTask> segs = lr_segs;  // maximal stretches, in rows
-            long long total_rows = 0;
-            int longest = 1;
-            for (const WaveTask& g : lr_segs) total_rows += 2 * (g.y1 - g.y0), longest = std::max(longest, g.y1 - g.y0);
             for (int b = 0; b < s->batch; ++b)
                 for (int tx = 0; tx < tp.tiles_x; ++tx) {
                     int run = 0;
@@ -746,30 +771,20 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
                             t.b = b, t.x0 = tx * tp.CW - tp.hx, t.y0 = (ty - run) * tp.CH, t.y1 = ty * tp.CH;
                             t.c0 = tp.hx, t.c1 = tp.hx + tp.CW, t.side = 0, t.pad = 0;
                             segs.push_back(t);
-                            total_rows += t.y1 - t.y0;
-                            longest = std::max(longest, t.y1 - t.y0);
                         }
                         run = 0;
                     }
                 }
-            const long long W = (long long)s->sm_count * WAVE_NW;
-            const long long m = std::max<long long>(1, (total_rows + W * run_rows - 1) / (W * run_rows));
-            auto run_len = [&](const WaveTask& g, int len) { return g.side ? std::max(4 * k, len / 2) : len; };
-            auto count_runs = [&](int len) {
-                long long c = 0;
-                for (const WaveTask& g : segs) c += (g.y1 - g.y0 + run_len(g, len) - 1) / run_len(g, len);
-                return c;
-            };
-            int lo = std::min(longest, 4 * k), hi = std::max(longest, 8 * k);  // shortest run length that gives at most m x W runs
-            while (lo < hi) {
-                const int mid = (lo + hi) / 2;
-                if (count_runs(mid) <= m * W) hi = mid; else lo = mid + 1;
-            }
-            for (const WaveTask& g : segs) {
-                const int rows = g.y1 - g.y0, len = run_len(g, lo), parts = (rows + len - 1) / len;
-                for (int q = 0; q < parts; ++q) {
+            std::vector<int> seg_rows(segs.size()), parts;
+            std::vector<unsigned char> seg_ring(segs.size());
+            for (size_t i = 0; i < segs.size(); ++i) seg_rows[i] = segs[i].y1 - segs[i].y0, seg_ring[i] = segs[i].side != 0;
+            plan_wave_runs(seg_rows, seg_ring, (long long)s->sm_count * WAVE_NW, run_rows, k, &parts);
+            for (size_t i = 0; i < segs.size(); ++i) {
+                const WaveTask& g = segs[i];
+                const int rows = seg_rows[i];
+                for (int q = 0; q < parts[i]; ++q) {
                     WaveTask t = g;
-                    t.y0 = g.y0 + (int)((long long)rows * q / parts), t.y1 = g.y0 + (int)((long long)rows * (q + 1) / parts);
+                    t.y0 = g.y0 + (int)((long long)rows * q / parts[i]), t.y1 = g.y0 + (int)((long long)rows * (q + 1) / parts[i]);
                     tasks.push_back(t);
                 }
             }
@@ -1617,6 +1632,18 @@ int fdtd2d_set_step_index(fdtd2d_sim* s, int64_t step) {
 int fdtd2d_set_kernel_variant(fdtd2d_sim* s, int variant) {
     REQUIRE(s && variant >= 0 && variant <= 4, "bad argument");
     s->variant = variant;
+    return 0;
+}
+
+int fdtd2d_plan_wave_runs(int n_stretches, const int32_t* rows, const uint8_t* ring, int warps, int cap_rows, int k, int32_t* parts,
+                          int32_t* run_rows) {
+    REQUIRE(n_stretches >= 0 && warps > 0 && cap_rows > 0 && k > 0 && (n_stretches == 0 || (rows && ring && parts)), "bad argument");
+    std::vector<int> r(rows, rows + n_stretches), pr;
+    std::vector<unsigned char> g(ring, ring + n_stretches);
+    for (int v : r) REQUIRE(v > 0, "a stretch has at least one row");
+    const int len = plan_wave_runs(r, g, warps, cap_rows, k, &pr);
+    for (int i = 0; i < n_stretches; ++i) parts[i] = pr[i];
+    if (run_rows) *run_rows = len;
     return 0;
 }
 

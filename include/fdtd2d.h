@@ -148,6 +148,12 @@ int fdtd2d_set_kernel_variant(fdtd2d_sim* s, int variant);
 /* Number of stepping passes so far: one per HBM round trip of the fields (k leapfrog steps of the tile / wavefront
  * kernels, or a whole fdtd2d_step call of the cluster-resident kernel).  bench.py's roofline divides by it. */
 int fdtd2d_pass_count(const fdtd2d_sim* s, int64_t* passes);
+/* Host-only planning helper (no GPU needed; exported so that the CPU tests cover it): how the row-streaming wavefront
+ * kernel cuts `n_stretches` vertical stretches of rows[i] rows (ring[i] != 0: a strip that carries the left / right Mur
+ * ring, whose rows cost about twice as much) into runs for `warps` independent warps.  parts[i] receives the number of
+ * (nearly equal) runs of stretch i, *run_rows the plain run length chosen.  No reference counterpart. */
+int fdtd2d_plan_wave_runs(int n_stretches, const int32_t* rows, const uint8_t* ring, int warps, int cap_rows, int k,
+                          int32_t* parts, int32_t* run_rows);
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 int fdtd2d_launch_count(const fdtd2d_sim* s, int64_t* launches);
 

@@ -165,3 +165,49 @@ def test_bench_fails_loudly_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "small", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def _plan(lib, rows, ring, warps=1184, cap=640, k=8):
+    rows = np.ascontiguousarray(rows, np.int32)
+    ring = np.ascontiguousarray(ring, np.uint8)
+    parts = np.zeros(len(rows), np.int32)
+    length = ctypes.c_int32()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _lib.check(lib.fdtd2d_plan_wave_runs(len(rows), p(rows), p(ring), warps, cap, k, p(parts), ctypes.cast(ctypes.byref(length), ctypes.c_void_p)))
+    return parts, length.value
+
+
+@pytest.mark.parametrize("n", [4096, 6000, 8192, 16384])
+def test_wave_run_planning_balances_the_warps(lib, n):
+    """The host logic that cuts the wavefront kernel's work into runs (fdtd2d_plan_wave_runs, no GPU needed): an n x n
+    grid's strips fall into at most m x 1184 runs of (nearly) equal cost -- m as small as the ~640-row cap allows -- with
+    the two ring strips cut to half the length; nothing shorter than 4k rows, no stretch lost."""
+    k, CH, CW, W = 8, 48, 112, 148 * 8
+    strips = -(-n // CW) - 2                       # plain tile columns
+    rows_plain = (n // CH - 2) * CH                # rows between the top and the bottom ring tiles
+    rows = [rows_plain] * strips + [rows_plain] * 2
+    ring = [0] * strips + [1] * 2
+    parts, L = _plan(lib, rows, ring, W, 640, k)
+    weighted = rows_plain * (strips + 4)           # ring rows count double
+    m = max(1, -(-weighted // (W * 640)))
+    assert parts.sum() <= m * W
+    assert parts.sum() > 0.9 * m * W or m == 1     # and the budget is used: the last round is not mostly idle warps
+    assert L >= 4 * k
+    plain_len, ring_len = rows_plain / parts[0], rows_plain / parts[-1]
+    assert plain_len <= L and plain_len > 0.8 * L
+    assert 0.4 * L <= ring_len <= max(4 * k, L / 2)
+    # a shorter run length would not fit the budget
+    if L > 4 * k:
+        shorter = sum(-(-r // ((L - 1) // 2 if g else (L - 1))) for r, g in zip(rows, ring))
+        assert shorter > m * W
+
+
+def test_wave_run_planning_edge_cases(lib):
+    parts, L = _plan(lib, [], [])
+    assert len(parts) == 0 and L >= 1
+    parts, L = _plan(lib, [5], [0])                # a stretch shorter than 4k rows is one run
+    assert list(parts) == [1]
+    parts, L = _plan(lib, [48, 4800, 96], [0, 0, 1], warps=16, cap=640, k=8)
+    assert all(parts >= 1) and parts[1] >= parts[0]
+    with pytest.raises(fd.Fdtd2dError):
+        _plan(lib, [0], [0])
