@@ -10,6 +10,8 @@ from .build import LIB_PATH
 F32, F64 = 0, 1
 PHASE_H, PHASE_E, PHASE_SRC = 1, 2, 4
 MAX_K = 12
+PEER_BLOB_BYTES = 640
+PLAN_INFO_WORDS = 12
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -30,11 +32,18 @@ _SIGNATURES = {
     "fdtd2d_destroy": ([_vp], _i),
     "fdtd2d_set_stream": ([_vp, _vp], _i),
     "fdtd2d_reset_stream": ([_vp], _i),
+    "fdtd2d_get_stream": ([_vp, _pp], _i),
     "fdtd2d_sync": ([_vp], _i),
+    "fdtd2d_set_option": ([_vp, ctypes.c_char_p, _i], _i),
+    "fdtd2d_get_option": ([_vp, ctypes.c_char_p, _ip], _i),
     "fdtd2d_geometry": ([_vp, _ip, _ip, _ip, _ip, _ip, _ip, ctypes.POINTER(_sz)], _i),
     "fdtd2d_upload_state": ([_vp, _vp, _vp, _vp], _i),
     "fdtd2d_download_state": ([_vp, _vp, _vp, _vp], _i),
     "fdtd2d_zero_state": ([_vp], _i),
+    "fdtd2d_upload_state_async": ([_vp, _vp, _vp, _vp], _i),
+    "fdtd2d_download_state_async": ([_vp, _vp, _vp, _vp], _i),
+    "fdtd2d_copy_wait": ([_vp], _i),
+    "fdtd2d_set_materials_async": ([_vp, _vp, _vp, _d, _d], _i),
     "fdtd2d_set_coeffs": ([_vp, _vp, _vp, _vp], _i),
     "fdtd2d_set_materials": ([_vp, _vp, _vp, _d, _d], _i),
     "fdtd2d_set_mur_coef": ([_vp, _vp], _i),
@@ -50,12 +59,19 @@ _SIGNATURES = {
     "fdtd2d_step_phases": ([_vp, _i], _i),
     "fdtd2d_get_step_index": ([_vp, ctypes.POINTER(_i64)], _i),
     "fdtd2d_set_step_index": ([_vp, _i64], _i),
+    "fdtd2d_source_steps": ([_vp, _ip, _ip, ctypes.POINTER(_i64)], _i),
     "fdtd2d_set_kernel_variant": ([_vp, _i], _i),
+    "fdtd2d_plan_host": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i], _i),
+    "fdtd2d_plan_info": ([_vp, _i, _vp, _i], _i),
     "fdtd2d_launch_count": ([_vp, ctypes.POINTER(_i64)], _i),
     "fdtd2d_pass_count": ([_vp, ctypes.POINTER(_i64)], _i),
     "fdtd2d_plan_wave_runs": ([_i, _vp, _vp, _i, _i, _i, _vp, _vp], _i),
     "fdtd2d_halo_block": ([_vp, _i, _i, _pp, _pp, ctypes.POINTER(_sz)], _i),
     "fdtd2d_halo_block_next": ([_vp, _i, _i, _pp, _pp, ctypes.POINTER(_sz)], _i),
+    "fdtd2d_peer_export": ([_vp, _vp], _i),
+    "fdtd2d_peer_attach": ([_vp, _i, _vp], _i),
+    "fdtd2d_peer_detach": ([_vp], _i),
+    "fdtd2d_peer_status": ([_vp, _vp], _i),
     "fdtd2d_pass_begin": ([_vp, _i], _i),
     "fdtd2d_pass_end": ([_vp], _i),
     "fdtd2d_set_snapshot_background": ([_vp, _vp, _vp], _i),

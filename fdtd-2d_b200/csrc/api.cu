@@ -1,23 +1,29 @@
 // libfdtd2d: C-ABI implementation (include/fdtd2d.h) over the sm_100a kernels.
-// Host-side logic only: handle lifetime, padded device layout, tile planning, launches.
+// Host-side logic only: handle lifetime, padded device layout, tile / run planning, launches, the peer links of y-slabs.
 // There is no CPU compute path in this file or anywhere in the library.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
+#include <type_traits>
 #include <vector>
+
+#include <unistd.h>
 
 #include "../../include/fdtd2d.h"
 #include "common.cuh"
+#include "options.h"
 #include "tile_edge.cuh"
-#include "tile_fast.cuh"
 #include "tile_tma.cuh"
 #include "tile_generic.cuh"
 #include "grid_resident.cuh"
 #include "strip_wave.cuh"
+#include "grid_small.cuh"
 
 using namespace fdtd2d;
 
@@ -50,44 +56,43 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------
-// tile geometry of the generic kernel
+// tile geometry
 // ------------------------------------------------------------------------------------------------
-constexpr int G_TH = 36, G_TW = 128;
+constexpr int G_TH = 36, G_TW = 128;  // the shared-memory generic kernel (per-function passes, variant 1)
 // threads per generic CTA: tiles that fill most of an SM's shared memory (1 CTA/SM) get 1024 threads
 template <typename T, int TH> constexpr int generic_nt() { return 6 * TH * G_TW * sizeof(T) > 113 * 1024 ? 1024 : 512; }
-// register-resident fast kernel (fp32): MR rows per thread, NW warps -> (MR*NW) x 128 tiles.
-// Several shapes are compiled; fdtd2d_set_fast_config / FDTD2D_FAST_CFG picks one (default below).
-struct FastCfg {
-    int MR, NW;
-    bool tma;   // persistent TMA-fed kernel (tile_tma.cuh) instead of the plain-load kernel (tile_fast.cuh)
-    bool wave;  // k = 8 passes: runs of plain tiles go to the row-streaming wavefront kernel (strip_wave.cuh)
-};
-static const FastCfg kFastCfgs[] = {{4, 8, false, false},  {4, 12, false, false}, {4, 16, false, false},
-                                    {6, 8, false, false},  {8, 8, false, false},  {2, 16, false, false},
-                                    {4, 16, true, false},  {4, 16, true, false},  {4, 16, true, true}};
-constexpr int N_FAST_CFG = sizeof(kFastCfgs) / sizeof(kFastCfgs[0]);
-constexpr int DEFAULT_FAST_CFG = 8;  // k = 8 passes of large grids: wavefront strips; otherwise persistent TMA-fed 64 x 128 tiles
+// register-resident tile kernels: MR rows per thread x NW warps -> (MR * NW) x 128 tiles
+constexpr int F_MR = 4, F_NW = 16, F_TH = F_MR * F_NW;  // fp32: 64 x 128 (edge tiles, persistent TMA-fed plain tiles)
+constexpr int D_MR = 2, D_NW = 16, D_TH = D_MR * D_NW;  // fp64: 32 x 128 (edge tiles)
+constexpr int TILE_TW = 128;
 constexpr int MIN_LAST = 8;  // smallest core extent allowed for the last tile row/column (ring safety)
 
 struct TilePlan {
     int k = 0, hx = 0, CH = 0, CW = 0, tiles_y = 0, tiles_x = 0;
 };
 
-// One cached pass configuration: the tile grid for k steps and, in hybrid mode, which tiles are plain
-// (fast kernel) and which need the generic kernel (Mur ring, sources, probes, array edges).
+// One cached pass configuration for k steps: the tile grid, which tiles need the edge-capable kernel (Mur ring, sources,
+// probes, array edges, a slab's band) and how the rest is covered -- runs of the wavefront kernel or the TMA tile kernel.
 struct PassPlan {
     bool valid = false;
     TilePlan tp;
-    int n_generic = 0, n_fast = 0;
-    int n_generic_band = 0, n_fast_band = 0;  // leading entries of each list: tiles that produce halo rows / touch ghost rows
-    int* d_generic = nullptr;
+    int n_edge = 0, n_edge_band = 0;  // edge tiles; the first n_edge_band hold band rows of a slab
+    int n_fast = 0;                   // plain tiles of the TMA kernel (never band tiles)
+    int* d_edge = nullptr;
     int* d_fast = nullptr;
-    // wavefront runs built from the plain tiles: [0, n_wave_rest) avoid the band rows, [n_wave_rest, n_wave_rest + n_wave_all)
-    // cover every plain tile
-    int n_wave_rest = 0, n_wave_all = 0;
+    int n_wave = 0, n_wave_band = 0;  // wavefront runs; the first n_wave_band are band runs
     WaveTask* d_wave = nullptr;
-    bool wave_ring = false;   // both task lists start with the runs of the strips that hold the left / right Mur ring
-    int* d_ticket = nullptr;  // next run to hand out (reset before every launch)
+    bool wave_ring = false;           // the list holds runs of the strips with the left / right Mur ring
+    int band_expected[2] = {0, 0};    // band tasks (runs + edge tiles) next to the top / bottom neighbour
+    int* d_ticket = nullptr;          // next run to hand out (reset before every launch)
+};
+
+// one neighbour slab as this process sees it
+struct PeerLink {
+    bool attached = false, ipc = false;
+    void* field[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    unsigned* flags = nullptr;
+    int row0 = 0, device = -1;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -105,6 +110,7 @@ struct fdtd2d_sim {
     int cur = 0;
     bool coeffs_set = false, mur_set = false;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    Options opt;
     // sources
     int n_src = 0, n_waves = 0, amp_steps = 0;
     Cell* d_src = nullptr;
@@ -119,8 +125,7 @@ struct fdtd2d_sim {
     std::vector<int> probe_perm;  // sorted position -> caller's index
     long long step = 0, launches = 0, passes = 0;
     int variant = 0;
-    int fast_cfg = DEFAULT_FAST_CFG;
-    cudaStream_t side_stream = nullptr;  // generic (edge) tiles run here, concurrently with the fast tiles
+    cudaStream_t side_stream = nullptr;  // edge tiles run here, concurrently with the plain tiles / runs
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     PassPlan hybrid[FDTD2D_MAX_K + 1];
     std::vector<Cell> h_src, h_probe;  // host copies (sorted) for tile classification
@@ -128,17 +133,49 @@ struct fdtd2d_sim {
     int tma_box_rows = 0;              // box height the maps were encoded for (0 = not built)
     int sm_count = 0;
     int open_pass_k = 0;  // > 0 between fdtd2d_pass_begin and fdtd2d_pass_end
-    int ch_uniform = -1;      // dt/(mu*dx) the same in every cell? (-1 = not checked since the maps last changed)
-    float ch_value = 0.0f;
+    int ch_uniform = -1;  // dt/(mu*dx) the same in every cell? (-1 = not checked since the maps last changed)
+    double ch_value = 0.0;
     int* d_flag = nullptr;
-    int resident_ok = -1;     // cluster-resident kernel usable for this handle? (-1 = not decided yet)
+    int resident_ok = -1;  // cluster-resident kernel usable for this handle? (-1 = not decided yet)
     int resident_cluster = 0, resident_rpc = 0, resident_edge = 0, resident_cfg = 0;  // CTAs per grid, rows per middle / first CTA, kResCfgs index
     unsigned char* d_gray = nullptr;  // snapshot background (Rl x C per grid)
     unsigned char* d_rgb = nullptr;   // one rendered frame (Rl x C x 3)
     double* d_lut = nullptr;          // 256 x 3 colormap
+    // y-slabs: flag block (common.cuh FLAG_*), the neighbours' buffers, passes stepped with a peer attached
+    unsigned* d_slab_flags = nullptr;
+    PeerLink peer[2];
+    unsigned pass_seq = 0;
+    cudaEvent_t ev_copy = nullptr;  // fdtd2d_*_async: the last asynchronous copy
+    cudaStream_t copy_stream = nullptr;
 };
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// Restores the caller's current device when an entry point returns (a multi-GPU host process must not find its
+// device changed by a library call, least of all by a destroy that runs from a garbage collector).
+struct DeviceGuard {
+    int prev = -1, dev;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int d) : dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
+#define USE_DEVICE(s)               \
+    DeviceGuard guard_((s)->device); \
+    if (guard_.err != cudaSuccess) return fail(FDTD2D_ECUDA, "cudaSetDevice(%d) failed: %s", (s)->device, cudaGetErrorString(guard_.err))
+
+static int sm_count(fdtd2d_sim* s) {
+    if (!s->sm_count) cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+    return s->sm_count > 0 ? s->sm_count : 148;
+}
+
+static bool peer_mode(const fdtd2d_sim* s) { return s->peer[0].attached || s->peer[1].attached; }
+static int own_first(const fdtd2d_sim* s) { return s->row_begin - s->row0; }  // local row of the first owned row
+static int own_last(const fdtd2d_sim* s) { return s->row_end - s->row0; }     // one past the last owned row
 
 static int plan_axis(int extent, int core_max, int quantum, int* core, int* tiles) {
     int c = core_max;
@@ -155,15 +192,20 @@ static int plan_axis(int extent, int core_max, int quantum, int* core, int* tile
     return -1;
 }
 
-static int plan_tiles(const fdtd2d_sim* s, int k, int TH, TilePlan* tp, int col_quantum = 0) {
+// The tile grid covers the OWNED rows of the handle (all rows unless it is a slab): a slab's ghost rows are only ever
+// halo, so its first and last tile rows are as plain as any other.  cw_max > 0 caps the core width (fp64 wavefront:
+// a tile column is two strips).
+static int plan_tiles(const fdtd2d_sim* s, int k, int TH, TilePlan* tp, int col_quantum = 0, int cw_max = 0) {
     // columns are handled in groups: the 16-byte vector of the generic kernel, 4 cells per lane in the
     // register-resident kernels
     const int vn = col_quantum ? col_quantum : (int)(16 / s->esize);
     tp->k = k;
     tp->hx = (int)round_up((size_t)k, (size_t)vn);
-    if (plan_axis(s->Rl, TH - 2 * k, 1, &tp->CH, &tp->tiles_y) != 0 ||
-        plan_axis(s->C, G_TW - 2 * tp->hx, vn, &tp->CW, &tp->tiles_x) != 0)
-        return fail(FDTD2D_EINVAL, "cannot tile a %d x %d grid with k=%d", s->Rl, s->C, k);
+    int cw = TILE_TW - 2 * tp->hx;
+    if (cw_max > 0) cw = std::min(cw, cw_max);
+    if (plan_axis(own_last(s) - own_first(s), TH - 2 * k, 1, &tp->CH, &tp->tiles_y) != 0 ||
+        plan_axis(s->C, cw, vn, &tp->CW, &tp->tiles_x) != 0)
+        return fail(FDTD2D_EINVAL, "cannot tile a %d x %d grid with k=%d", own_last(s) - own_first(s), s->C, k);
     return 0;
 }
 
@@ -312,11 +354,6 @@ __global__ void snapshot_kernel(const T* ez, const unsigned char* gray, const do
 // ------------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------------
-static int use_device(const fdtd2d_sim* s) {
-    CUDA_TRY(cudaSetDevice(s->device));
-    return 0;
-}
-
 static int hy_rows(const fdtd2d_sim* s) {
     // Hy has one row fewer than Ez when the handle holds the global last row (main.py:84)
     return (s->row0 + s->Rl == s->Rg) ? s->Rl - 1 : s->Rl;
@@ -333,22 +370,6 @@ template <typename T, int TH> static int set_generic_attr(int dev) {
                                       (int)(6 * TH * G_TW * sizeof(T))));
         done = true;
     }
-    return 0;
-}
-
-static size_t fast_smem(int MR, int NW) { return (size_t)(2 * MR * NW * FAST_TW + 2 * NW * FAST_TW) * sizeof(float); }
-
-template <int MR, int NW, int MINB>
-static int launch_fast_t(fdtd2d_sim* s, const PassParams<float>& p, int n_tiles) {
-    static bool done_[MAX_DEVICES] = {};
-    bool& done = done_[s->device % MAX_DEVICES];
-    const size_t smem = fast_smem(MR, NW);
-    if (!done) {
-        CUDA_TRY(cudaFuncSetAttribute(tile_fast_kernel<MR, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        done = true;
-    }
-    tile_fast_kernel<MR, NW, MINB><<<(unsigned)n_tiles, NW * 32, smem, s->stream>>>(p);
-    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
@@ -369,7 +390,7 @@ static int encode_map(const fdtd2d_sim* s, void* base, int box_rows, CUtensorMap
     // 2-D view: inner = padded row (pitch floats), outer = all rows of all grids of the batch
     const cuuint64_t dims[2] = {(cuuint64_t)s->pitch, (cuuint64_t)s->Rl * (cuuint64_t)s->batch};
     const cuuint64_t strides[1] = {(cuuint64_t)s->pitch * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)FAST_TW, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)TILE_TW, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -394,22 +415,21 @@ static int build_tma_maps(fdtd2d_sim* s, int box_rows) {
 template <int MR, int NW, bool PAIR> static int launch_tma_t(fdtd2d_sim* s, const PassParams<float>& p, int n_tiles) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[s->device % MAX_DEVICES];
-    const size_t smem = (size_t)(5 * MR * NW * FAST_TW + (PAIR ? 4 : 2) * NW * FAST_TW) * sizeof(float);
+    const size_t smem = (size_t)(5 * MR * NW * TILE_TW + (PAIR ? 4 : 2) * NW * TILE_TW) * sizeof(float);
     if (!done) {
         CUDA_TRY(cudaFuncSetAttribute(tile_tma_kernel<MR, NW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
     }
-    if (!s->sm_count) CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
     if (int rc = build_tma_maps(s, MR * NW)) return rc;
-    const int grid = std::min(n_tiles, s->sm_count);
+    const int grid = std::min(n_tiles, sm_count(s));
     tile_tma_kernel<MR, NW, PAIR><<<grid, NW * 32, smem, s->stream>>>(s->tma_maps[s->cur], p, n_tiles);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
 // Is dt/(mu*dx) one value in every cell of the local array?  (True for every material_init output: main.py:105,121.)
-__global__ void uniform_check_kernel(const float* a, int rows, int cols, int pitch, int* differs) {
-    const float v = a[0];
+template <typename T> __global__ void uniform_check_kernel(const T* a, int rows, int cols, int pitch, int* differs) {
+    const T v = a[0];
     const long long n = (long long)rows * cols;
     int bad = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -424,70 +444,111 @@ static int check_ch_uniform(fdtd2d_sim* s) {
     if (!s->d_flag) CUDA_TRY(cudaMalloc(&s->d_flag, sizeof(int)));
     CUDA_TRY(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
     // the batch grids are back to back: rows = batch * Rl
-    uniform_check_kernel<<<148 * 8, 256, 0, s->stream>>>((const float*)s->ch, s->batch * s->Rl, s->C, (int)s->pitch, s->d_flag);
-    CUDA_TRY(cudaGetLastError());
+    const int blocks = sm_count(s) * 8;
     int differs = 1;
-    CUDA_TRY(cudaMemcpyAsync(&differs, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(&s->ch_value, s->ch, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    s->ch_uniform = differs ? 0 : 1;
-    if (const char* e = getenv("FDTD2D_NO_UNIFORM_CH"))
-        if (atoi(e)) s->ch_uniform = 0;
+    if (s->dtype == FDTD2D_F32) {
+        float v = 0.0f;
+        uniform_check_kernel<float><<<blocks, 256, 0, s->stream>>>((const float*)s->ch, s->batch * s->Rl, s->C, (int)s->pitch, s->d_flag);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(&v, s->ch, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(&differs, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        s->ch_value = v;
+    } else {
+        double v = 0.0;
+        uniform_check_kernel<double><<<blocks, 256, 0, s->stream>>>((const double*)s->ch, s->batch * s->Rl, s->C, (int)s->pitch, s->d_flag);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(&v, s->ch, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(&differs, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        s->ch_value = v;
+    }
+    s->ch_uniform = (differs || !s->opt.uniform_ch) ? 0 : 1;
     s->launches += 1;
     return 0;
 }
 
-// One instantiation of the wavefront kernel: K levels, scalar or uniform dt/(mu*dx), P rows of prefetch, X2 = packed
-// two-wide fp32 instructions (strip_wave_x2_kernel).
-template <int K, bool UCH, int P, bool X2, bool RING = false>
-static int launch_wave_t(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, int grid) {
+// ---- wavefront launches --------------------------------------------------------------------------
+// One instantiation of the packed fp32 wavefront kernel: K levels, scalar or mapped dt/(mu*dx), P rows of prefetch, with /
+// without the ring-strip and the slab-band forms of the run.
+template <int K, bool UCH, int P, bool RING, bool SLAB>
+static int launch_wave_x2_t(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, int grid) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[s->device % MAX_DEVICES];
-    const size_t smem = wave_smem_bytes(WAVE_NW, X2 && UCH);
-    const float chv = UCH ? s->ch_value : 0.0f;
-    if (X2) {
-        if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_x2_kernel<K, UCH, P, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        strip_wave_x2_kernel<K, UCH, P, RING><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, chv, 0x8000000080000000ull);
-    } else {
-        if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_kernel<K, UCH, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        strip_wave_kernel<K, UCH, P><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, chv);
-    }
+    const size_t smem = wave_smem_bytes(WAVE_NW, UCH);
+    if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_x2_kernel<K, UCH, P, RING, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = true;
+    strip_wave_x2_kernel<K, UCH, P, RING, SLAB><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, UCH ? (float)s->ch_value : 0.0f,
+                                                                                       0x8000000080000000ull);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-// FDTD2D_WAVE_X2=0 selects the scalar instantiations (FADD/FMUL) instead of the packed ones (FADD2/FFMA2)
-static bool wave_x2() {
-    const char* e = getenv("FDTD2D_WAVE_X2");
-    return e ? atoi(e) != 0 : true;
+// the scalar form, used for fp64
+template <int K, bool UCH, bool SLAB>
+static int launch_wave_f64_t(fdtd2d_sim* s, const PassParams<double>& p, const WaveTask* tasks, int n_tasks, int* ticket, int grid) {
+    static bool done_[MAX_DEVICES] = {};
+    bool& done = done_[s->device % MAX_DEVICES];
+    const size_t smem = wave_smem_bytes(WAVE_NW, UCH);
+    if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_kernel<double, K, UCH, WAVE_P, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = true;
+    strip_wave_kernel<double, K, UCH, WAVE_P, SLAB><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, UCH ? s->ch_value : 0.0);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// levels for which a wavefront instantiation exists
+static bool wave_has_k(const fdtd2d_sim* s, int k) {
+    if (s->dtype == FDTD2D_F64) return k == 4 || k == 6 || k == 8;
+    return k == 8 || (k == 12 && !s->has_top_nb && !s->has_bot_nb);  // (12 levels: whole grids with uniform permeability)
 }
 
 static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k, bool ring) {
     if (int rc = check_ch_uniform(s)) return rc;
-    if (!s->sm_count) CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
-    const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, s->sm_count);
+    const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, sm_count(s));
     CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int), s->stream));
     const bool uch = s->ch_uniform == 1;  // uniform permeability: the map is not read at all (28 instead of 32 B per cell and pass)
-    const bool x2 = wave_x2();
+    const bool slab = s->has_top_nb || s->has_bot_nb;
     if (k == 12) {  // (runs for k = 12 are only built when the permeability is uniform)
-        if (!uch) return fail(FDTD2D_EINVAL, "the 12-level wavefront kernel needs uniform permeability");
-        return x2 ? launch_wave_t<12, true, 2, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<12, true, 2, false>(s, p, tasks, n_tasks, ticket, grid);
+        if (!uch || slab) return fail(FDTD2D_EINVAL, "the 12-level wavefront kernel needs uniform permeability and a whole grid");
+        return launch_wave_x2_t<12, true, 2, false, false>(s, p, tasks, n_tasks, ticket, grid);
     }
-    if (k == 10) {
-        if (!uch) return fail(FDTD2D_EINVAL, "the 10-level wavefront kernel needs uniform permeability");
-        return launch_wave_t<10, true, WAVE_P, true>(s, p, tasks, n_tasks, ticket, grid);
+    if (k != 8) return fail(FDTD2D_EINVAL, "no fp32 wavefront kernel for k=%d", k);
+    const int sel = (uch ? 4 : 0) | (ring ? 2 : 0) | (slab ? 1 : 0);
+    switch (sel) {
+        case 0: return launch_wave_x2_t<8, false, WAVE_P, false, false>(s, p, tasks, n_tasks, ticket, grid);
+        case 1: return launch_wave_x2_t<8, false, WAVE_P, false, true>(s, p, tasks, n_tasks, ticket, grid);
+        case 2: return launch_wave_x2_t<8, false, WAVE_P, true, false>(s, p, tasks, n_tasks, ticket, grid);
+        case 3: return launch_wave_x2_t<8, false, WAVE_P, true, true>(s, p, tasks, n_tasks, ticket, grid);
+        case 4: return launch_wave_x2_t<8, true, WAVE_P, false, false>(s, p, tasks, n_tasks, ticket, grid);
+        case 5: return launch_wave_x2_t<8, true, WAVE_P, false, true>(s, p, tasks, n_tasks, ticket, grid);
+        case 6: return launch_wave_x2_t<8, true, WAVE_P, true, false>(s, p, tasks, n_tasks, ticket, grid);
+        default: return launch_wave_x2_t<8, true, WAVE_P, true, true>(s, p, tasks, n_tasks, ticket, grid);
     }
-    if (ring)  // the task list starts with ring-strip runs (built only for k = 8 with the packed kernel)
-        return uch ? launch_wave_t<8, true, WAVE_P, true, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<8, false, WAVE_P, true, true>(s, p, tasks, n_tasks, ticket, grid);
-    if (uch) return x2 ? launch_wave_t<8, true, WAVE_P, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<8, true, WAVE_P, false>(s, p, tasks, n_tasks, ticket, grid);
-    return x2 ? launch_wave_t<8, false, WAVE_P, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_t<8, false, WAVE_P, false>(s, p, tasks, n_tasks, ticket, grid);
+}
+
+template <int K> static int launch_wave_f64_k(fdtd2d_sim* s, const PassParams<double>& p, const WaveTask* tasks, int n_tasks, int* ticket, int grid) {
+    const bool uch = s->ch_uniform == 1, slab = s->has_top_nb || s->has_bot_nb;
+    if (uch) return slab ? launch_wave_f64_t<K, true, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_f64_t<K, true, false>(s, p, tasks, n_tasks, ticket, grid);
+    return slab ? launch_wave_f64_t<K, false, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_f64_t<K, false, false>(s, p, tasks, n_tasks, ticket, grid);
+}
+
+static int launch_wave(fdtd2d_sim* s, const PassParams<double>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k, bool) {
+    if (int rc = check_ch_uniform(s)) return rc;
+    const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, sm_count(s));
+    CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int), s->stream));
+    switch (k) {
+        case 4: return launch_wave_f64_k<4>(s, p, tasks, n_tasks, ticket, grid);
+        case 6: return launch_wave_f64_k<6>(s, p, tasks, n_tasks, ticket, grid);
+        case 8: return launch_wave_f64_k<8>(s, p, tasks, n_tasks, ticket, grid);
+        default: return fail(FDTD2D_EINVAL, "no fp64 wavefront kernel for k=%d", k);
+    }
 }
 
 template <typename T, int MR, int NW> static int launch_edge_tt(int dev, const PassParams<T>& p, int n_tiles, cudaStream_t st) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[dev % MAX_DEVICES];
-    const size_t smem = (size_t)(2 * MR * NW * FAST_TW + 2 * NW * FAST_TW) * sizeof(T);
+    const size_t smem = (size_t)(2 * MR * NW * TILE_TW + 2 * NW * TILE_TW) * sizeof(T);
     if (!done) {
         CUDA_TRY(cudaFuncSetAttribute(tile_edge_kernel<T, MR, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
@@ -496,10 +557,8 @@ template <typename T, int MR, int NW> static int launch_edge_tt(int dev, const P
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-
-template <int MR, int NW> static int launch_edge_t(int dev, const PassParams<float>& p, int n_tiles, cudaStream_t st) {
-    return launch_edge_tt<float, MR, NW>(dev, p, n_tiles, st);
-}
+static int launch_edge(int dev, const PassParams<float>& p, int n, cudaStream_t st) { return launch_edge_tt<float, F_MR, F_NW>(dev, p, n, st); }
+static int launch_edge(int dev, const PassParams<double>& p, int n, cudaStream_t st) { return launch_edge_tt<double, D_MR, D_NW>(dev, p, n, st); }
 
 template <int TH> static int launch_generic_list_t(int dev, const PassParams<float>& p, int n_tiles, cudaStream_t st) {
     if (int rc = set_generic_attr<float, TH>(dev)) return rc;
@@ -509,7 +568,7 @@ template <int TH> static int launch_generic_list_t(int dev, const PassParams<flo
     return 0;
 }
 
-template <typename T> static void fill_params(const fdtd2d_sim* s, const TilePlan& tp, int phases, PassParams<T>* pp) {
+template <typename T> static void fill_params(const fdtd2d_sim* s, const TilePlan& tp, int phases, PassParams<T>* pp, const PassPlan* pl = nullptr) {
     PassParams<T>& p = *pp;
     memset(&p, 0, sizeof p);
     for (int f = 0; f < 3; ++f) {
@@ -545,24 +604,30 @@ template <typename T> static void fill_params(const fdtd2d_sim* s, const TilePla
     p.n_probe = s->n_probe;
     p.trace = static_cast<T*>(s->d_trace);
     p.trace_cap = s->trace_cap;
+    // y-slabs: the tile grid starts at the first owned row; band rows; the neighbours' buffers
+    p.org = own_first(s);
+    p.store_lo = own_first(s);
+    p.store_hi = own_last(s);
+    p.band_lo[0] = own_first(s);
+    p.band_hi[0] = own_first(s) + (s->has_top_nb ? s->halo : 0);
+    p.band_lo[1] = own_last(s) - (s->has_bot_nb ? s->halo : 0);
+    p.band_hi[1] = own_last(s);
+    p.flags = s->d_slab_flags;
+    p.seq = s->pass_seq;
+    for (int side = 0; side < 2; ++side) {
+        const PeerLink& pe = s->peer[side];
+        if (!pe.attached) continue;
+        for (int f = 0; f < 3; ++f) p.peer_out[side][f] = static_cast<T*>(pe.field[s->cur ^ 1][f]);
+        p.peer_shift[side] = (long long)(s->row0 - pe.row0) * (long long)s->pitch;
+        // I am the bottom neighbour of the slab above me and the top neighbour of the slab below me
+        p.peer_flag[side] = pe.flags + (side == 0 ? FLAG_IN_BOT : FLAG_IN_TOP);
+        p.band_expected[side] = pl ? pl->band_expected[side] : 0;
+    }
 }
 
-// fp64: every tile on the register-resident edge-capable kernel (2 rows x 4 columns per thread, 32 x 128 tiles)
-constexpr int D_MR = 2, D_NW = 16;
-static int launch_edge_all_f64(fdtd2d_sim* s, int k) {
-    TilePlan tp;
-    if (int rc = plan_tiles(s, k, D_MR * D_NW, &tp, 4)) return rc;
-    PassParams<double> p;
-    fill_params(s, tp, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC, &p);
-    const long long n_tiles = (long long)s->batch * tp.tiles_y * tp.tiles_x;
-    if (n_tiles > 0x7fffffffLL) return fail(FDTD2D_EINVAL, "too many tiles");
-    if (int rc = launch_edge_tt<double, D_MR, D_NW>(s->device, p, (int)n_tiles, s->stream)) return rc;
-    s->launches += 1;
-    return 0;
-}
-
-// Generic kernel over the whole tile grid (fp64, per-function passes, variant 1).
+// Generic kernel over the whole tile grid (per-function passes, variant 1).
 template <typename T> static int launch_generic_all(fdtd2d_sim* s, int k, int phases) {
+    if (peer_mode(s)) return fail(FDTD2D_EINVAL, "the generic kernel (variant 1 / single phases) does not take part in the peer halo exchange");
     TilePlan tp;
     if (int rc = plan_tiles(s, k, G_TH, &tp)) return rc;
     PassParams<T> p;
@@ -581,15 +646,13 @@ template <typename T> static int launch_generic_all(fdtd2d_sim* s, int k, int ph
 static void free_plans(fdtd2d_sim* s) {
     s->resident_ok = -1;
     for (PassPlan& pl : s->hybrid) {
-        cudaFree(pl.d_generic);
+        cudaFree(pl.d_edge);
         cudaFree(pl.d_fast);
         cudaFree(pl.d_wave);
         cudaFree(pl.d_ticket);
         pl = PassPlan();
     }
 }
-
-static int check_ch_uniform(fdtd2d_sim* s);
 
 // Run lengths of the wavefront kernel (host only, no CUDA; exported as fdtd2d_plan_wave_runs for the CPU tests).
 // rows[i] is the height of stretch i (a vertical sequence of plain tiles of one strip), ring[i] != 0 marks a ring strip,
@@ -619,23 +682,58 @@ static int plan_wave_runs(const std::vector<int>& rows, const std::vector<unsign
     return lo;
 }
 
-// Split the TH x 128 tile grid into plain tiles (fast kernel) and the rest (generic kernel).
-static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
+// Classify the tile grid of a k-step pass and build its task lists (cached per k until sources, probes, materials or
+// options change).
+//   * The tile grid (TH x 128 windows, core CH x CW) covers the owned rows.  A tile is PLAIN when nothing but interior
+//     cells is within k cells of its core: no Mur ring, no array edge, no source in its window, no probe in its core.
+//   * Wavefront mode (a k with a wavefront instantiation, enough plain tiles): vertical stretches of plain tiles become
+//     runs of rows; the first / last tile column may ride along as ring strips; a slab's band rows are cut out as runs of
+//     their own and put first.  Everything else is an edge tile.
+//   * Tile mode: plain tiles whose whole window lies inside the local array and that hold no band row go to the
+//     persistent TMA kernel (fp32), the rest to the edge kernel.
+struct PlanLists {
+    TilePlan tp;
+    std::vector<unsigned char> kind;  // per tile: 0 edge, 1 wavefront (plain), 2 wavefront (ring strip), 3 TMA tile kernel
+    std::vector<int> edge, fast;      // edge tiles (band tiles first), TMA tiles
+    int n_edge_band = 0;
+    std::vector<WaveTask> tasks;      // band runs first
+    int n_wave_band = 0;
+    bool wave_ring = false;
+    int band_expected[2] = {0, 0};
+};
+
+// The planning itself: host arithmetic only (s->sm_count and s->ch_uniform are read as they are), so that the CPU
+// tests can check it for every geometry (fdtd2d_plan_host).
+static int plan_pass(const fdtd2d_sim* s, int k, PlanLists* pl) {
+    const bool f64 = s->dtype == FDTD2D_F64;
+    const int TH = f64 ? D_TH : F_TH;
+    const bool wave_k = s->opt.wavefront && wave_has_k(s, k) && s->variant != 3;
+    // fp64 strips are 64 columns wide (two columns per lane): a tile column is cut into two strips
+    const int hxw = (int)round_up((size_t)k, 2), strip_core_max = 64 - 2 * hxw;
     TilePlan& tp = pl->tp;
-    const int F_TH = kFastCfgs[s->fast_cfg].MR * kFastCfgs[s->fast_cfg].NW;
-    if (int rc = plan_tiles(s, k, F_TH, &tp, 4)) return rc;
+    pl->wave_ring = false, pl->n_wave_band = 0, pl->n_edge_band = 0;
+    if (int rc = plan_tiles(s, k, TH, &tp, 4, (f64 && wave_k) ? 2 * strip_core_max : 0)) return rc;
     const int per_grid = tp.tiles_y * tp.tiles_x;
     const long long n_tiles = (long long)s->batch * per_grid;
     if (n_tiles > 0x7fffffffLL) return fail(FDTD2D_EINVAL, "too many tiles");
+    const int org = own_first(s), own_hi = own_last(s);
+    const bool slab = s->has_top_nb || s->has_bot_nb;
+    const int band_lo[2] = {org, own_hi - (s->has_bot_nb ? s->halo : 0)};
+    const int band_hi[2] = {org + (s->has_top_nb ? s->halo : 0), own_hi};
+    auto row_lo = [&](int ty) { return org + ty * tp.CH; };
+    auto row_hi = [&](int ty) { return std::min(org + (ty + 1) * tp.CH, own_hi); };
+    auto tile_band = [&](int ty, int side) { return row_lo(ty) < band_hi[side] && row_hi(ty) > band_lo[side]; };
+
     std::vector<unsigned char> special((size_t)n_tiles, 0);
-    auto mark = [&](int b, int lrow, int col, int row_pad_lo, int row_pad_hi, int col_pad_lo, int col_pad_hi) {
-        // tiles whose window [t*CH - pad_lo, t*CH + CH + pad_hi) contains the cell
-        const int ty_lo = std::max(0, (lrow - tp.CH - row_pad_hi + 1 + tp.CH - 1) / tp.CH - 1);
-        const int tx_lo = std::max(0, (col - tp.CW - col_pad_hi + 1 + tp.CW - 1) / tp.CW - 1);
+    auto mark = [&](int b, int trow, int col, int row_pad_lo, int row_pad_hi, int col_pad_lo, int col_pad_hi) {
+        // trow = row relative to the tile grid's origin; marks the tiles whose window
+        // [t*CH - pad_lo, t*CH + CH + pad_hi) x [t*CW - pad_lo, ...) contains the cell
+        const int ty_lo = std::max(0, (trow - row_pad_hi) / tp.CH - 1);
+        const int tx_lo = std::max(0, (col - col_pad_hi) / tp.CW - 1);
         for (int ty = ty_lo; ty < tp.tiles_y; ++ty) {
             const int r0 = ty * tp.CH - row_pad_lo, r1 = ty * tp.CH + tp.CH + row_pad_hi;
-            if (lrow < r0) break;
-            if (lrow >= r1) continue;
+            if (trow < r0) break;
+            if (trow >= r1) continue;
             for (int tx = tx_lo; tx < tp.tiles_x; ++tx) {
                 const int c0 = tx * tp.CW - col_pad_lo, c1 = tx * tp.CW + tp.CW + col_pad_hi;
                 if (col < c0) break;
@@ -646,203 +744,245 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
     };
     // a source anywhere in the haloed tile; a probe in the core
     for (const Cell& c : s->h_src)
-        mark(c.grid, c.row - s->row0, c.col, k, F_TH - k - tp.CH, tp.hx, FAST_TW - tp.hx - tp.CW);
-    for (const Cell& c : s->h_probe) mark(c.grid, c.row - s->row0, c.col, 0, 0, 0, 0);
-    // slab handles: tile rows whose core holds rows that are sent to a neighbour, or ghost rows, form the
-    // "band" that fdtd2d_pass_begin launches first so the halo exchange can overlap the rest of the pass
-    const int own_first = s->row_begin - s->row0, own_last = s->row_end - s->row0;
-    auto in_band = [&](int ty) {
-        const int r0 = ty * tp.CH, r1 = std::min(s->Rl, r0 + tp.CH);
-        if (s->has_top_nb && r0 < own_first + s->halo) return true;
-        if (s->has_bot_nb && r1 > own_last - s->halo) return true;
-        return false;
-    };
-    // Ring strips: tiles of the first / last tile column whose ROWS are plain go to the ring instantiation of the
-    // wavefront kernel (8 levels, packed) when the plain tiles do; the band tiles of a slab stay on the tile kernels.
-    // The right strip is the last 128 columns of the padded row, so a source / probe must be re-checked against it.
-    const bool lr_ok = kFastCfgs[s->fast_cfg].wave && k == 8 && wave_x2() && s->C >= 4 * FAST_TW && !getenv("FDTD2D_NO_RING_STRIPS");
-    const int lr_x0[2] = {0, (s->C + 3) / 4 * 4 - FAST_TW};
+        mark(c.grid, c.row - s->row0 - org, c.col, k, std::max(k, TH - k - tp.CH), tp.hx, TILE_TW - tp.hx - tp.CW);
+    for (const Cell& c : s->h_probe) mark(c.grid, c.row - s->row0 - org, c.col, 0, 0, 0, 0);
+
+    // Ring strips: the first / last 128 columns of the padded row.  A source / probe must be re-checked against them
+    // (the right strip is not aligned with the tile grid).
+    const bool lr_ok = wave_k && !f64 && k == 8 && s->opt.ring_strips && s->C >= 4 * TILE_TW;
+    const int lr_x0[2] = {0, (s->C + 3) / 4 * 4 - TILE_TW};
     std::vector<unsigned char> lr_special((size_t)n_tiles, 0);
     if (lr_ok) {
-        auto mark_lr = [&](const Cell& c, int row_pad_lo, int row_pad_hi) {
+        auto mark_lr = [&](const Cell& c, int row_pad) {
             for (int side = 0; side < 2; ++side) {
-                if (c.col < lr_x0[side] || c.col >= lr_x0[side] + FAST_TW) continue;
+                if (c.col < lr_x0[side] || c.col >= lr_x0[side] + TILE_TW) continue;
                 const int tx = side ? tp.tiles_x - 1 : 0, lrow = c.row - s->row0;
                 for (int ty = 0; ty < tp.tiles_y; ++ty)
-                    if (lrow >= ty * tp.CH - row_pad_lo && lrow < ty * tp.CH + tp.CH + row_pad_hi)
+                    if (lrow >= row_lo(ty) - row_pad && lrow < row_hi(ty) + row_pad)
                         lr_special[(size_t)c.grid * per_grid + (size_t)ty * tp.tiles_x + tx] = 1;
             }
         };
-        for (const Cell& c : s->h_src) mark_lr(c, k, k);
-        for (const Cell& c : s->h_probe) mark_lr(c, 0, 0);
+        for (const Cell& c : s->h_src) mark_lr(c, k);
+        for (const Cell& c : s->h_probe) mark_lr(c, 0);
     }
-    std::vector<int> gen, fast, gen_rest, fast_rest, lr_tiles;
+
+    // per tile row: are its rows plain for the wavefront (rows [lo - k, hi + k) exist and hold no top / bottom ring) and
+    // for the tile kernels (the whole TH-row window as well, and a full core)?
+    std::vector<unsigned char> rows_wave(tp.tiles_y), rows_tile(tp.tiles_y);
+    for (int ty = 0; ty < tp.tiles_y; ++ty) {
+        const int lo = row_lo(ty) - k, hi = row_hi(ty) + k, whi = row_lo(ty) - k + TH;
+        rows_wave[ty] = lo >= 0 && hi <= s->Rl && lo + s->row0 >= RING && hi + s->row0 <= s->Rg - RING;
+        rows_tile[ty] = rows_wave[ty] && row_hi(ty) - row_lo(ty) == tp.CH && whi <= s->Rl && whi + s->row0 <= s->Rg - RING;
+    }
+    auto cols_plain = [&](int tx) {
+        const int lc0 = tx * tp.CW - tp.hx;
+        return lc0 >= RING && lc0 + TILE_TW <= s->C - RING;
+    };
+    // wavefront mode?  Small grids: one run per warp gets too short against its 2k warm-up rows, and the persistent tile
+    // kernel wins.  Measured on B200 with balanced runs (profiles/): 3000^2 696 vs 593, 2048^2 548 vs 491, 1536^2 364 vs
+    // 390 Gcell/s (wavefront vs tiles) -> the wavefront takes over from ~0.4 plain fp32 tiles (48 x 112 cells) per warp
+    long long n_plain_cells = 0;
+    if (wave_k)
+        for (int b = 0; b < s->batch; ++b)
+            for (int ty = 0; ty < tp.tiles_y; ++ty)
+                for (int tx = 0; tx < tp.tiles_x; ++tx)
+                    if (rows_wave[ty] && cols_plain(tx) && !special[(size_t)b * per_grid + ty * tp.tiles_x + tx])
+                        n_plain_cells += (long long)(row_hi(ty) - row_lo(ty)) * tp.CW;
+    const long long warps = (long long)std::max(1, s->sm_count) * WAVE_NW, tile_cells = 48 * 112;
+    const long long min_tiles = s->opt.wave_min_tiles >= 0 ? s->opt.wave_min_tiles : 2 * warps / 5;
+    const long long ring_min_tiles = s->opt.ring_min_tiles >= 0 ? s->opt.ring_min_tiles : 2 * warps;
+    bool use_wave = wave_k && n_plain_cells > 0 && n_plain_cells >= min_tiles * tile_cells;
+    if (k == 12 && s->ch_uniform != 1) use_wave = false;  // (12 levels exist for uniform permeability only)
+    // (on small grids the ring strips do not pay: 2048^2 539 with, 590 Gcell/s without)
+    const bool use_lr = use_wave && lr_ok && n_plain_cells >= ring_min_tiles * tile_cells;
+
+    // kind of every tile: 0 edge, 1 wavefront (plain), 2 wavefront (ring strip), 3 TMA tile kernel
+    std::vector<unsigned char>& kind = pl->kind;
+    kind.assign((size_t)n_tiles, 0);
+    std::vector<int> edge_band, edge_rest;
+    std::vector<int>& fast = pl->fast;
+    fast.clear();
+    pl->band_expected[0] = pl->band_expected[1] = 0;
     for (int b = 0; b < s->batch; ++b)
-        for (int ty = 0; ty < tp.tiles_y; ++ty) {
-            const int lr0 = ty * tp.CH - k, gr0 = lr0 + s->row0;
-            const bool rows_plain = lr0 >= 0 && lr0 + F_TH <= s->Rl && gr0 >= RING && gr0 + F_TH <= s->Rg - RING;
-            const bool band = in_band(ty);
+        for (int ty = 0; ty < tp.tiles_y; ++ty)
             for (int tx = 0; tx < tp.tiles_x; ++tx) {
-                const int lc0 = tx * tp.CW - tp.hx;
-                const bool cols_plain = lc0 >= RING && lc0 + FAST_TW <= s->C - RING;
                 const int id = b * per_grid + ty * tp.tiles_x + tx;
-                const bool plain = rows_plain && cols_plain && !special[id];
-                if (lr_ok && !plain && !band && rows_plain && !special[id] && !lr_special[id] && (tx == 0 || tx == tp.tiles_x - 1))
-                    lr_tiles.push_back(id);  // decided below: ring strip or edge tile
-                else
-                    (plain ? (band ? fast : fast_rest) : (band ? gen : gen_rest)).push_back(id);
+                const bool band = tile_band(ty, 0) || tile_band(ty, 1);
+                int kd = 0;
+                if (!special[id]) {
+                    if (cols_plain(tx)) {
+                        if (use_wave && rows_wave[ty]) kd = 1;
+                        else if (!use_wave && !f64 && rows_tile[ty] && !band && s->variant != 1) kd = 3;
+                    } else if (use_lr && rows_wave[ty] && !lr_special[id] && (tx == 0 || tx == tp.tiles_x - 1)) {
+                        kd = 2;
+                    }
+                }
+                kind[id] = (unsigned char)kd;
+                if (kd == 0) {
+                    (band ? edge_band : edge_rest).push_back(id);
+                    for (int side = 0; side < 2; ++side) pl->band_expected[side] += tile_band(ty, side) ? 1 : 0;
+                } else if (kd == 3) {
+                    fast.push_back(id);
+                }
             }
-        }
-    // the wavefront kernel exists for k = 8 and, with uniform permeability, for k = 12
-    bool wave_k = kFastCfgs[s->fast_cfg].wave && (k == 8 || k == 10 || k == 12);
-    if (wave_k && k > 8) {
-        if (int rc = check_ch_uniform(s)) return rc;
-        wave_k = s->ch_uniform == 1;
-    }
-    if (wave_k) {
-        // Vertical stretches of plain tiles of one tile column are cut into RUNS of rows, one wavefront task each.  A run
-        // costs 2k warm-up rows, and the GPU has W = SMs x 8 independent warps: the cut is chosen so that there are (at
-        // most) m x W runs of nearly the same length -- every warp gets m of them -- with m as small as a cap of
-        // ~WAVE_RUN_ROWS rows per run allows.  (With runs of whole tiles a 4096^2 grid gave 720 runs to 1184 warps.)
-        if (!s->sm_count) CUDA_TRY(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
-        const long long n_plain = (long long)fast.size() + (long long)fast_rest.size();
-        std::vector<unsigned char> is_plain((size_t)n_tiles, 0), is_band((size_t)n_tiles, 0);
-        for (int id : fast) is_plain[id] = 1, is_band[id] = 1;
-        for (int id : fast_rest) is_plain[id] = 1;
-        long long run_rows = 640;
-        if (const char* e = getenv("FDTD2D_WAVE_RUN_ROWS")) run_rows = std::max(1, atoi(e));
-        // small grids: one run per warp gets too short against its 2k warm-up rows, and the persistent tile kernel wins.
-        // Measured on B200 with balanced runs (profiles/): 3000^2 696 vs 593, 2048^2 548 vs 491, 1536^2 364 vs 390 Gcell/s
-        // (wavefront vs tiles) -> the wavefront takes over from ~0.4 plain tiles per warp of the GPU
-        long long min_tiles = 2LL * s->sm_count * WAVE_NW / 5;
-        if (const char* e = getenv("FDTD2D_WAVE_MIN_TILES")) min_tiles = std::max(0, atoi(e));
-        const bool use_wave = n_plain >= min_tiles && n_plain > 0;
-        // stretches of ring-strip tiles (first / last tile column): a row of them costs about twice a plain row, so they
-        // are cut to half the run length, counted in the same budget of runs and handed out first
-        std::vector<WaveTask> lr_segs;
-        // (on small grids the ring strips do not pay: 2048^2 539 with, 590 Gcell/s without)
-        long long ring_min_tiles = 2LL * s->sm_count * WAVE_NW;
-        if (const char* e = getenv("FDTD2D_RING_MIN_TILES")) ring_min_tiles = std::max(0, atoi(e));
-        if (use_wave && !lr_tiles.empty() && n_plain >= ring_min_tiles) {
-            std::vector<unsigned char> is_lr((size_t)n_tiles, 0);
-            for (int id : lr_tiles) is_lr[id] = 1;
-            for (int b = 0; b < s->batch; ++b)
-                for (int side = 0; side < 2; ++side) {
-                    const int tx = side ? tp.tiles_x - 1 : 0;
-                    if (side && tp.tiles_x == 1) continue;
-                    int run = 0;
-                    for (int ty = 0; ty <= tp.tiles_y; ++ty) {
-                        const bool ok = ty < tp.tiles_y && is_lr[b * per_grid + ty * tp.tiles_x + tx];
-                        if (ok) {
-                            ++run;
-                            continue;
-                        }
-                        if (run) {
+
+    std::vector<WaveTask>& tasks = pl->tasks;
+    tasks.clear();
+    if (use_wave) {
+        // stretches: maximal vertical sequences of tiles of one kind in one tile column, in rows; a slab's band rows are
+        // cut out of them as tasks of their own
+        std::vector<WaveTask> segs, band_tasks;
+        auto add_stretch = [&](WaveTask t) {
+            int cuts[4], nc = 0;
+            cuts[nc++] = t.y0;
+            for (int side = 0; side < 2; ++side) {
+                const int c = side == 0 ? band_hi[0] : band_lo[1];
+                if (band_hi[side] > band_lo[side] && c > cuts[nc - 1] && c < t.y1) cuts[nc++] = c;
+            }
+            cuts[nc++] = t.y1;
+            for (int i = 0; i + 1 < nc; ++i) {
+                WaveTask q = t;
+                q.y0 = cuts[i], q.y1 = cuts[i + 1];
+                q.band = 0;
+                for (int side = 0; side < 2; ++side)
+                    if (band_hi[side] > band_lo[side] && q.y0 >= band_lo[side] && q.y1 <= band_hi[side]) q.band = side + 1;
+                (q.band ? band_tasks : segs).push_back(q);
+            }
+        };
+        const int strips = f64 ? 2 : 1, sw = tp.CW / strips;  // strips per tile column, their core width
+        for (int b = 0; b < s->batch; ++b)
+            for (int tx = 0; tx < tp.tiles_x; ++tx) {
+                int run = 0, run_kind = 0;
+                for (int ty = 0; ty <= tp.tiles_y; ++ty) {
+                    const int kd = ty < tp.tiles_y ? kind[b * per_grid + ty * tp.tiles_x + tx] : 0;
+                    const bool wavey = kd == 1 || kd == 2;
+                    if (wavey && (run == 0 || kd == run_kind)) {
+                        ++run, run_kind = kd;
+                        continue;
+                    }
+                    if (run) {
+                        const int y0 = row_lo(ty - run), y1 = row_hi(ty - 1);
+                        if (run_kind == 1) {
+                            for (int q = 0; q < strips; ++q) {
+                                WaveTask t;
+                                t.b = b, t.y0 = y0, t.y1 = y1, t.side = 0, t.band = 0;
+                                if (f64) {
+                                    t.x0 = tx * tp.CW + q * sw - hxw, t.c0 = hxw, t.c1 = hxw + sw;
+                                } else {
+                                    t.x0 = tx * tp.CW - tp.hx, t.c0 = tp.hx, t.c1 = tp.hx + tp.CW;
+                                }
+                                add_stretch(t);
+                            }
+                        } else {
+                            const int side = tx == 0 ? 0 : 1;
                             WaveTask t;
-                            t.b = b, t.x0 = lr_x0[side], t.side = side + 1, t.pad = 0;
-                            t.y0 = (ty - run) * tp.CH, t.y1 = ty * tp.CH;
+                            t.b = b, t.y0 = y0, t.y1 = y1, t.side = side + 1, t.band = 0, t.x0 = lr_x0[side];
                             // stored columns: the tile's core, in strip coordinates (whole 16-byte groups; the last group
                             // may reach into the pad columns, which keep their zeros)
                             t.c0 = side ? tx * tp.CW - t.x0 : 0;
-                            t.c1 = side ? FAST_TW : tp.CW;
-                            lr_segs.push_back(t);
+                            t.c1 = side ? TILE_TW : tp.CW;
+                            add_stretch(t);
+                            pl->wave_ring = true;
                         }
-                        run = 0;
                     }
-                }
-            lr_tiles.clear();
-            pl->wave_ring = true;
-        }
-        std::vector<WaveTask> tasks;
-        for (int pass = 0; use_wave && pass < 2; ++pass) {  // pass 0: plain tiles outside the band; pass 1: all plain tiles
-            std::vector<WaveTask> segs = lr_segs;  // maximal stretches, in rows
-            for (int b = 0; b < s->batch; ++b)
-                for (int tx = 0; tx < tp.tiles_x; ++tx) {
-                    int run = 0;
-                    for (int ty = 0; ty <= tp.tiles_y; ++ty) {
-                        const int id = b * per_grid + ty * tp.tiles_x + tx;
-                        const bool ok = ty < tp.tiles_y && is_plain[id] && (pass == 1 || !is_band[id]);
-                        if (ok) {
-                            ++run;
-                            continue;
-                        }
-                        if (run) {
-                            WaveTask t;
-                            t.b = b, t.x0 = tx * tp.CW - tp.hx, t.y0 = (ty - run) * tp.CH, t.y1 = ty * tp.CH;
-                            t.c0 = tp.hx, t.c1 = tp.hx + tp.CW, t.side = 0, t.pad = 0;
-                            segs.push_back(t);
-                        }
-                        run = 0;
-                    }
-                }
-            std::vector<int> seg_rows(segs.size()), parts;
-            std::vector<unsigned char> seg_ring(segs.size());
-            for (size_t i = 0; i < segs.size(); ++i) seg_rows[i] = segs[i].y1 - segs[i].y0, seg_ring[i] = segs[i].side != 0;
-            plan_wave_runs(seg_rows, seg_ring, (long long)s->sm_count * WAVE_NW, run_rows, k, &parts);
-            for (size_t i = 0; i < segs.size(); ++i) {
-                const WaveTask& g = segs[i];
-                const int rows = seg_rows[i];
-                for (int q = 0; q < parts[i]; ++q) {
-                    WaveTask t = g;
-                    t.y0 = g.y0 + (int)((long long)rows * q / parts[i]), t.y1 = g.y0 + (int)((long long)rows * (q + 1) / parts[i]);
-                    tasks.push_back(t);
+                    run = wavey ? 1 : 0, run_kind = kd;
                 }
             }
-            // ring-strip runs first; then row band by row band: warps that work at the same time then hold neighbouring
-            // strips of the same rows, so the 8 halo columns they share are read from DRAM once and from L2 the second time
-            std::stable_sort(tasks.begin() + (pass == 0 ? 0 : pl->n_wave_rest), tasks.end(), [](const WaveTask& a, const WaveTask& b) {
-                if ((a.side != 0) != (b.side != 0)) return a.side != 0;
-                if (a.b != b.b) return a.b < b.b;
-                if (a.y0 != b.y0) return a.y0 < b.y0;
-                return a.x0 < b.x0;
-            });
-            (pass == 0 ? pl->n_wave_rest : pl->n_wave_all) = (int)tasks.size() - (pass == 0 ? 0 : pl->n_wave_rest);
+        // Non-band stretches are cut into RUNS of rows, one wavefront task each.  A run costs 2k warm-up rows, and the GPU
+        // has W = SMs x 8 independent warps: the cut is chosen so that there are (at most) m x W runs of nearly the same
+        // length -- every warp gets m of them -- with m as small as a cap of ~wave_run_rows rows per run allows.  (With
+        // runs of whole tiles a 4096^2 grid gave 720 runs to 1184 warps.)
+        std::vector<int> seg_rows(segs.size()), parts;
+        std::vector<unsigned char> seg_ring(segs.size());
+        for (size_t i = 0; i < segs.size(); ++i) seg_rows[i] = segs[i].y1 - segs[i].y0, seg_ring[i] = segs[i].side != 0;
+        plan_wave_runs(seg_rows, seg_ring, warps, std::max(1, s->opt.wave_run_rows), k, &parts);
+        for (size_t i = 0; i < segs.size(); ++i) {
+            const WaveTask& g = segs[i];
+            const int rows = seg_rows[i];
+            for (int q = 0; q < parts[i]; ++q) {
+                WaveTask t = g;
+                t.y0 = g.y0 + (int)((long long)rows * q / parts[i]), t.y1 = g.y0 + (int)((long long)rows * (q + 1) / parts[i]);
+                tasks.push_back(t);
+            }
         }
-        if (!tasks.empty()) {
-            CUDA_TRY(cudaMalloc(&pl->d_ticket, sizeof(int)));
-            CUDA_TRY(cudaMalloc(&pl->d_wave, sizeof(WaveTask) * tasks.size()));
-            // on the handle's own stream: a plain cudaMemcpy goes through the legacy default stream, which a non-blocking
-            // stream does not wait for -- with another handle keeping the GPU busy the kernel could read the list before it
-            // had landed (seen as an illegal address with two handles in two host threads)
-            CUDA_TRY(cudaMemcpyAsync(pl->d_wave, tasks.data(), sizeof(WaveTask) * tasks.size(), cudaMemcpyHostToDevice, s->stream));
-            CUDA_TRY(cudaStreamSynchronize(s->stream));  // `tasks` dies with this block
-        }
+        // ring-strip runs first (they are the heavier ones); then row band by row band: warps that work at the same time
+        // then hold neighbouring strips of the same rows, so the halo columns they share are read from DRAM once and from
+        // L2 the second time
+        auto order = [](const WaveTask& a, const WaveTask& b) {
+            if ((a.side != 0) != (b.side != 0)) return a.side != 0;
+            if (a.b != b.b) return a.b < b.b;
+            if (a.y0 != b.y0) return a.y0 < b.y0;
+            return a.x0 < b.x0;
+        };
+        std::stable_sort(tasks.begin(), tasks.end(), order);
+        std::stable_sort(band_tasks.begin(), band_tasks.end(), order);
+        for (const WaveTask& t : band_tasks) pl->band_expected[t.band - 1] += 1;
+        pl->n_wave_band = (int)band_tasks.size();
+        tasks.insert(tasks.begin(), band_tasks.begin(), band_tasks.end());  // the band runs go first
     }
-    gen_rest.insert(gen_rest.end(), lr_tiles.begin(), lr_tiles.end());  // no ring strips: they are ordinary edge tiles
-    std::sort(gen_rest.begin(), gen_rest.end());
-    pl->n_generic_band = (int)gen.size();
-    pl->n_fast_band = (int)fast.size();
-    gen.insert(gen.end(), gen_rest.begin(), gen_rest.end());
-    fast.insert(fast.end(), fast_rest.begin(), fast_rest.end());
-    pl->n_generic = (int)gen.size();
-    pl->n_fast = (int)fast.size();
-    if (pl->n_generic) {
-        CUDA_TRY(cudaMalloc(&pl->d_generic, sizeof(int) * gen.size()));
-        CUDA_TRY(cudaMemcpyAsync(pl->d_generic, gen.data(), sizeof(int) * gen.size(), cudaMemcpyHostToDevice, s->stream));
+    if (!slab) pl->band_expected[0] = pl->band_expected[1] = 0;
+    pl->n_edge_band = (int)edge_band.size();
+    pl->edge = edge_band;
+    pl->edge.insert(pl->edge.end(), edge_rest.begin(), edge_rest.end());
+    return 0;
+}
+
+// Classify the tile grid of a k-step pass and put its task lists on the device (cached per k until sources, probes,
+// materials, options or peer links change).
+static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
+    sm_count(s);
+    if (s->opt.wavefront && wave_has_k(s, k) && (k == 12 || s->dtype == FDTD2D_F64))  // (these read the permeability check)
+        if (int rc = check_ch_uniform(s)) return rc;
+    PlanLists L;
+    if (int rc = plan_pass(s, k, &L)) return rc;
+    pl->tp = L.tp;
+    pl->wave_ring = L.wave_ring;
+    pl->band_expected[0] = L.band_expected[0], pl->band_expected[1] = L.band_expected[1];
+    pl->n_wave = (int)L.tasks.size(), pl->n_wave_band = L.n_wave_band;
+    pl->n_edge = (int)L.edge.size(), pl->n_edge_band = L.n_edge_band;
+    pl->n_fast = (int)L.fast.size();
+    if (pl->n_wave) {
+        CUDA_TRY(cudaMalloc(&pl->d_ticket, sizeof(int)));
+        CUDA_TRY(cudaMalloc(&pl->d_wave, sizeof(WaveTask) * L.tasks.size()));
+        // on the handle's own stream: a plain cudaMemcpy goes through the legacy default stream, which a non-blocking
+        // stream does not wait for -- with another handle keeping the GPU busy the kernel could read the list before it
+        // had landed (seen as an illegal address with two handles in two host threads)
+        CUDA_TRY(cudaMemcpyAsync(pl->d_wave, L.tasks.data(), sizeof(WaveTask) * L.tasks.size(), cudaMemcpyHostToDevice, s->stream));
+    }
+    if (pl->n_edge) {
+        CUDA_TRY(cudaMalloc(&pl->d_edge, sizeof(int) * L.edge.size()));
+        CUDA_TRY(cudaMemcpyAsync(pl->d_edge, L.edge.data(), sizeof(int) * L.edge.size(), cudaMemcpyHostToDevice, s->stream));
     }
     if (pl->n_fast) {
-        CUDA_TRY(cudaMalloc(&pl->d_fast, sizeof(int) * fast.size()));
-        CUDA_TRY(cudaMemcpyAsync(pl->d_fast, fast.data(), sizeof(int) * fast.size(), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaMalloc(&pl->d_fast, sizeof(int) * L.fast.size()));
+        CUDA_TRY(cudaMemcpyAsync(pl->d_fast, L.fast.data(), sizeof(int) * L.fast.size(), cudaMemcpyHostToDevice, s->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(s->stream));  // the host vectors die here
+    const TilePlan& tp = pl->tp;
+    if (s->opt.debug)
+        fprintf(stderr, "[fdtd2d] plan k=%d: tiles %d x %d (core %d x %d), edge %d (band %d), tma %d, wave runs %d (band %d, ring %d), band tasks %d | %d\n", k,
+                tp.tiles_y, tp.tiles_x, tp.CH, tp.CW, pl->n_edge, pl->n_edge_band, pl->n_fast, pl->n_wave, pl->n_wave_band, (int)pl->wave_ring,
+                pl->band_expected[0], pl->band_expected[1]);
     pl->valid = true;
     return 0;
 }
 
-// fp32 hybrid pass: plain tiles on the register-resident kernel, the rest on the generic kernel
-// (same tile grid), the two launches overlapped on two streams.
-// part: 0 = every tile, 1 = only the band (halo-producing) tiles, 2 = everything but the band
-static int launch_hybrid(fdtd2d_sim* s, int k, int part) {
+// One pass of the tile / wavefront kernels: edge tiles on a side stream, concurrently with the runs / plain tiles.
+// part: 0 = everything, 1 = only the tasks that hold band rows of a slab, 2 = everything else.
+template <typename T> static int launch_hybrid_t(fdtd2d_sim* s, int k, int part) {
     PassPlan& pl = s->hybrid[k];
     if (!pl.valid)
         if (int rc = classify_tiles(s, k, &pl)) return rc;
-    PassParams<float> p;
-    fill_params(s, pl.tp, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC, &p);
-    const int g_off = part == 2 ? pl.n_generic_band : 0, f_off = part == 2 ? pl.n_fast_band : 0;
-    const int n_gen = part == 1 ? pl.n_generic_band : pl.n_generic - g_off;
-    const int n_fst = part == 1 ? pl.n_fast_band : pl.n_fast - f_off;
-    const bool both = n_gen > 0 && n_fst > 0;
-    cudaStream_t gstream = s->stream;
+    PassParams<T> p;
+    fill_params(s, pl.tp, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC, &p, &pl);
+    const int e_off = part == 2 ? pl.n_edge_band : 0, w_off = part == 2 ? pl.n_wave_band : 0;
+    const int n_edge = part == 1 ? pl.n_edge_band : pl.n_edge - e_off;
+    const int n_wave = part == 1 ? pl.n_wave_band : pl.n_wave - w_off;
+    const int n_fast = part == 1 ? 0 : pl.n_fast;
+    if (peer_mode(s) && part != 2)  // band tasks done in this pass: counted from zero
+        CUDA_TRY(cudaMemsetAsync(s->d_slab_flags + FLAG_CNT_TOP, 0, 2 * sizeof(unsigned), s->stream));
+    const bool both = n_edge > 0 && (n_wave > 0 || n_fast > 0);
+    cudaStream_t estream = s->stream;
     if (both) {
         if (!s->side_stream) {
             CUDA_TRY(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
@@ -851,64 +991,48 @@ static int launch_hybrid(fdtd2d_sim* s, int k, int part) {
         }
         CUDA_TRY(cudaEventRecord(s->ev_fork, s->stream));
         CUDA_TRY(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
-        gstream = s->side_stream;
+        estream = s->side_stream;
     }
-    const FastCfg fc = kFastCfgs[s->fast_cfg];
-    if (n_gen) {
-        p.tile_list = pl.d_generic + g_off;
+    if (n_edge) {
+        p.tile_list = pl.d_edge + e_off;
         int rc;
-        if (s->variant == 3) {  // debugging aid: shared-memory generic kernel for the non-plain tiles
-            switch (fc.MR * fc.NW) {
-                case 32: rc = launch_generic_list_t<32>(s->device, p, n_gen, gstream); break;
-                case 48: rc = launch_generic_list_t<48>(s->device, p, n_gen, gstream); break;
-                case 64: rc = launch_generic_list_t<64>(s->device, p, n_gen, gstream); break;
-                default: return fail(FDTD2D_EINVAL, "no generic kernel for %d-row tiles", fc.MR * fc.NW);
+        if (s->variant == 3) {  // debugging aid: shared-memory generic kernel for the edge tiles (fp32)
+            if constexpr (std::is_same<T, float>::value) {
+                if (peer_mode(s)) return fail(FDTD2D_EINVAL, "variant 3 does not take part in the peer halo exchange");
+                rc = launch_generic_list_t<F_TH>(s->device, p, n_edge, estream);
+            } else {
+                return fail(FDTD2D_EINVAL, "variant 3 is an fp32 debugging aid");
             }
-        } else if (fc.MR == 4 && fc.NW == 16) {
-            rc = launch_edge_t<4, 16>(s->device, p, n_gen, gstream);
-        } else if (fc.MR == 6 && fc.NW == 8) {
-            rc = launch_edge_t<6, 8>(s->device, p, n_gen, gstream);
-        } else if (fc.MR == 4 && fc.NW == 12) {
-            rc = launch_edge_t<4, 12>(s->device, p, n_gen, gstream);
-        } else if (fc.MR == 4 && fc.NW == 8) {
-            rc = launch_edge_t<4, 8>(s->device, p, n_gen, gstream);
         } else {
-            return fail(FDTD2D_EINVAL, "no edge kernel for this tile shape");
+            rc = launch_edge(s->device, p, n_edge, estream);
         }
         if (rc) return rc;
         s->launches += 1;
     }
-    const bool wave = pl.d_wave && part != 1;  // the band tiles of a slab stay on the tile kernel
-    if (wave && n_fst) {
-        const WaveTask* tasks = part == 2 ? pl.d_wave : pl.d_wave + pl.n_wave_rest;
-        const int n_tasks = part == 2 ? pl.n_wave_rest : pl.n_wave_all;
-        p.tile_list = nullptr;
-        if (n_tasks)
-            if (int rc = launch_wave(s, p, tasks, n_tasks, pl.d_ticket, k, pl.wave_ring)) return rc;
-        s->launches += n_tasks ? 1 : 0;
-    } else if (n_fst) {
-        p.tile_list = pl.d_fast + f_off;
-        int rc;
-        switch (s->fast_cfg) {
-            case 0: rc = launch_fast_t<4, 8, 3>(s, p, n_fst); break;
-            case 1: rc = launch_fast_t<4, 12, 2>(s, p, n_fst); break;
-            case 2: rc = launch_fast_t<4, 16, 1>(s, p, n_fst); break;
-            case 3: rc = launch_fast_t<6, 8, 2>(s, p, n_fst); break;
-            case 4: rc = launch_fast_t<8, 8, 1>(s, p, n_fst); break;
-            case 5: rc = launch_fast_t<2, 16, 2>(s, p, n_fst); break;
-            case 6: rc = launch_tma_t<4, 16, false>(s, p, n_fst); break;
-            case 7: rc = launch_tma_t<4, 16, true>(s, p, n_fst); break;
-            case 8: rc = launch_tma_t<4, 16, false>(s, p, n_fst); break;
-            default: return fail(FDTD2D_EINVAL, "bad fast config");
-        }
-        if (rc) return rc;
+    p.tile_list = nullptr;
+    if (n_wave) {
+        if (int rc = launch_wave(s, p, pl.d_wave + w_off, n_wave, pl.d_ticket, k, pl.wave_ring)) return rc;
         s->launches += 1;
+    }
+    if (n_fast) {
+        if constexpr (std::is_same<T, float>::value) {
+            p.tile_list = pl.d_fast;
+            const int rc = s->opt.tma_pair ? launch_tma_t<F_MR, F_NW, true>(s, p, n_fast) : launch_tma_t<F_MR, F_NW, false>(s, p, n_fast);
+            if (rc) return rc;
+            s->launches += 1;
+        } else {
+            return fail(FDTD2D_EINVAL, "internal: TMA tiles are fp32 only");
+        }
     }
     if (both) {
         CUDA_TRY(cudaEventRecord(s->ev_join, s->side_stream));
         CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
     }
     return 0;
+}
+
+static int launch_hybrid(fdtd2d_sim* s, int k, int part) {
+    return s->dtype == FDTD2D_F64 ? launch_hybrid_t<double>(s, k, part) : launch_hybrid_t<float>(s, k, part);
 }
 
 // ---- cluster-resident path (grid_resident.cuh) ---------------------------------------------------
@@ -921,12 +1045,9 @@ struct ResCfg {
 static const ResCfg kResCfgs[] = {{3, 16}, {4, 12}, {2, 16}, {4, 8}, {3, 12}};
 constexpr int N_RES_CFG = sizeof(kResCfgs) / sizeof(kResCfgs[0]);
 
-static int resident_cfg() {
-    if (const char* e = getenv("FDTD2D_RESIDENT_CFG")) {
-        const int v = atoi(e);
-        if (v >= 0 && v < N_RES_CFG) return v;
-    }
-    return 0;
+static int resident_cfg(const fdtd2d_sim* s) {
+    const int v = s->opt.resident_cfg;
+    return (v >= 0 && v < N_RES_CFG) ? v : 0;
 }
 
 // Small fp32 grids that fit a thread-block cluster: whole-run residency instead of k-step tiles.
@@ -934,10 +1055,9 @@ static bool resident_eligible(fdtd2d_sim* s) {
     if (s->resident_ok >= 0) return s->resident_ok != 0;
     s->resident_ok = 0;
     if (s->dtype != FDTD2D_F32 || s->has_top_nb || s->has_bot_nb) return false;
-    const int rcfg = resident_cfg(), mr = kResCfgs[rcfg].MR, band = mr * kResCfgs[rcfg].NW;
+    const int rcfg = resident_cfg(s), mr = kResCfgs[rcfg].MR, band = mr * kResCfgs[rcfg].NW;
     if (s->C < 16 || s->C > RES_TW || s->Rg < 16 || s->Rg > 8 * band) return false;
-    if (const char* e = getenv("FDTD2D_NO_RESIDENT"))
-        if (atoi(e)) return false;
+    if (!s->opt.resident) return false;
     // every source / probe cell may need a 4-cell slot in its CTA's slot frame
     std::vector<int> per_grid((size_t)s->batch, 0);
     for (const Cell& c : s->h_src) per_grid[c.grid] += 1;
@@ -945,14 +1065,11 @@ static bool resident_eligible(fdtd2d_sim* s) {
     for (int v : per_grid)
         if (v > RES_MAX_SLOTS) return false;
     int n = (s->Rg + band - 1) / band;
-    if (const char* e = getenv("FDTD2D_RESIDENT_CLUSTER")) {  // tuning knob: more, thinner bands per grid
-        const int v = atoi(e);
-        if (v >= n && v <= 8) n = v;
-    }
+    if (s->opt.resident_cluster >= n && s->opt.resident_cluster <= 8) n = s->opt.resident_cluster;  // tuning knob: more, thinner bands per grid
     // The first and last CTA of a cluster also run the top / bottom boundary pass: give them `trim` rows fewer
     // than the middle ones when the grid leaves room (rows: edge | (n-2) x rpc | what is left, at most edge).
     int trim = 4 * mr;
-    if (const char* e = getenv("FDTD2D_RESIDENT_TRIM")) trim = std::max(0, atoi(e)) / mr * mr;
+    if (s->opt.resident_trim >= 0) trim = s->opt.resident_trim / mr * mr;
     int rpc = 0, edge = 0, last = 0;
     for (;; trim -= mr) {
         if (n <= 2 || trim <= 0) {
@@ -1002,7 +1119,7 @@ template <int MR, int NW> static int launch_resident_t(fdtd2d_sim* s, int n_step
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (getenv("FDTD2D_DEBUG")) {
+    if (s->opt.debug) {
         int nc = -1;
         cudaOccupancyMaxActiveClusters(&nc, grid_resident_kernel<MR, NW>, &cfg);
         fprintf(stderr, "[fdtd2d] resident: %d grids x cluster %d (%d | %d rows per CTA, %d x %d warps), %zu B smem, max active clusters %d\n",
@@ -1025,49 +1142,111 @@ static int launch_resident(fdtd2d_sim* s, int n_steps) {
     }
 }
 
-static bool uses_hybrid(const fdtd2d_sim* s, int phases) {
-    const int all = FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC;
-    return s->dtype == FDTD2D_F32 && phases == all && s->variant != 1;
-}
+// ---- tiny grids (grid_small.cuh) ------------------------------------------------------------------------
+static bool small_grid(const fdtd2d_sim* s) { return s->Rg < 2 * RING + 1 || s->C < 2 * RING + 1; }
 
-static int run_pass(fdtd2d_sim* s, int k, int phases) {
-    int rc;
-    const int all_phases = FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC;
-    if (s->dtype == FDTD2D_F64)
-        rc = (phases == all_phases && s->variant != 1) ? launch_edge_all_f64(s, k) : launch_generic_all<double>(s, k, phases);
-    else if (uses_hybrid(s, phases))
-        rc = launch_hybrid(s, k, 0);
-    else
-        rc = launch_generic_all<float>(s, k, phases);
-    if (rc) return rc;
-    s->cur ^= 1;
+template <typename T> static int launch_small_t(fdtd2d_sim* s, int n_steps, int phases) {
+    TilePlan tp;
+    tp.k = n_steps;
+    PassParams<T> p;
+    fill_params(s, tp, phases, &p);
+    grid_small_kernel<T><<<s->batch, SMALL_NT, 0, s->stream>>>(p);  // in place: the current state stays current
+    CUDA_TRY(cudaGetLastError());
+    s->launches += 1;
     s->passes += 1;
     return 0;
 }
 
+static int launch_small(fdtd2d_sim* s, int n_steps, int phases = FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC) {
+    return s->dtype == FDTD2D_F64 ? launch_small_t<double>(s, n_steps, phases) : launch_small_t<float>(s, n_steps, phases);
+}
+
+static bool uses_hybrid(const fdtd2d_sim* s, int phases) {
+    const int all = FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC;
+    return phases == all && s->variant != 1;
+}
+
+static int run_pass(fdtd2d_sim* s, int k, int phases) {
+    int rc;
+    if (uses_hybrid(s, phases))
+        rc = launch_hybrid(s, k, 0);
+    else
+        rc = s->dtype == FDTD2D_F64 ? launch_generic_all<double>(s, k, phases) : launch_generic_all<float>(s, k, phases);
+    if (rc) return rc;
+    s->cur ^= 1;
+    s->passes += 1;
+    if (peer_mode(s)) s->pass_seq += 1;
+    return 0;
+}
+
+// ---- y-slab peer links -------------------------------------------------------------------------------
+// What a slab tells its neighbours (fdtd2d_peer_export / fdtd2d_peer_attach): geometry for the checks, the device
+// pointers of its two field sets and its flag block -- used as they are inside one process -- and their CUDA IPC
+// handles for a neighbour in another process.
+struct PeerBlob {
+    uint32_t magic;
+    int32_t pid, device, dtype, Rg, C, row0, Rl, row_begin, row_end, halo, cur;
+    uint64_t pitch;
+    uint64_t ptr[7];            // field[0][0..2], field[1][0..2], flags
+    cudaIpcMemHandle_t ipc[7];
+};
+static_assert(sizeof(PeerBlob) <= FDTD2D_PEER_BLOB_BYTES, "peer blob does not fit the size the header promises");
+constexpr uint32_t PEER_MAGIC = 0x46443250u;  // "FD2P"
+
+static void peer_close(fdtd2d_sim* s, int side) {
+    PeerLink& pe = s->peer[side];
+    if (pe.attached && pe.ipc) {
+        for (int h = 0; h < 2; ++h)
+            for (int f = 0; f < 3; ++f)
+                if (pe.field[h][f]) cudaIpcCloseMemHandle(pe.field[h][f]);
+        if (pe.flags) cudaIpcCloseMemHandle(pe.flags);
+    }
+    pe = PeerLink();
+}
+
+// Read the flag block; wait (on the host) until both attached neighbours have delivered the ghost rows of the current
+// state, so that a download that follows sees them.  A timeout inside a kernel or here is an error.
+static int peer_settle(fdtd2d_sim* s) {
+    if (!peer_mode(s)) return 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        unsigned f[FLAG_WORDS];
+        CUDA_TRY(cudaMemcpyAsync(f, s->d_slab_flags, sizeof f, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (f[FLAG_ERR]) return fail(FDTD2D_ESTATE, "halo wait timed out: the %s neighbour slab did not deliver its rows (are all slabs stepping the same passes?)",
+                                     f[FLAG_ERR] == 1 ? "top" : "bottom");
+        const bool top_ok = !s->peer[0].attached || (int)(f[FLAG_IN_TOP] - s->pass_seq) >= 0;
+        const bool bot_ok = !s->peer[1].attached || (int)(f[FLAG_IN_BOT] - s->pass_seq) >= 0;
+        if (top_ok && bot_ok) return 0;
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20))
+            return fail(FDTD2D_ESTATE, "halo rows of state %u have not arrived after 20 s (flags %u / %u)", s->pass_seq, f[FLAG_IN_TOP], f[FLAG_IN_BOT]);
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+}
+
 // 2-D copy between a dense host array (rows x width elements) and the padded device layout
-static int copy2d(const fdtd2d_sim* s, void* dev, void* host, int rows, int width, bool to_device) {
+static int copy2d(const fdtd2d_sim* s, void* dev, void* host, int rows, int width, bool to_device, cudaStream_t st) {
     const size_t wbytes = (size_t)width * s->esize;
     if ((size_t)width == s->pitch) {  // no padding on either side: one linear copy
         CUDA_TRY(cudaMemcpyAsync(to_device ? dev : host, to_device ? host : dev, wbytes * rows,
-                                 to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, s->stream));
+                                 to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st));
         return 0;
     }
     if (to_device)
         CUDA_TRY(cudaMemcpy2DAsync(dev, s->pitch * s->esize, host, wbytes, wbytes, rows, cudaMemcpyHostToDevice,
-                                   s->stream));
+                                   st));
     else
         CUDA_TRY(cudaMemcpy2DAsync(host, wbytes, dev, s->pitch * s->esize, wbytes, rows, cudaMemcpyDeviceToHost,
-                                   s->stream));
+                                   st));
     return 0;
 }
 
-static int transfer_field(fdtd2d_sim* s, void* dev, void* host, int rows_host, int width, bool to_device) {
+static int transfer_field(fdtd2d_sim* s, void* dev, void* host, int rows_host, int width, bool to_device, cudaStream_t st) {
     // per grid: rows_host x width on the host, Rl x pitch on the device
     if (rows_host == s->Rl && (size_t)s->batch * rows_host < (size_t)0x7fffffff)
         // the grids are back to back on both sides: the whole batch is one strided copy (1024 small grids would
         // otherwise be 1024 copies of 256 KB each)
-        return copy2d(s, dev, host, s->batch * rows_host, width, to_device);
+        return copy2d(s, dev, host, s->batch * rows_host, width, to_device, st);
     if (s->batch > 1) {  // Hy: one row fewer per grid on the host than on the device -> one 3-D copy for the batch
         const size_t wbytes = (size_t)width * s->esize;
         cudaMemcpy3DParms c = {};
@@ -1077,13 +1256,13 @@ static int transfer_field(fdtd2d_sim* s, void* dev, void* host, int rows_host, i
         c.dstPtr = to_device ? d : h;
         c.extent = make_cudaExtent(wbytes, (size_t)rows_host, (size_t)s->batch);
         c.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-        CUDA_TRY(cudaMemcpy3DAsync(&c, s->stream));
+        CUDA_TRY(cudaMemcpy3DAsync(&c, st));
         return 0;
     }
     for (int b = 0; b < s->batch; ++b) {
         char* d = static_cast<char*>(dev) + (size_t)b * s->grid_elems * s->esize;
         char* h = static_cast<char*>(host) + (size_t)b * rows_host * width * s->esize;
-        if (int rc = copy2d(s, d, h, rows_host, width, to_device)) return rc;
+        if (int rc = copy2d(s, d, h, rows_host, width, to_device, st)) return rc;
     }
     return 0;
 }
@@ -1108,7 +1287,7 @@ static int create_impl(fdtd2d_sim** out, int Rg, int C, int row_begin, int row_e
                        int batch) {
     REQUIRE(out, "out is null");
     *out = nullptr;
-    REQUIRE(Rg >= 2 * RING + 1 && C >= 2 * RING + 1, "rows and cols must be >= 11 (got %d x %d)", Rg, C);
+    REQUIRE(Rg >= SMALL_MIN && C >= SMALL_MIN, "rows and cols must be >= %d (got %d x %d): the reference's own boundary code indexes 6 cells deep", SMALL_MIN, Rg, C);
     REQUIRE(dtype == FDTD2D_F32 || dtype == FDTD2D_F64, "dtype must be FDTD2D_F32 or FDTD2D_F64");
     REQUIRE(batch >= 1, "batch must be >= 1");
     REQUIRE(0 <= row_begin && row_begin < row_end && row_end <= Rg, "bad slab rows [%d, %d) of %d", row_begin, row_end, Rg);
@@ -1117,13 +1296,15 @@ static int create_impl(fdtd2d_sim** out, int Rg, int C, int row_begin, int row_e
     if (top_nb || bot_nb) {
         REQUIRE(batch == 1, "slab handles must have batch = 1");
         REQUIRE(halo >= 1, "a slab with neighbours needs halo >= 1");
+        REQUIRE(Rg >= 2 * RING + 1 && C >= 2 * RING + 1, "slabs need a grid of at least 11 x 11");
         REQUIRE(row_end - row_begin >= 2 * FDTD2D_MAX_K + 2 * RING, "slab of %d rows is too thin", row_end - row_begin);
     }
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (ndev <= 0) return fail(FDTD2D_ECUDA, "no CUDA device (libfdtd2d has no CPU fallback)");
     REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return fail(FDTD2D_ECUDA, "cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(guard.err));
 
     const int row0_ = row_begin - (top_nb ? halo : 0);
     const int rl_ = (row_end + (bot_nb ? halo : 0)) - row0_;
@@ -1146,6 +1327,7 @@ static int create_impl(fdtd2d_sim** out, int Rg, int C, int row_begin, int row_e
     s->esize = dtype == FDTD2D_F32 ? 4 : 8;
     s->pitch = round_up((size_t)C, 128 / s->esize);  // rows start on 128-byte lines
     s->grid_elems = (size_t)s->Rl * s->pitch;
+    s->opt = options_from_env();  // the environment is read here, once; fdtd2d_set_option changes this handle only
     const size_t bytes = s->grid_elems * s->esize * (size_t)batch;
 
     cudaError_t e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
@@ -1154,10 +1336,10 @@ static int create_impl(fdtd2d_sim** out, int Rg, int C, int row_begin, int row_e
         return fail(FDTD2D_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
     }
     s->stream = s->own_stream;
-    void** bufs[9] = {&s->field[0][0], &s->field[0][1], &s->field[0][2], &s->field[1][0], &s->field[1][1],
-                      &s->field[1][2], &s->ce,          &s->ch,          &s->mur};
-    for (int i = 0; i < 9; ++i) {
-        const size_t nb = i == 8 ? (size_t)batch * s->esize : bytes;
+    void** bufs[10] = {&s->field[0][0], &s->field[0][1], &s->field[0][2], &s->field[1][0], &s->field[1][1],
+                       &s->field[1][2], &s->ce,          &s->ch,          &s->mur,         reinterpret_cast<void**>(&s->d_slab_flags)};
+    for (int i = 0; i < 10; ++i) {
+        const size_t nb = i == 8 ? (size_t)batch * s->esize : (i == 9 ? FLAG_WORDS * sizeof(unsigned) : bytes);
         e = cudaMalloc(bufs[i], nb);
         if (e == cudaSuccess) e = cudaMemsetAsync(*bufs[i], 0, nb, s->stream);
         if (e != cudaSuccess) {
@@ -1166,9 +1348,11 @@ static int create_impl(fdtd2d_sim** out, int Rg, int C, int row_begin, int row_e
                         "device allocation of %zu bytes failed: %s", nb, cudaGetErrorString(e));
         }
     }
-    if (const char* e = getenv("FDTD2D_FAST_CFG")) {
-        const int v = atoi(e);
-        if (v >= 0 && v < N_FAST_CFG) s->fast_cfg = v;
+    // (the flag block must read zero before a neighbour can possibly raise it)
+    e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) {
+        fdtd2d_destroy(s);
+        return fail(FDTD2D_ECUDA, "device initialisation failed: %s", cudaGetErrorString(e));
     }
     *out = s;
     return 0;
@@ -1185,8 +1369,10 @@ int fdtd2d_create_slab(fdtd2d_sim** out, int global_rows, int cols, int row_begi
 
 int fdtd2d_destroy(fdtd2d_sim* s) {
     if (!s) return 0;
-    cudaSetDevice(s->device);
+    DeviceGuard guard(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    peer_close(s, 0);
+    peer_close(s, 1);
     for (int h = 0; h < 2; ++h)
         for (int f = 0; f < 3; ++f) cudaFree(s->field[h][f]);
     cudaFree(s->ce);
@@ -1202,18 +1388,42 @@ int fdtd2d_destroy(fdtd2d_sim* s) {
     cudaFree(s->d_rgb);
     cudaFree(s->d_lut);
     cudaFree(s->d_flag);
+    cudaFree(s->d_slab_flags);
     free_plans(s);
     if (s->side_stream) cudaStreamDestroy(s->side_stream);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->ev_copy) cudaEventDestroy(s->ev_copy);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
     return 0;
 }
 
+int fdtd2d_set_option(fdtd2d_sim* s, const char* key, int value) {
+    REQUIRE(s && key, "null argument");
+    const OptionKey* k = find_option(key);
+    REQUIRE(k, "unknown option '%s'", key);
+    if (s->opt.*(k->field) == value) return 0;
+    USE_DEVICE(s);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->opt.*(k->field) = value;
+    s->ch_uniform = -1;  // (uniform_ch decides how the result of the check is used)
+    free_plans(s);
+    return 0;
+}
+
+int fdtd2d_get_option(const fdtd2d_sim* s, const char* key, int* value) {
+    REQUIRE(s && key && value, "null argument");
+    const OptionKey* k = find_option(key);
+    REQUIRE(k, "unknown option '%s'", key);
+    *value = s->opt.*(k->field);
+    return 0;
+}
+
 int fdtd2d_set_stream(fdtd2d_sim* s, void* cuda_stream) {
     REQUIRE(s, "handle is null");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->stream = static_cast<cudaStream_t>(cuda_stream);
     return 0;
@@ -1221,17 +1431,24 @@ int fdtd2d_set_stream(fdtd2d_sim* s, void* cuda_stream) {
 
 int fdtd2d_reset_stream(fdtd2d_sim* s) {
     REQUIRE(s, "handle is null");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->stream = s->own_stream;
     return 0;
 }
 
+int fdtd2d_get_stream(const fdtd2d_sim* s, void** cuda_stream) {
+    REQUIRE(s && cuda_stream, "null argument");
+    *cuda_stream = s->stream;
+    return 0;
+}
+
 int fdtd2d_sync(fdtd2d_sim* s) {
     REQUIRE(s, "handle is null");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return 0;
+    if (s->copy_stream) CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+    return peer_settle(s);
 }
 
 int fdtd2d_geometry(const fdtd2d_sim* s, int* local_rows, int* cols, int* row0, int* global_rows, int* batch,
@@ -1247,33 +1464,87 @@ int fdtd2d_geometry(const fdtd2d_sim* s, int* local_rows, int* cols, int* row0, 
     return 0;
 }
 
+static int upload_state_on(fdtd2d_sim* s, const void* Ez, const void* Hx, const void* Hy, cudaStream_t st) {
+    void** f = s->field[s->cur];
+    if (int rc = transfer_field(s, f[0], const_cast<void*>(Ez), s->Rl, s->C, true, st)) return rc;
+    if (int rc = transfer_field(s, f[1], const_cast<void*>(Hx), s->Rl, s->C - 1, true, st)) return rc;
+    if (int rc = transfer_field(s, f[2], const_cast<void*>(Hy), hy_rows(s), s->C, true, st)) return rc;
+    return 0;
+}
+
 int fdtd2d_upload_state(fdtd2d_sim* s, const void* Ez, const void* Hx, const void* Hy) {
     REQUIRE(s && Ez && Hx && Hy, "null argument");
-    if (int rc = use_device(s)) return rc;
-    void** f = s->field[s->cur];
-    if (int rc = transfer_field(s, f[0], const_cast<void*>(Ez), s->Rl, s->C, true)) return rc;
-    if (int rc = transfer_field(s, f[1], const_cast<void*>(Hx), s->Rl, s->C - 1, true)) return rc;
-    if (int rc = transfer_field(s, f[2], const_cast<void*>(Hy), hy_rows(s), s->C, true)) return rc;
-    return 0;
+    USE_DEVICE(s);
+    return upload_state_on(s, Ez, Hx, Hy, s->stream);
 }
 
 int fdtd2d_download_state(fdtd2d_sim* s, void* Ez, void* Hx, void* Hy) {
     REQUIRE(s, "handle is null");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
+    if (int rc = peer_settle(s)) return rc;  // (a slab's ghost rows are written by its neighbours)
     void** f = s->field[s->cur];
     if (Ez)
-        if (int rc = transfer_field(s, f[0], Ez, s->Rl, s->C, false)) return rc;
+        if (int rc = transfer_field(s, f[0], Ez, s->Rl, s->C, false, s->stream)) return rc;
     if (Hx)
-        if (int rc = transfer_field(s, f[1], Hx, s->Rl, s->C - 1, false)) return rc;
+        if (int rc = transfer_field(s, f[1], Hx, s->Rl, s->C - 1, false, s->stream)) return rc;
     if (Hy)
-        if (int rc = transfer_field(s, f[2], Hy, hy_rows(s), s->C, false)) return rc;
+        if (int rc = transfer_field(s, f[2], Hy, hy_rows(s), s->C, false, s->stream)) return rc;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// ---- asynchronous copies (pinned host memory): one host thread can keep several handles busy -------------------
+// The copy runs on the handle's copy stream, ordered after the stepping work issued so far (a download reads the
+// result of the last fdtd2d_step; an upload waits until the stepping kernels that still read the old state are done);
+// stepping work issued AFTER the call is ordered behind the copy.  The host does not block; fdtd2d_copy_wait (or
+// fdtd2d_sync) does.
+static int copy_fork(fdtd2d_sim* s) {
+    if (!s->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(s->ev_copy, s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->ev_copy, 0));
+    return 0;
+}
+static int copy_join(fdtd2d_sim* s) {
+    CUDA_TRY(cudaEventRecord(s->ev_copy, s->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_copy, 0));
+    return 0;
+}
+
+int fdtd2d_upload_state_async(fdtd2d_sim* s, const void* Ez, const void* Hx, const void* Hy) {
+    REQUIRE(s && Ez && Hx && Hy, "null argument");
+    USE_DEVICE(s);
+    if (int rc = copy_fork(s)) return rc;
+    if (int rc = upload_state_on(s, Ez, Hx, Hy, s->copy_stream)) return rc;
+    return copy_join(s);
+}
+
+int fdtd2d_download_state_async(fdtd2d_sim* s, void* Ez, void* Hx, void* Hy) {
+    REQUIRE(s, "handle is null");
+    USE_DEVICE(s);
+    if (int rc = copy_fork(s)) return rc;
+    void** f = s->field[s->cur];
+    if (Ez)
+        if (int rc = transfer_field(s, f[0], Ez, s->Rl, s->C, false, s->copy_stream)) return rc;
+    if (Hx)
+        if (int rc = transfer_field(s, f[1], Hx, s->Rl, s->C - 1, false, s->copy_stream)) return rc;
+    if (Hy)
+        if (int rc = transfer_field(s, f[2], Hy, hy_rows(s), s->C, false, s->copy_stream)) return rc;
+    return copy_join(s);
+}
+
+int fdtd2d_copy_wait(fdtd2d_sim* s) {
+    REQUIRE(s, "handle is null");
+    USE_DEVICE(s);
+    if (s->copy_stream) CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
     return 0;
 }
 
 int fdtd2d_zero_state(fdtd2d_sim* s) {
     REQUIRE(s, "handle is null");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     const size_t bytes = s->grid_elems * s->esize * (size_t)s->batch;
     for (int h = 0; h < 2; ++h)
         for (int f = 0; f < 3; ++f) CUDA_TRY(cudaMemsetAsync(s->field[h][f], 0, bytes, s->stream));
@@ -1281,9 +1552,16 @@ int fdtd2d_zero_state(fdtd2d_sim* s) {
     return 0;
 }
 
+// the maps changed: the permeability check and every cached plan that depends on it start over
+static void materials_changed(fdtd2d_sim* s) {
+    s->coeffs_set = true;
+    s->ch_uniform = -1;
+    free_plans(s);
+}
+
 int fdtd2d_set_mur_coef(fdtd2d_sim* s, const void* mur_coef) {
     REQUIRE(s && mur_coef, "null argument");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     CUDA_TRY(cudaMemcpyAsync(s->mur, mur_coef, (size_t)s->batch * s->esize, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->mur_set = true;
@@ -1292,25 +1570,34 @@ int fdtd2d_set_mur_coef(fdtd2d_sim* s, const void* mur_coef) {
 
 int fdtd2d_set_coeffs(fdtd2d_sim* s, const void* ce, const void* ch, const void* mur_coef) {
     REQUIRE(s && ce && ch, "null argument");
-    if (int rc = use_device(s)) return rc;
-    if (int rc = transfer_field(s, s->ce, const_cast<void*>(ce), s->Rl, s->C, true)) return rc;
-    if (int rc = transfer_field(s, s->ch, const_cast<void*>(ch), s->Rl, s->C, true)) return rc;
+    USE_DEVICE(s);
+    if (int rc = transfer_field(s, s->ce, const_cast<void*>(ce), s->Rl, s->C, true, s->stream)) return rc;
+    if (int rc = transfer_field(s, s->ch, const_cast<void*>(ch), s->Rl, s->C, true, s->stream)) return rc;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    s->coeffs_set = true;
-    s->ch_uniform = -1;
+    materials_changed(s);
     if (mur_coef) return fdtd2d_set_mur_coef(s, mur_coef);
     return 0;
 }
 
-static int finish_materials(fdtd2d_sim* s, double dt, double dx);
+static int finish_materials(fdtd2d_sim* s, double dt, double dx, bool wait);
 
 int fdtd2d_set_materials(fdtd2d_sim* s, const void* eps, const void* mu, double dt, double dx) {
     REQUIRE(s && eps && mu, "null argument");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     // stage eps in ce and mu in ch, then transform in place on the device
-    if (int rc = transfer_field(s, s->ce, const_cast<void*>(eps), s->Rl, s->C, true)) return rc;
-    if (int rc = transfer_field(s, s->ch, const_cast<void*>(mu), s->Rl, s->C, true)) return rc;
-    return finish_materials(s, dt, dx);
+    if (int rc = transfer_field(s, s->ce, const_cast<void*>(eps), s->Rl, s->C, true, s->stream)) return rc;
+    if (int rc = transfer_field(s, s->ch, const_cast<void*>(mu), s->Rl, s->C, true, s->stream)) return rc;
+    return finish_materials(s, dt, dx, true);
+}
+
+int fdtd2d_set_materials_async(fdtd2d_sim* s, const void* eps, const void* mu, double dt, double dx) {
+    REQUIRE(s && eps && mu, "null argument");
+    USE_DEVICE(s);
+    if (int rc = copy_fork(s)) return rc;
+    if (int rc = transfer_field(s, s->ce, const_cast<void*>(eps), s->Rl, s->C, true, s->copy_stream)) return rc;
+    if (int rc = transfer_field(s, s->ch, const_cast<void*>(mu), s->Rl, s->C, true, s->copy_stream)) return rc;
+    if (int rc = copy_join(s)) return rc;
+    return finish_materials(s, dt, dx, false);
 }
 
 double fdtd2d_hash_uniform(uint64_t seed, uint32_t grid, uint32_t row, uint32_t col) {
@@ -1319,10 +1606,10 @@ double fdtd2d_hash_uniform(uint64_t seed, uint32_t grid, uint32_t row, uint32_t 
 
 int fdtd2d_set_materials_random(fdtd2d_sim* s, uint64_t seed, double span, double dt, double dx) {
     REQUIRE(s, "handle is null");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     const double eps0 = 8.85418e-12, mu0 = 4 * 3.141592653589793 * 1e-7;  // main.py:100-101
     const long long n = (long long)s->Rl * s->C * s->batch;
-    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    const int blocks = (int)std::min<long long>((n + 255) / 256, sm_count(s) * 16);
     if (s->dtype == FDTD2D_F32)
         random_materials_kernel<float><<<blocks, 256, 0, s->stream>>>(
             (float*)s->ce, (float*)s->ch, (float*)s->mur, s->Rl, s->C, (int)s->pitch, s->row0, (long long)s->grid_elems,
@@ -1333,17 +1620,16 @@ int fdtd2d_set_materials_random(fdtd2d_sim* s, uint64_t seed, double span, doubl
             (long long)s->grid_elems, s->batch, seed, span, eps0, mu0, dt, dx);
     CUDA_TRY(cudaGetLastError());
     s->launches += 1;
-    s->coeffs_set = true;
-    s->ch_uniform = -1;
+    materials_changed(s);
     s->mur_set = true;
     return 0;
 }
 
 // eps/mu are staged in ce/ch: form the Mur coefficient(s) and the coefficient maps in place (device-side tail of
 // every fdtd2d_set_materials* entry point)
-static int finish_materials(fdtd2d_sim* s, double dt, double dx) {
+static int finish_materials(fdtd2d_sim* s, double dt, double dx, bool wait) {
     const long long n = (long long)s->grid_elems * s->batch;
-    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+    const int blocks = (int)std::min<long long>((n + 255) / 256, sm_count(s) * 16);
     const bool has_corner = s->row0 == 0;
     if (s->dtype == FDTD2D_F32) {
         if (has_corner)
@@ -1359,17 +1645,16 @@ static int finish_materials(fdtd2d_sim* s, double dt, double dx) {
         coeff_from_materials_kernel<double><<<blocks, 256, 0, s->stream>>>((double*)s->ce, (double*)s->ch, n, dt, dx);
     }
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (wait) CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->launches += has_corner ? 2 : 1;
-    s->coeffs_set = true;
-    s->ch_uniform = -1;
+    materials_changed(s);
     if (has_corner) s->mur_set = true;
     return 0;
 }
 
 int fdtd2d_set_materials_gray(fdtd2d_sim* s, const unsigned char* gray, double black_point, double dt, double dx) {
     REQUIRE(s && gray, "null argument");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     const double eps0 = 8.85418e-12, mu0 = 4 * 3.141592653589793 * 1e-7;  // main.py:100-101
     const size_t n = (size_t)s->Rl * s->C * s->batch;
     unsigned char* d_g = nullptr;
@@ -1379,7 +1664,7 @@ int fdtd2d_set_materials_gray(fdtd2d_sim* s, const unsigned char* gray, double b
         cudaFree(d_g);
         return fail(FDTD2D_ECUDA, "gray upload failed: %s", cudaGetErrorString(e));
     }
-    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count(s) * 16);
     if (s->dtype == FDTD2D_F32)
         gray_materials_kernel<float><<<blocks, 256, 0, s->stream>>>(d_g, (float*)s->ce, (float*)s->ch, s->Rl, s->C, (int)s->pitch,
                                                                    (long long)s->grid_elems, s->batch, black_point, eps0, mu0);
@@ -1392,14 +1677,14 @@ int fdtd2d_set_materials_gray(fdtd2d_sim* s, const unsigned char* gray, double b
     cudaFree(d_g);
     if (e != cudaSuccess) return fail(FDTD2D_ECUDA, "gray_materials_kernel failed: %s", cudaGetErrorString(e));
     s->launches += 1;
-    return finish_materials(s, dt, dx);
+    return finish_materials(s, dt, dx, true);
 }
 
 int fdtd2d_generate_materials_blobs(fdtd2d_sim* s, uint64_t seed, const float* weights, double eps_lo, double eps_hi, double mu,
                                     double dt, double dx, void* eps_out) {
     REQUIRE(s && weights, "null argument");
     REQUIRE(!s->has_top_nb && !s->has_bot_nb, "the blob generator works on whole grids, not slabs");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     float* d_w = nullptr;
     const size_t wbytes = sizeof(float) * BLOB_K * BLOB_K * (size_t)s->batch;
     CUDA_TRY(cudaMalloc(&d_w, wbytes));
@@ -1420,19 +1705,19 @@ int fdtd2d_generate_materials_blobs(fdtd2d_sim* s, uint64_t seed, const float* w
     if (e != cudaSuccess) return fail(FDTD2D_ECUDA, "blob_materials_kernel failed: %s", cudaGetErrorString(e));
     s->launches += 1;
     if (eps_out) {  // the permittivity maps themselves are part of a dataset sample
-        if (int rc = transfer_field(s, s->ce, eps_out, s->Rl, s->C, false)) return rc;
+        if (int rc = transfer_field(s, s->ce, eps_out, s->Rl, s->C, false, s->stream)) return rc;
         CUDA_TRY(cudaStreamSynchronize(s->stream));
     }
-    return finish_materials(s, dt, dx);
+    return finish_materials(s, dt, dx, true);
 }
 
 int fdtd2d_download_coeffs(fdtd2d_sim* s, void* ce, void* ch, void* mur_coef) {
     REQUIRE(s, "handle is null");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     if (ce)
-        if (int rc = transfer_field(s, s->ce, ce, s->Rl, s->C, false)) return rc;
+        if (int rc = transfer_field(s, s->ce, ce, s->Rl, s->C, false, s->stream)) return rc;
     if (ch)
-        if (int rc = transfer_field(s, s->ch, ch, s->Rl, s->C, false)) return rc;
+        if (int rc = transfer_field(s, s->ch, ch, s->Rl, s->C, false, s->stream)) return rc;
     if (mur_coef)
         CUDA_TRY(cudaMemcpyAsync(mur_coef, s->mur, (size_t)s->batch * s->esize, cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1483,7 +1768,7 @@ static int build_cells(const fdtd2d_sim* s, int n, const int32_t* grid, const in
 int fdtd2d_set_sources(fdtd2d_sim* s, int n_cells, const int32_t* grid, const int32_t* row, const int32_t* col,
                        const int32_t* wave, int n_waves, int n_steps, const double* tables) {
     REQUIRE(s, "handle is null");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     cudaFree(s->d_src);
     cudaFree(s->d_src_range);
@@ -1517,7 +1802,7 @@ int fdtd2d_set_sources(fdtd2d_sim* s, int n_cells, const int32_t* grid, const in
 int fdtd2d_set_probes(fdtd2d_sim* s, int n_probes, const int32_t* grid, const int32_t* row, const int32_t* col,
                       int capacity_steps) {
     REQUIRE(s, "handle is null");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     cudaFree(s->d_probe);
     cudaFree(s->d_probe_range);
@@ -1554,7 +1839,7 @@ int fdtd2d_read_probes(fdtd2d_sim* s, void* out, int64_t first_step, int n_steps
     REQUIRE(s->n_probe > 0, "no probes set");
     REQUIRE(first_step >= 0 && n_steps >= 0 && first_step + n_steps <= s->trace_cap, "probe rows [%lld, %lld) outside capacity %lld",
             (long long)first_step, (long long)(first_step + n_steps), s->trace_cap);
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     const size_t row_bytes = (size_t)s->n_probe * s->esize;
     std::vector<char> tmp(row_bytes * (size_t)n_steps);
     CUDA_TRY(cudaMemcpyAsync(tmp.data(), static_cast<char*>(s->d_trace) + (size_t)first_step * row_bytes, tmp.size(),
@@ -1574,7 +1859,13 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
     REQUIRE(n_steps >= 0, "n_steps must be >= 0");
     REQUIRE(k_temporal >= 0 && k_temporal <= FDTD2D_MAX_K, "k_temporal must be in [0, %d]", FDTD2D_MAX_K);
     if (!s->coeffs_set || !s->mur_set) return fail(FDTD2D_ESTATE, "coefficients / Mur coefficient not set");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
+    if (n_steps > 0 && small_grid(s)) {
+        // rows or cols below 11: the reference's boundary statements overlap, so they are executed one by one
+        if (int rc = launch_small(s, n_steps)) return rc;
+        s->step += n_steps;
+        return 0;
+    }
     if (n_steps > 0 && (s->variant == 0 || s->variant == 4) && resident_eligible(s)) {
         // the whole run in one launch, the grid resident on chip (k_temporal does not apply)
         if (int rc = launch_resident(s, n_steps)) return rc;
@@ -1582,20 +1873,40 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
         return 0;
     }
     if (s->variant == 4 && n_steps > 0) return fail(FDTD2D_EINVAL, "variant 4 (cluster-resident) needs fp32, 16..256 columns, 16..384 rows, no slabs");
-    int k = k_temporal ? k_temporal : (s->dtype == FDTD2D_F32 ? 8 : 4);
-    if (!k_temporal && s->dtype == FDTD2D_F32 && s->variant != 1 && !s->has_top_nb && !s->has_bot_nb && n_steps >= 12 &&
-        getenv("FDTD2D_AUTO_K12")) {
-        // large grid with uniform permeability: the 12-level wavefront moves a third less DRAM traffic per step, but on
-        // B200 it is bound by latency (2 warps per scheduler at 255 registers), not by DRAM: 1418 against 1564 Gcell/s
-        // at 16384^2 -- so it is opt-in (k_temporal = 12, or this variable for the automatic choice)
-        PassPlan& pl = s->hybrid[12];
-        if (!pl.valid)
-            if (int rc = classify_tiles(s, 12, &pl)) return rc;
-        if (pl.d_wave) k = 12;
+    const bool slab = s->has_top_nb || s->has_bot_nb;
+    int k = k_temporal;
+    if (!k) {
+        if (s->dtype == FDTD2D_F32) {
+            k = 8;
+            if (s->opt.auto_k12 && s->variant != 1 && !slab && n_steps >= 12) {
+                // large grid with uniform permeability: the 12-level wavefront moves a third less DRAM traffic per step, but on
+                // B200 it is bound by latency (2 warps per scheduler at 255 registers), not by DRAM: 1418 against 1564 Gcell/s
+                // at 16384^2 -- so it is opt-in (k_temporal = 12, or this option for the automatic choice)
+                PassPlan& pl = s->hybrid[12];
+                if (!pl.valid)
+                    if (int rc = classify_tiles(s, 12, &pl)) return rc;
+                if (pl.d_wave) k = 12;
+            }
+        } else {
+            // fp64: 8 levels where the wavefront kernel takes the grid, 4 steps per pass on the tile kernel otherwise
+            k = s->opt.f64_k > 0 ? std::min(s->opt.f64_k, FDTD2D_MAX_K) : 8;
+            if (s->opt.f64_k <= 0) {
+                if (s->variant == 1) {
+                    k = 4;
+                } else {
+                    PassPlan& pl = s->hybrid[8];
+                    if (!pl.valid)
+                        if (int rc = classify_tiles(s, 8, &pl)) return rc;
+                    if (!pl.d_wave) k = 4;
+                }
+            }
+        }
     }
-    if (s->has_top_nb || s->has_bot_nb) {
+    if (slab) {
         k = std::min(k, s->halo);
-        REQUIRE(n_steps <= s->halo, "a slab handle can advance at most halo=%d steps between halo exchanges", s->halo);
+        // the host layer exchanges halos after every pass unless the peer links do it inside the kernels
+        const bool linked = (!s->has_top_nb || s->peer[0].attached) && (!s->has_bot_nb || s->peer[1].attached);
+        REQUIRE(linked || n_steps <= s->halo, "a slab handle without peer links can advance at most halo=%d steps between halo exchanges", s->halo);
     }
     int left = n_steps;
     while (left > 0) {
@@ -1611,8 +1922,12 @@ int fdtd2d_step_phases(fdtd2d_sim* s, int phases) {
     REQUIRE(s, "handle is null");
     REQUIRE(phases > 0 && phases < 8, "phases must be a non-empty FDTD2D_PHASE_* mask");
     if (!s->coeffs_set || !s->mur_set) return fail(FDTD2D_ESTATE, "coefficients / Mur coefficient not set");
-    if (int rc = use_device(s)) return rc;
-    if (int rc = run_pass(s, 1, phases)) return rc;
+    USE_DEVICE(s);
+    if (small_grid(s)) {
+        if (int rc = launch_small(s, 1, phases)) return rc;
+    } else if (int rc = run_pass(s, 1, phases)) {
+        return rc;
+    }
     if (phases & FDTD2D_PHASE_SRC) s->step += 1;
     return 0;
 }
@@ -1629,9 +1944,21 @@ int fdtd2d_set_step_index(fdtd2d_sim* s, int64_t step) {
     return 0;
 }
 
+int fdtd2d_source_steps(const fdtd2d_sim* s, int* n_cells, int* n_steps, int64_t* probe_capacity) {
+    REQUIRE(s, "handle is null");
+    if (n_cells) *n_cells = s->n_src;
+    if (n_steps) *n_steps = s->amp_steps;
+    if (probe_capacity) *probe_capacity = s->n_probe ? s->trace_cap : 0;
+    return 0;
+}
+
 int fdtd2d_set_kernel_variant(fdtd2d_sim* s, int variant) {
     REQUIRE(s && variant >= 0 && variant <= 4, "bad argument");
+    if (variant == s->variant) return 0;
+    USE_DEVICE(s);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->variant = variant;
+    free_plans(s);
     return 0;
 }
 
@@ -1644,6 +1971,57 @@ int fdtd2d_plan_wave_runs(int n_stretches, const int32_t* rows, const uint8_t* r
     const int len = plan_wave_runs(r, g, warps, cap_rows, k, &pr);
     for (int i = 0; i < n_stretches; ++i) parts[i] = pr[i];
     if (run_rows) *run_rows = len;
+    return 0;
+}
+
+int fdtd2d_plan_host(const int32_t* geom, int n_src, const int32_t* src, int n_probe, const int32_t* probe, int32_t* plan,
+                     int32_t* tile_kind, int cap_tiles, int32_t* tasks, int cap_tasks) {
+    REQUIRE(geom && plan && (n_src == 0 || src) && (n_probe == 0 || probe) && n_src >= 0 && n_probe >= 0, "bad argument");
+    fdtd2d_sim s;  // geometry only: no device resources are created or touched
+    s.dtype = geom[0], s.batch = geom[1], s.Rg = geom[2], s.C = geom[3], s.row_begin = geom[4], s.row_end = geom[5], s.halo = geom[6];
+    const int k = geom[7];
+    s.sm_count = geom[8], s.variant = geom[9];
+    s.opt = Options();
+    s.opt.wave_min_tiles = geom[10], s.opt.ring_min_tiles = geom[11], s.opt.wavefront = geom[12], s.opt.ring_strips = geom[13];
+    s.ch_uniform = geom[14];
+    REQUIRE((s.dtype == FDTD2D_F32 || s.dtype == FDTD2D_F64) && s.batch >= 1 && s.Rg >= 2 * RING + 1 && s.C >= 2 * RING + 1 && k >= 1 && k <= FDTD2D_MAX_K &&
+                0 <= s.row_begin && s.row_begin < s.row_end && s.row_end <= s.Rg && s.halo >= 0 && s.halo <= FDTD2D_MAX_K && s.sm_count > 0,
+            "bad geometry");
+    s.has_top_nb = s.row_begin > 0, s.has_bot_nb = s.row_end < s.Rg;
+    REQUIRE(!(s.has_top_nb || s.has_bot_nb) || (s.halo >= k && s.batch == 1 && s.row_end - s.row_begin >= 2 * FDTD2D_MAX_K + 2 * RING), "bad slab");
+    s.row0 = s.row_begin - (s.has_top_nb ? s.halo : 0);
+    s.Rl = s.row_end + (s.has_bot_nb ? s.halo : 0) - s.row0;
+    s.esize = s.dtype == FDTD2D_F32 ? 4 : 8;
+    s.pitch = round_up((size_t)s.C, 128 / s.esize);
+    for (int i = 0; i < n_src; ++i) s.h_src.push_back(Cell{src[3 * i], src[3 * i + 1], src[3 * i + 2], 0});
+    for (int i = 0; i < n_probe; ++i) s.h_probe.push_back(Cell{probe[3 * i], probe[3 * i + 1], probe[3 * i + 2], 0});
+    PlanLists L;
+    if (int rc = plan_pass(&s, k, &L)) return rc;
+    const int32_t v[16] = {L.tp.tiles_y, L.tp.tiles_x, L.tp.CH, L.tp.CW, L.tp.hx, s.row_begin - s.row0, s.Rl, (int32_t)L.edge.size(), L.n_edge_band,
+                           (int32_t)L.fast.size(), (int32_t)L.tasks.size(), L.n_wave_band, L.wave_ring ? 1 : 0, L.band_expected[0], L.band_expected[1],
+                           (int32_t)s.pitch};
+    memcpy(plan, v, sizeof v);
+    if (tile_kind) {
+        REQUIRE((size_t)cap_tiles >= L.kind.size(), "tile_kind holds %d entries, %zu needed", cap_tiles, L.kind.size());
+        for (size_t i = 0; i < L.kind.size(); ++i) tile_kind[i] = L.kind[i];
+    }
+    if (tasks) {
+        REQUIRE((size_t)cap_tasks >= L.tasks.size(), "tasks holds %d entries, %zu needed", cap_tasks, L.tasks.size());
+        memcpy(tasks, L.tasks.data(), sizeof(WaveTask) * L.tasks.size());
+    }
+    return 0;
+}
+
+int fdtd2d_plan_info(fdtd2d_sim* s, int k, int32_t* info, int n_info) {
+    REQUIRE(s && info && n_info >= 0 && k >= 1 && k <= FDTD2D_MAX_K, "bad argument");
+    if (!s->coeffs_set) return fail(FDTD2D_ESTATE, "coefficients not set");
+    USE_DEVICE(s);
+    PassPlan& pl = s->hybrid[k];
+    if (!pl.valid)
+        if (int rc = classify_tiles(s, k, &pl)) return rc;
+    const int32_t v[FDTD2D_PLAN_INFO_WORDS] = {pl.tp.tiles_y, pl.tp.tiles_x, pl.tp.CH, pl.tp.CW, pl.n_edge, pl.n_edge_band, pl.n_fast,
+                                              pl.n_wave, pl.n_wave_band, pl.wave_ring ? 1 : 0, pl.band_expected[0], pl.band_expected[1]};
+    for (int i = 0; i < n_info && i < FDTD2D_PLAN_INFO_WORDS; ++i) info[i] = v[i];
     return 0;
 }
 
@@ -1667,10 +2045,8 @@ static int halo_block_impl(fdtd2d_sim* s, int state, int field, int side, void**
     const size_t row_bytes = s->pitch * s->esize;
     const int h = s->halo;
     // local rows: [0,h) top ghosts | owned | [Rl-h, Rl) bottom ghosts
-    const int own_first = s->has_top_nb ? h : 0;
-    const int own_last = s->Rl - (s->has_bot_nb ? h : 0);  // one past
-    const int send_row = side == 0 ? own_first : own_last - h;
-    const int recv_row = side == 0 ? 0 : own_last;
+    const int send_row = side == 0 ? own_first(s) : own_last(s) - h;
+    const int recv_row = side == 0 ? 0 : own_last(s);
     if (send_ptr) *send_ptr = base + (size_t)send_row * row_bytes;
     if (recv_ptr) *recv_ptr = base + (size_t)recv_row * row_bytes;
     if (nbytes) *nbytes = (size_t)h * row_bytes;
@@ -1692,14 +2068,13 @@ int fdtd2d_pass_begin(fdtd2d_sim* s, int k) {
     REQUIRE(k >= 1 && k <= FDTD2D_MAX_K && k <= std::max(1, s->halo), "k must be in [1, min(halo, %d)]", FDTD2D_MAX_K);
     REQUIRE(s->open_pass_k == 0, "a pass is already open");
     if (!s->coeffs_set || !s->mur_set) return fail(FDTD2D_ESTATE, "coefficients / Mur coefficient not set");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     const int all = FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC;
     int rc;
     if (uses_hybrid(s, all))
         rc = launch_hybrid(s, k, 1);
-    else  // no band split for the generic-only paths: do the whole pass now
-        rc = s->dtype == FDTD2D_F64 ? (s->variant != 1 ? launch_edge_all_f64(s, k) : launch_generic_all<double>(s, k, all))
-                                    : launch_generic_all<float>(s, k, all);
+    else  // no band split for the generic kernel: do the whole pass now
+        rc = s->dtype == FDTD2D_F64 ? launch_generic_all<double>(s, k, all) : launch_generic_all<float>(s, k, all);
     if (rc) return rc;
     s->open_pass_k = k;
     return 0;
@@ -1708,20 +2083,115 @@ int fdtd2d_pass_begin(fdtd2d_sim* s, int k) {
 int fdtd2d_pass_end(fdtd2d_sim* s) {
     REQUIRE(s, "handle is null");
     REQUIRE(s->open_pass_k > 0, "no open pass");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     const int k = s->open_pass_k;
     if (uses_hybrid(s, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC))
         if (int rc = launch_hybrid(s, k, 2)) return rc;
     s->open_pass_k = 0;
     s->cur ^= 1;
     s->passes += 1;
+    if (peer_mode(s)) s->pass_seq += 1;
     s->step += k;
+    return 0;
+}
+
+// ---- peer links: the halo exchange inside the stepping kernels (NVLink peer stores + flags) ----------------------
+int fdtd2d_peer_export(fdtd2d_sim* s, void* blob) {
+    REQUIRE(s && blob, "null argument");
+    REQUIRE(s->has_top_nb || s->has_bot_nb, "not a slab handle");
+    USE_DEVICE(s);
+    PeerBlob b;
+    memset(&b, 0, sizeof b);
+    b.magic = PEER_MAGIC;
+    b.pid = (int32_t)getpid();
+    b.device = s->device, b.dtype = s->dtype, b.Rg = s->Rg, b.C = s->C, b.row0 = s->row0, b.Rl = s->Rl;
+    b.row_begin = s->row_begin, b.row_end = s->row_end, b.halo = s->halo, b.cur = s->cur;
+    b.pitch = s->pitch;
+    void* ptrs[7] = {s->field[0][0], s->field[0][1], s->field[0][2], s->field[1][0], s->field[1][1], s->field[1][2], s->d_slab_flags};
+    for (int i = 0; i < 7; ++i) {
+        b.ptr[i] = reinterpret_cast<uint64_t>(ptrs[i]);
+        CUDA_TRY(cudaIpcGetMemHandle(&b.ipc[i], ptrs[i]));
+    }
+    memset(blob, 0, FDTD2D_PEER_BLOB_BYTES);
+    memcpy(blob, &b, sizeof b);
+    return 0;
+}
+
+int fdtd2d_peer_attach(fdtd2d_sim* s, int side, const void* blob) {
+    REQUIRE(s && blob && (side == 0 || side == 1), "bad argument");
+    REQUIRE(side == 0 ? s->has_top_nb : s->has_bot_nb, "no neighbour on that side");
+    REQUIRE(s->variant != 1, "the generic kernel (variant 1) does not take part in the peer halo exchange");
+    PeerBlob b;
+    memcpy(&b, blob, sizeof b);
+    REQUIRE(b.magic == PEER_MAGIC, "not a peer blob");
+    REQUIRE(b.dtype == s->dtype && b.Rg == s->Rg && b.C == s->C && b.pitch == s->pitch && b.halo == s->halo,
+            "the neighbour is a slab of a different grid (%d x %d, dtype %d, halo %d)", b.Rg, b.C, b.dtype, b.halo);
+    REQUIRE(side == 0 ? b.row_end == s->row_begin : b.row_begin == s->row_end, "the neighbour's rows [%d, %d) do not touch mine [%d, %d) on that side",
+            b.row_begin, b.row_end, s->row_begin, s->row_end);
+    REQUIRE(b.cur == s->cur, "the neighbour has stepped a different number of passes: attach before stepping");
+    USE_DEVICE(s);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    peer_close(s, side);
+    PeerLink pe;
+    pe.row0 = b.row0;
+    pe.device = b.device;
+    void* ptrs[7];
+    if (b.pid == (int32_t)getpid()) {  // same process: the pointers are valid as they are
+        if (b.device != s->device) {
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, s->device, b.device));
+            REQUIRE(can, "device %d cannot access device %d", s->device, b.device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled)
+                cudaGetLastError();
+            else
+                CUDA_TRY(e);
+        }
+        for (int i = 0; i < 7; ++i) ptrs[i] = reinterpret_cast<void*>(b.ptr[i]);
+    } else {
+        for (int i = 0; i < 7; ++i) {
+            const cudaError_t e = cudaIpcOpenMemHandle(&ptrs[i], b.ipc[i], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                for (int j = 0; j < i; ++j) cudaIpcCloseMemHandle(ptrs[j]);
+                return fail(FDTD2D_ECUDA, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+            }
+        }
+        pe.ipc = true;
+    }
+    for (int i = 0; i < 6; ++i) pe.field[i / 3][i % 3] = ptrs[i];
+    pe.flags = static_cast<unsigned*>(ptrs[6]);
+    pe.attached = true;
+    s->peer[side] = pe;
+    free_plans(s);
+    return 0;
+}
+
+int fdtd2d_peer_detach(fdtd2d_sim* s) {
+    REQUIRE(s, "handle is null");
+    USE_DEVICE(s);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    peer_close(s, 0);
+    peer_close(s, 1);
+    return 0;
+}
+
+int fdtd2d_peer_status(fdtd2d_sim* s, uint32_t* flags_out) {
+    REQUIRE(s && flags_out, "null argument");
+    USE_DEVICE(s);
+    flags_out[0] = (s->peer[0].attached ? 1u : 0u) | (s->peer[1].attached ? 2u : 0u);
+    flags_out[1] = s->pass_seq;
+    unsigned f[FLAG_WORDS] = {0};
+    if (s->d_slab_flags) {
+        CUDA_TRY(cudaMemcpyAsync(f, s->d_slab_flags, sizeof f, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    flags_out[2] = f[FLAG_IN_TOP], flags_out[3] = f[FLAG_IN_BOT], flags_out[4] = f[FLAG_ERR];
     return 0;
 }
 
 int fdtd2d_set_snapshot_background(fdtd2d_sim* s, const unsigned char* gray, const double* lut) {
     REQUIRE(s && gray && lut, "null argument");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     const size_t n = (size_t)s->Rl * s->C * s->batch;
     if (!s->d_gray) {
         CUDA_TRY(cudaMalloc(&s->d_gray, n));
@@ -1737,9 +2207,9 @@ int fdtd2d_set_snapshot_background(fdtd2d_sim* s, const unsigned char* gray, con
 int fdtd2d_render_snapshot(fdtd2d_sim* s, int grid, double vmin, double vmax, unsigned char* out_rgb) {
     REQUIRE(s && out_rgb && grid >= 0 && grid < s->batch, "bad argument");
     if (!s->d_gray) return fail(FDTD2D_ESTATE, "snapshot background not set");
-    if (int rc = use_device(s)) return rc;
+    USE_DEVICE(s);
     const long long n = (long long)s->Rl * s->C;
-    const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    const int blocks = (int)std::min<long long>((n + 255) / 256, sm_count(s) * 8);
     const unsigned char* gray = s->d_gray + (size_t)grid * n;
     if (s->dtype == FDTD2D_F32) {
         const float* ez = static_cast<const float*>(s->field[s->cur][0]) + (size_t)grid * s->grid_elems;

@@ -79,7 +79,86 @@ template <typename T> struct PassParams {
     int n_probe;
     T* trace;  // [trace_cap][n_probe]
     long long trace_cap;
+    // ---- y-slabs ----------------------------------------------------------------------
+    int org;                 // local row where the tile grid starts (= first owned row: ghost rows are halo, never core)
+    int store_lo, store_hi;  // local rows this handle stores: its owned rows
+    int band_lo[2], band_hi[2];  // local rows next to the top / bottom neighbour whose results the neighbour needs (its ghost rows)
+    // peer mode: the tasks that produce band rows store them into the neighbour's ghost rows as well (NVLink peer stores)
+    // and the last one to finish raises the neighbour's flag; the tasks that read ghost rows wait for their own flag.
+    T* peer_out[2][3];        // the state set the neighbour's pass is writing (mapped peer memory); null = no peer protocol
+    long long peer_shift[2];  // element offset: my local offset + shift = the same cell in the neighbour's arrays
+    unsigned* flags;          // this handle's flag block (FLAG_* below); the IN words are written by the neighbours
+    unsigned* peer_flag[2];   // the word of the neighbour's block that I raise (its IN word for my side)
+    int band_expected[2];     // band tasks (wavefront runs + edge tiles) per side in this pass
+    unsigned seq;             // sequence number of the state this pass reads (passes since the handle was created)
 };
+
+// Flag block of a slab handle: 8 words of device memory.  IN_TOP / IN_BOT = sequence number of the newest state whose
+// ghost rows the top / bottom neighbour has delivered; CNT_* = band tasks of the running pass that are done (reset by
+// the host before every pass); ERR != 0: a wait for a neighbour timed out (reported by fdtd2d_sync).
+enum { FLAG_IN_TOP = 0, FLAG_IN_BOT = 1, FLAG_CNT_TOP = 2, FLAG_CNT_BOT = 3, FLAG_ERR = 4, FLAG_WORDS = 8 };
+constexpr unsigned long long HALO_WAIT_NS = 2000000000ull;  // give up on a neighbour after 2 s instead of hanging the GPU
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// the neighbour's arrays of side 0 or 1 (selects, not indexed parameter loads: a run-time index would move the parameter
+// block onto the stack)
+template <typename T> __device__ __forceinline__ T* peer_field(const PassParams<T>& p, int side, int f) {
+    return side ? p.peer_out[1][f] : p.peer_out[0][f];
+}
+template <typename T> __device__ __forceinline__ long long peer_shift(const PassParams<T>& p, int side) {
+    return side ? p.peer_shift[1] : p.peer_shift[0];
+}
+
+// Which band a local row belongs to: 0 top, 1 bottom, -1 none.
+template <typename T> __device__ __forceinline__ int band_of_row(const PassParams<T>& p, int row) {
+    if (row >= p.band_lo[0] && row < p.band_hi[0]) return 0;
+    if (row >= p.band_lo[1] && row < p.band_hi[1]) return 1;
+    return -1;
+}
+
+// A task that reads ghost rows of `side` calls this (every thread, before its first load): the neighbour's band tasks of
+// the previous pass have stored those rows once its flag has reached the sequence number of the state this pass reads.
+// Every thread does its own acquire load, so its later loads are ordered behind it without relying on a barrier.
+// (parameter arrays are read through selects: a run-time index would move the parameter block onto the stack)
+template <typename T> __device__ __forceinline__ void band_wait(const PassParams<T>& p, int side) {
+    if (!(side ? p.peer_out[1][0] : p.peer_out[0][0])) return;
+    const unsigned* f = p.flags + FLAG_IN_TOP + side;
+    if ((int)(ld_acquire_sys(f) - p.seq) >= 0) return;
+    const unsigned long long t0 = globaltimer_ns();
+    while ((int)(ld_acquire_sys(f) - p.seq) < 0) {
+        if (ld_acquire_sys(p.flags + FLAG_ERR)) return;  // somebody already gave up: do not wait 2 s per task
+        __nanosleep(256);
+        if (globaltimer_ns() - t0 > HALO_WAIT_NS) {
+            atomicExch(p.flags + FLAG_ERR, 1u + (unsigned)side);
+            return;
+        }
+    }
+}
+
+// One thread of a band task calls this after ALL threads of the task have issued their mirrored stores, executed
+// __threadfence_system() and synchronised (warp or CTA barrier): counts the task; the last task of the side publishes.
+template <typename T> __device__ __forceinline__ void band_done(const PassParams<T>& p, int side) {
+    if (!(side ? p.peer_out[1][0] : p.peer_out[0][0])) return;
+    __threadfence_system();  // cumulative: covers the stores of the threads this one has synchronised with
+    const unsigned done = atomicAdd(p.flags + FLAG_CNT_TOP + side, 1u) + 1u;
+    if (done == (unsigned)(side ? p.band_expected[1] : p.band_expected[0])) {
+        __threadfence_system();
+        st_release_sys(side ? p.peer_flag[1] : p.peer_flag[0], p.seq + 1u);
+    }
+}
 
 // Counter-based uniform in [0,1) with 24 random bits (exact in fp32): splitmix64 finaliser over
 // (seed, grid, row, col).  Same code runs on host (fdtd2d_hash_uniform) and device.

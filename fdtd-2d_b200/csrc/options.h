@@ -1,0 +1,86 @@
+// Per-handle tuning options of libfdtd2d (host only).  A handle copies the defaults when it is created -- the defaults
+// come from the FDTD2D_* environment variables, read ONCE at that moment -- and fdtd2d_set_option changes them for that
+// handle alone afterwards, so nothing on the stepping path calls getenv() and two host threads driving two handles
+// never share mutable state.
+#pragma once
+#include <cctype>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+namespace fdtd2d {
+
+struct Options {
+    int wavefront = 1;         // k = 8 / 12 passes (fp64: 4 / 6 / 8) of large grids on the row-streaming wavefront kernel
+    int wave_min_tiles = -1;   // plain fp32-sized tiles (48 x 112 cells) from which the wavefront takes over; -1: 0.4 per warp of the GPU
+    int ring_min_tiles = -1;   // ... from which the left / right Mur ring rides along the wavefront; -1: 2 per warp
+    int ring_strips = 1;       // left / right ring strips on the wavefront at all
+    int wave_run_rows = 640;   // cap on the rows of one wavefront run
+    int auto_k12 = 0;          // k_temporal = 0 picks the 12-level wavefront when it exists (uniform permeability)
+    int uniform_ch = 1;        // pass dt/(mu*dx) as a scalar when the map is uniform
+    int resident = 1;          // cluster-resident kernel for small fp32 grids
+    int resident_cfg = 0;      // its shape (index into kResCfgs)
+    int resident_cluster = 0;  // CTAs per grid (0: as few as fit)
+    int resident_trim = -1;    // rows the first / last CTA of a cluster hold fewer than the others (-1: 4 x rows per thread)
+    int tma_pair = 0;          // pairwise mbarriers instead of CTA barriers in the TMA tile kernel
+    int f64_k = 0;             // default k_temporal of fp64 handles (0: 8 on the wavefront, else 4)
+    int debug = 0;             // print launch geometry to stderr
+};
+
+struct OptionKey {
+    const char* name;
+    int Options::*field;
+};
+
+inline const OptionKey* option_keys(int* n) {
+    static const OptionKey keys[] = {
+        {"wavefront", &Options::wavefront},
+        {"wave_min_tiles", &Options::wave_min_tiles},
+        {"ring_min_tiles", &Options::ring_min_tiles},
+        {"ring_strips", &Options::ring_strips},
+        {"wave_run_rows", &Options::wave_run_rows},
+        {"auto_k12", &Options::auto_k12},
+        {"uniform_ch", &Options::uniform_ch},
+        {"resident", &Options::resident},
+        {"resident_cfg", &Options::resident_cfg},
+        {"resident_cluster", &Options::resident_cluster},
+        {"resident_trim", &Options::resident_trim},
+        {"tma_pair", &Options::tma_pair},
+        {"f64_k", &Options::f64_k},
+        {"debug", &Options::debug},
+    };
+    *n = (int)(sizeof(keys) / sizeof(keys[0]));
+    return keys;
+}
+
+inline const OptionKey* find_option(const char* name) {
+    int n = 0;
+    const OptionKey* keys = option_keys(&n);
+    for (int i = 0; i < n; ++i)
+        if (name && strcmp(name, keys[i].name) == 0) return &keys[i];
+    return nullptr;
+}
+
+// Defaults for a new handle: FDTD2D_<KEY> for every key above, plus the negative spellings of round 1
+// (FDTD2D_NO_RESIDENT, FDTD2D_NO_RING_STRIPS, FDTD2D_NO_UNIFORM_CH).
+inline Options options_from_env() {
+    Options o;
+    int n = 0;
+    const OptionKey* keys = option_keys(&n);
+    for (int i = 0; i < n; ++i) {
+        std::string env = "FDTD2D_";
+        for (const char* c = keys[i].name; *c; ++c) env += (char)toupper((unsigned char)*c);
+        if (const char* v = getenv(env.c_str()))
+            if (*v) o.*(keys[i].field) = atoi(v);
+    }
+    auto on = [](const char* name) {
+        const char* v = getenv(name);
+        return v && atoi(v) != 0;
+    };
+    if (on("FDTD2D_NO_RESIDENT")) o.resident = 0;
+    if (on("FDTD2D_NO_RING_STRIPS")) o.ring_strips = 0;
+    if (on("FDTD2D_NO_UNIFORM_CH")) o.uniform_ch = 0;
+    return o;
+}
+
+}  // namespace fdtd2d

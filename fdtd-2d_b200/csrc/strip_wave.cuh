@@ -1,23 +1,30 @@
-// Row-streaming wavefront kernels (fp32): K leapfrog steps per HBM round trip with redundancy only in the COLUMN halo.
-// Two forms: strip_wave_kernel (scalar arithmetic, plain regions only) and, further down, strip_wave_x2_kernel -- the
-// default -- with sm_100a's two-wide fp32 instructions and, in its LR form, the left / right Mur ring riding along.
+// Row-streaming wavefront kernels: K leapfrog steps per HBM round trip with redundancy only in the COLUMN halo.
+// Two forms: strip_wave_x2_kernel (fp32, sm_100a's two-wide fp32 instructions; in its LR form the left / right Mur ring
+// rides along) and strip_wave_kernel (scalar arithmetic, used for fp64: two columns per lane, 64-column strips).
 //
 // The overlapped tiles of tile_tma.cuh recompute a halo of K rows above and below every 64-row tile (core 48 x 112 of
-// 64 x 128: 34 % of the arithmetic is thrown away at K = 8).  Here one WARP owns a strip of 128 columns (core 112) and
-// marches down a long run of rows, carrying all K time levels of a sliding window of rows in its REGISTERS:
+// 64 x 128: 34 % of the arithmetic is thrown away at K = 8).  Here one WARP owns a strip of 32 x 16 bytes of columns
+// (fp32: 128 columns, core 112 at K = 8) and marches down a long run of rows, carrying all K time levels of a sliding
+// window of rows in its REGISTERS:
 //   level 0 row i arrives from HBM; for s = 0..K-1 the row stored at level s (row i-s-1) and the arriving one (row i-s)
 //   give level s+1 of row i-s-1 (H half-step main.py:69-74, then the interior Ez update main.py:21-27, which takes
 //   Hx of the row above from the row stored at level s+1); that result is the arriving row of the next level; what
 //   leaves level K-1 is row i-K advanced K steps and goes straight to HBM.
-// So every row is loaded once, stepped K times and stored once; the only recomputation is the 8 halo columns on each
-// side of the strip (12.5 %) and K warm-up rows per run of rows (< 4 %).  A warp never talks to another warp: no
-// __syncthreads, no shared-memory exchange of field rows; column neighbours come from two shuffles per row and level.
-// Rows are prefetched three iterations ahead with cp.async (16 B per lane and array) into a small per-warp ring; the
-// coefficient rows stay in their ring until the last level has used them (K rows later).  Runs of rows are handed
+// So every row is loaded once, stepped K times and stored once; the only recomputation is the halo columns on each
+// side of the strip (12.5 % at K = 8 in fp32) and K warm-up rows per run of rows (< 4 %).  A warp never talks to another
+// warp: no __syncthreads, no shared-memory exchange of field rows; column neighbours come from two shuffles per row and
+// level.  Rows are prefetched three iterations ahead with cp.async (16 B per lane and array) into a small per-warp ring;
+// the coefficient rows stay in their ring until the last level has used them (K rows later).  Runs of rows are handed
 // out to the warps dynamically (one atomic per run).
 // Cells next to the strip's edge columns and above the first / below the last row of the run read neighbours that are
 // missing; they go stale one cell per level exactly as in the overlapped tiles and are never stored.
 // Arithmetic and results are bit-identical to the other kernels (same operations, same order).
+//
+// y-slabs (SLAB instantiations): a run whose rows are a slab's BAND (the `halo` owned rows next to a neighbour slab) first
+// waits until that neighbour has delivered the ghost rows it reads, stores its result rows into the neighbour's ghost
+// rows as well (peer stores over NVLink) and, when it is the last band task of its side, raises the neighbour's flag
+// (common.cuh: band_wait / band_done).  Band runs come first in the task list, so the exchange is over long before the
+// pass is.
 #pragma once
 #include "common.cuh"
 #include "tile_edge.cuh"
@@ -28,150 +35,189 @@ constexpr int WAVE_NW = 8;      // warps per CTA: 2 per scheduler, each may use 
 constexpr int WAVE_P = 3;       // rows prefetched ahead at K = 8 (6 was measured: no gain); K = 12 uses 2 so the ring still fits
 constexpr int WAVE_NF = 4;      // rows of the field ring (a power of two > P)
 constexpr int WAVE_NC = 16;     // rows of the coefficient ring (a power of two >= K + P + 2)
-constexpr int WAVE_TW = 128;    // strip width (columns per warp)
+constexpr int WAVE_ROW_BYTES = 512;  // one ring row of one array: 16 bytes per lane (128 fp32 / 64 fp64 columns)
+constexpr int WAVE_TW = 128;    // fp32 strip width (columns per warp)
 
-// one run of rows of one strip: grid b, haloed strip starts at column x0, rows [y0, y1) are stored.
-// Ring strips (side != 0, wave_run_x2<.., LR = true>) also say which of their 128 columns they store: [c0, c1).
+// one run of rows of one strip: grid b, the strip's first column is x0, rows [y0, y1) are stored, of the strip's columns
+// [c0, c1) (strip coordinates; whole 16-byte groups).
 struct WaveTask {
     int32_t b, x0, y0, y1;
-    int32_t c0, c1, side, pad;  // side: 0 plain strip, 1 holds the left Mur ring (columns 0..4), 2 the right one
+    int32_t c0, c1;
+    int32_t side;  // 0 plain strip, 1 holds the left Mur ring (columns 0..4), 2 the right one
+    int32_t band;  // 0, or 1 / 2: the rows are the band next to the top / bottom neighbour slab
 };
 
-// per warp: NF rows of the three fields + NC rows of dt/(eps*dx) (+ NC rows of dt/(mu*dx) unless that is a scalar:
-// the packed kernel then leaves the second ring out)
-__host__ __device__ constexpr size_t wave_smem_bytes(int warps = WAVE_NW, bool no_ch_ring = false) {
-    return (size_t)warps * (WAVE_NF * 3 + WAVE_NC * (no_ch_ring ? 1 : 2)) * WAVE_TW * sizeof(float);
+// per warp: NF rows of the three fields + NC rows of dt/(eps*dx) (+ NC rows of dt/(mu*dx) unless that is a scalar)
+__host__ __device__ constexpr size_t wave_smem_bytes(int warps, bool no_ch_ring) {
+    return (size_t)warps * (WAVE_NF * 3 + WAVE_NC * (no_ch_ring ? 1 : 2)) * WAVE_ROW_BYTES;
 }
 
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
                  : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// UCH: dt/(mu*dx) is the same in every cell (true for every material_init output, main.py:105,121): it comes as a
-// kernel argument and the map is neither fetched nor kept in the ring.
-template <int K, bool UCH, int P>
-__global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassParams<float> p, const WaveTask* tasks, const int n_tasks, int* ticket, const float ch_uniform) {
-    constexpr int TW = WAVE_TW, NF = WAVE_NF, NC = WAVE_NC;
-    static_assert((NF & (NF - 1)) == 0 && NF > P && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
+// 16 bytes <-> registers
+__device__ __forceinline__ void ld16(const float* p, float (&a)[4]) { unpack4(*reinterpret_cast<const float4*>(p), a); }
+__device__ __forceinline__ void ld16(const double* p, double (&a)[2]) {
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    a[0] = v.x, a[1] = v.y;
+}
+__device__ __forceinline__ void st16(float* p, const float (&a)[4]) { *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]); }
+__device__ __forceinline__ void st16(double* p, const double (&a)[2]) { *reinterpret_cast<double2*>(p) = make_double2(a[0], a[1]); }
+
+// ---- scalar form (fp64; also valid for fp32) ---------------------------------------------------------------------------
+// One run of rows of one strip, K levels deep.  UCH: dt/(mu*dx) is the same in every cell (true for every material_init
+// output, main.py:105,121): it comes as a kernel argument and the map is neither fetched nor kept in the ring.
+// The window: two register sets X, Y that swap roles every iteration so that no row is ever moved.  In an iteration
+// ST[s] (s < K) is the row stored at level s (row i-s-1 when row i arrives), ST[K][1] the Hx of the last row that left;
+// AR[0] receives the arriving level-0 row and AR[s+1] the result of level s, i.e. the row arriving at level s+1.  After
+// the iteration the arrived rows ARE the stored rows: the sets swap.
+template <typename T, int K, bool UCH, int P, bool BAND>
+__device__ __forceinline__ void wave_run_scalar(const PassParams<T>& p, const WaveTask& tk, T* fring, T* cring, const int l, const T ch_uniform) {
+    constexpr int NQ = 16 / (int)sizeof(T), TW = 32 * NQ, NF = WAVE_NF, NC = WAVE_NC, CS = UCH ? 1 : 2;
     constexpr unsigned FULL = 0xffffffffu;
+    const bool core = NQ * l >= tk.c0 && NQ * l < tk.c1;
+    const int side = tk.band - 1;
+    if (BAND) band_wait(p, side);
+    // j counts the level-0 rows of the run, `of` is the element offset of the next row to fetch and moves one row per
+    // iteration; the row that leaves level K-1 in iteration j is K rows behind the arriving one, i.e. P + 1 + K rows behind `of`
+    const int n = tk.y1 - tk.y0 + 2 * K;  // level-0 rows [y0 - K, y1 + K)
+    long long of = (long long)tk.b * p.grid_stride + tk.x0 + NQ * l + (long long)(tk.y0 - K) * p.pitch;
+    auto fetch = [&](int fs, int cs) {
+        cp_async16(fring + (fs * 3 + 0) * TW, p.in[0] + of);
+        cp_async16(fring + (fs * 3 + 1) * TW, p.in[1] + of);
+        cp_async16(fring + (fs * 3 + 2) * TW, p.in[2] + of);
+        cp_async16(cring + (cs * CS + 0) * TW, p.ce + of);
+        if (!UCH) cp_async16(cring + (cs * CS + 1) * TW, p.ch + of);
+    };
+    T X[K + 1][3][NQ], Y[K + 1][3][NQ];
+#pragma unroll
+    for (int s = 0; s <= K; ++s)
+#pragma unroll
+        for (int f = 0; f < 3; ++f)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) X[s][f][q] = Y[s][f][q] = (T)0;
+    // Row y0-K-1 (the row "stored" at level 0 before the first arrival) does not exist as data; its coefficient slot
+    // (slot 0) is read by level 0 in the first iteration: give it zeros.
+    int fs = 0, cs = 1;
+    {
+        T z[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) z[q] = (T)0;
+        st16(cring + 0 * TW, z);
+        if (!UCH) st16(cring + 1 * TW, z);
+    }
+#pragma unroll
+    for (int d = 0; d < P; ++d) {
+        fetch(fs, cs);
+        of += p.pitch;
+        cp_async_commit();
+        fs = (fs + 1) & (NF - 1);
+        cs = (cs + 1) & (NC - 1);
+    }
+    int fr = 0, cr = 0;
+    auto iter = [&](T (&ST)[K + 1][3][NQ], T (&AR)[K + 1][3][NQ], const int j) {
+        if (j + P < n) fetch(fs, cs);
+        of += p.pitch;
+        cp_async_commit();  // (an empty group keeps the wait count uniform at the end of the run)
+        fs = (fs + 1) & (NF - 1);
+        cs = (cs + 1) & (NC - 1);
+        cp_async_wait<P>();  // the arriving row has landed (every lane reads back only the 16 bytes it copied itself)
+        ld16(fring + (fr * 3 + 0) * TW, AR[0][0]);
+        ld16(fring + (fr * 3 + 1) * TW, AR[0][1]);
+        ld16(fring + (fr * 3 + 2) * TW, AR[0][2]);
+        fr = (fr + 1) & (NF - 1);
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            T ce[NQ], ch[NQ];
+            const int c = (cr - s) & (NC - 1);  // coefficient slot of row i-s-1
+            ld16(cring + (c * CS + 0) * TW, ce);
+            if (UCH) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) ch[q] = ch_uniform;
+            } else {
+                ld16(cring + (c * CS + 1) * TW, ch);
+            }
+            const T right_nb = __shfl_down_sync(FULL, ST[s][0][0], 1);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {  // H half-step of the stored row (main.py:69-74)
+                const T right = q < NQ - 1 ? ST[s][0][q < NQ - 1 ? q + 1 : q] : right_nb;
+                AR[s + 1][1][q] = sub_rn(ST[s][1][q], mul_rn(ch[q], sub_rn(AR[s][0][q], ST[s][0][q])));
+                AR[s + 1][2][q] = add_rn(ST[s][2][q], mul_rn(ch[q], sub_rn(right, ST[s][0][q])));
+            }
+            const T left_nb = __shfl_up_sync(FULL, AR[s + 1][2][NQ - 1], 1);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {  // its Ez update (main.py:21-27); Hx of the row above is one level up
+                const T left = q > 0 ? AR[s + 1][2][q > 0 ? q - 1 : 0] : left_nb;
+                const T curl = sub_rn(sub_rn(AR[s + 1][2][q], left), sub_rn(AR[s + 1][1][q], ST[s + 1][1][q]));
+                AR[s + 1][0][q] = add_rn(ST[s][0][q], mul_rn(curl, ce[q]));
+            }
+        }
+        cr = (cr + 1) & (NC - 1);
+        if (core && j >= 2 * K) {  // row y0 + (j - 2K) < y1 has left level K-1, K steps on
+            const long long o = of - (long long)(P + 1 + K) * p.pitch;
+            st16(p.out[0] + o, AR[K][0]);
+            st16(p.out[1] + o, AR[K][1]);
+            st16(p.out[2] + o, AR[K][2]);
+            if (BAND) {
+                T* const q0 = peer_field(p, side, 0);
+                if (q0) {
+                    const long long po = o + peer_shift(p, side);
+                    st16(q0 + po, AR[K][0]);
+                    st16(peer_field(p, side, 1) + po, AR[K][1]);
+                    st16(peer_field(p, side, 2) + po, AR[K][2]);
+                }
+            }
+        }
+    };
+    int j = 0;
+#pragma unroll 1
+    for (; j + 1 < n; j += 2) {
+        iter(X, Y, j);
+        iter(Y, X, j + 1);
+    }
+    if (j < n) iter(X, Y, j);
+    cp_async_wait<0>();
+    if (BAND) {
+        __threadfence_system();
+        __syncwarp();
+        if (l == 0) band_done(p, side);
+    }
+    __syncwarp();  // the ring is reused by the next run
+}
+
+template <typename T, int K, bool UCH, int P, bool SLAB>
+__global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassParams<T> p, const WaveTask* tasks, const int n_tasks, int* ticket, const T ch_uniform) {
+    constexpr int NQ = 16 / (int)sizeof(T), TW = 32 * NQ, NF = WAVE_NF, NC = WAVE_NC, CS = UCH ? 1 : 2;
+    static_assert((NF & (NF - 1)) == 0 && NF > P && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
     extern __shared__ __align__(16) unsigned char smem_wave[];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    float* fring = reinterpret_cast<float*>(smem_wave) + (size_t)w * (NF * 3 + NC * 2) * TW + 4 * l;  // [NF][3][TW], my 4 columns
-    float* cring = fring + NF * 3 * TW;                                                              // [NC][2][TW]
-    const bool core = 4 * l >= p.hx && 4 * l < p.hx + p.CW;
-
+    T* fring = reinterpret_cast<T*>(smem_wave) + (size_t)w * (NF * 3 + NC * CS) * TW + NQ * l;  // [NF][3][TW], my 16 bytes
+    T* cring = fring + NF * 3 * TW;                                                           // [NC][CS][TW]
     for (;;) {  // runs are handed out dynamically: a warp takes the next one as soon as it is done
         int t = 0;
         if (l == 0) t = atomicAdd(ticket, 1);
-        t = __shfl_sync(FULL, t, 0);
+        t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n_tasks) break;
         const WaveTask tk = tasks[t];
-        const long long base = (long long)tk.b * p.grid_stride + tk.x0 + 4 * l;
-        const int i0 = tk.y0 - K, i1 = tk.y1 + K;  // level-0 rows [i0, i1)
-        auto fetch = [&](int row, int fs, int cs) {  // row -> ring slots fs (fields), cs (coefficients)
-            const long long o = base + (long long)row * p.pitch;
-            cp_async16(fring + (fs * 3 + 0) * TW, p.in[0] + o);
-            cp_async16(fring + (fs * 3 + 1) * TW, p.in[1] + o);
-            cp_async16(fring + (fs * 3 + 2) * TW, p.in[2] + o);
-            cp_async16(cring + (cs * 2 + 0) * TW, p.ce + o);
-            if (!UCH) cp_async16(cring + (cs * 2 + 1) * TW, p.ch + o);
-        };
-        // The window: two register sets X, Y that swap roles every iteration so that no row is ever moved.  In an
-        // iteration ST[s] (s < K) is the row stored at level s (row i-s-1 when row i arrives), ST[K][1] the Hx of the
-        // last row that left; AR[0] receives the arriving level-0 row and AR[s+1] the result of level s, i.e. the row
-        // arriving at level s+1.  After the iteration the arrived rows ARE the stored rows: the sets swap.
-        float X[K + 1][3][4], Y[K + 1][3][4];
-#pragma unroll
-        for (int s = 0; s <= K; ++s)
-#pragma unroll
-            for (int f = 0; f < 3; ++f)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) X[s][f][q] = Y[s][f][q] = 0.0f;
-        // Row i0-1 (the row "stored" at level 0 before the first arrival) does not exist as data; its coefficient slot
-        // is read by level 0 in the first iteration: give it zeros.
-        int fs = 0, cs = 1;  // slots of the next row to FETCH; the coefficient slot of row i0-1 is 0
-        {
-            const float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            store4(cring + 0 * TW, z);
-            store4(cring + 1 * TW, z);
-        }
-#pragma unroll
-        for (int d = 0; d < P; ++d) {
-            fetch(i0 + d, fs, cs);
-            cp_async_commit();
-            fs = (fs + 1) & (NF - 1);
-            cs = (cs + 1) & (NC - 1);
-        }
-        int fr = 0;  // field slot of the arriving row
-        int cr = 0;  // coefficient slot of row i-1 (level 0's stored row)
-        auto iter = [&](float (&ST)[K + 1][3][4], float (&AR)[K + 1][3][4], const int i) {
-            if (i + P < i1) fetch(i + P, fs, cs);
-            cp_async_commit();  // (an empty group keeps the wait count uniform at the end of the run)
-            fs = (fs + 1) & (NF - 1);
-            cs = (cs + 1) & (NC - 1);
-            cp_async_wait<P>();  // row i has landed (every lane reads back only the 16 bytes it copied itself)
-            load4(fring + (fr * 3 + 0) * TW, AR[0][0]);
-            load4(fring + (fr * 3 + 1) * TW, AR[0][1]);
-            load4(fring + (fr * 3 + 2) * TW, AR[0][2]);
-            fr = (fr + 1) & (NF - 1);
-#pragma unroll
-            for (int s = 0; s < K; ++s) {
-                float ce[4], ch[4];
-                const int c = (cr - s) & (NC - 1);  // coefficient slot of row i-s-1
-                load4(cring + (c * 2 + 0) * TW, ce);
-                if (UCH)
-                    ch[0] = ch[1] = ch[2] = ch[3] = ch_uniform;
-                else
-                    load4(cring + (c * 2 + 1) * TW, ch);
-                const float right3 = __shfl_down_sync(FULL, ST[s][0][0], 1);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {  // H half-step of the stored row (main.py:69-74)
-                    const float right = q < 3 ? ST[s][0][q < 3 ? q + 1 : 3] : right3;
-                    AR[s + 1][1][q] = sub_rn(ST[s][1][q], mul_rn(ch[q], sub_rn(AR[s][0][q], ST[s][0][q])));
-                    AR[s + 1][2][q] = add_rn(ST[s][2][q], mul_rn(ch[q], sub_rn(right, ST[s][0][q])));
-                }
-                const float left0 = __shfl_up_sync(FULL, AR[s + 1][2][3], 1);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {  // its Ez update (main.py:21-27); Hx of the row above is one level up
-                    const float left = q > 0 ? AR[s + 1][2][q > 0 ? q - 1 : 0] : left0;
-                    const float curl = sub_rn(sub_rn(AR[s + 1][2][q], left), sub_rn(AR[s + 1][1][q], ST[s + 1][1][q]));
-                    AR[s + 1][0][q] = add_rn(ST[s][0][q], mul_rn(curl, ce[q]));
-                }
-            }
-            cr = (cr + 1) & (NC - 1);
-            const int r = i - K;  // the row that just left level K-1, K steps on
-            if (core && r >= tk.y0 && r < tk.y1) {
-                const long long o = base + (long long)r * p.pitch;
-                store4(p.out[0] + o, AR[K][0]);
-                store4(p.out[1] + o, AR[K][1]);
-                store4(p.out[2] + o, AR[K][2]);
-            }
-        };
-        int i = i0;
-#pragma unroll 1
-        for (; i + 1 < i1; i += 2) {
-            iter(X, Y, i);
-            iter(Y, X, i + 1);
-        }
-        if (i < i1) iter(X, Y, i);
-        cp_async_wait<0>();
-        __syncwarp();  // the ring is reused by the next run
+        if (SLAB && tk.band)
+            wave_run_scalar<T, K, UCH, P, true>(p, tk, fring, cring, l, ch_uniform);
+        else
+            wave_run_scalar<T, K, UCH, P, false>(p, tk, fring, cring, l, ch_uniform);
     }
 }
 
-// ---- packed variant: the same wavefront with Blackwell's two-wide fp32 instructions ------------------------------------
+// ---- packed form (fp32): the same wavefront with Blackwell's two-wide fp32 instructions ---------------------------------
 // sm_100a has add/sub/fma.rn.f32x2 (SASS FADD2 / FFMA2): one instruction, two IEEE round-to-nearest results on an aligned
 // register pair.  They run at half the issue rate of FADD (measured, profiles/micro/f32x2_rate.cu: 0.50 against 0.96
 // warp-instructions per clock and scheduler), i.e. the same 128 lane-operations per clock and SM, but they take half the
-// ISSUE SLOTS -- and the scalar kernel above is bound by issue (79 %), its FP pipe only 63 % busy.  A lane's four columns
+// ISSUE SLOTS -- and the scalar form is bound by issue (79 %), its FP pipe only 63 % busy.  A lane's four columns
 // are two pairs (c, c+1), (c+2, c+3), exactly as the 16-byte loads deliver them; only the two column differences, whose
-// operands straddle the pairs, stay scalar (their results land in a pair directly, so no register moves).
+// operands straddle the pairs, stay scalar (their results land in a pair directly).
 // A level is 18 packed + 8 scalar instructions + 2 shuffles instead of 44 + 2 (437 -> 362 instructions per row at K = 8).
-// At K = 8 the kernel is DRAM-bound either way (94 % of the copy bandwidth); the 12-level instance, which moves a third
-// less, needs the packed form to get level with it (1586 vs 1571 Gcell/s at 16384^2; scalar 1366) and stays opt-in.
 // Bit-exactness: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even with --fmad false (scalar code is not
 // touched), so the product is written as fma.rn.f32x2(a, b, -0) with the -0 pair coming in as a kernel argument the
 // compiler cannot see through: rn(a*b + -0) = rn(a*b) for every input incl. signed zeros, and an FFMA2 that already
@@ -194,18 +240,20 @@ __device__ __forceinline__ void store22(float* p, const u64* a) { *reinterpret_c
 // which is the reference's column-by-column loop with every read resolved (each column reads its inward neighbour
 // before that one is overwritten).  The reference's slice bounds (H: columns 0..C-2, Ez: 1..C-2) are imposed by selects
 // on the right strip, which also covers the pad columns >= C (kept as loaded: zero).
-template <int K, bool UCH, int P, bool LR>
+// BAND = true: the rows are a slab's band (see the top of the file).
+template <int K, bool UCH, int P, bool LR, bool BAND>
 __device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const WaveTask& tk, float* fring, float* cring, const int l, const u64 chu, const u64 negzero) {
     constexpr int TW = WAVE_TW, NF = WAVE_NF, NC = WAVE_NC, CS = UCH ? 1 : 2;
     constexpr unsigned FULL = 0xffffffffu;
-    bool core = 4 * l >= p.hx && 4 * l < p.hx + p.CW;
+    const bool core = 4 * l >= tk.c0 && 4 * l < tk.c1;
+    const int bside = tk.band - 1;
+    if (BAND) band_wait(p, bside);
     {
         // ring strips: which of my four columns are ring columns / beyond the reference's slices, as all-ones masks for
         // bitwise selects (one LOP3 each; predicates would have to be recomputed at every use)
         uint32_t ringm[4] = {0, 0, 0, 0}, hoffm[4] = {0, 0, 0, 0}, padm[4] = {0, 0, 0, 0};
         float coef = 0.0f;
         if (LR) {
-            core = 4 * l >= tk.c0 && 4 * l < tk.c1;
             coef = p.mur[tk.b];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -238,7 +286,7 @@ __device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const Wa
             cp_async16(cring + (cs * CS + 0) * TW, p.ce + o);
             if (!UCH) cp_async16(cring + (cs * CS + 1) * TW, p.ch + o);
         };
-        // the window of strip_wave_kernel, every row as two column pairs
+        // the window of wave_run_scalar, every row as two column pairs
         u64 X[K + 1][3][2], Y[K + 1][3][2];
 #pragma unroll
         for (int s = 0; s <= K; ++s)
@@ -281,7 +329,7 @@ __device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const Wa
                     load22(cring + (c * CS + 1) * TW, ch);
                 const u64 e0 = ST[s][0][0], e1 = ST[s][0][1];
                 // H half-step of the stored row (main.py:69-74).  The column differences straddle the pairs, so they
-                // are four scalar subtractions written straight into a pair (no register moves); the rest is two-wide.
+                // are four scalar subtractions written straight into a pair; the rest is two-wide.
                 const float right3 = __shfl_down_sync(FULL, lo2(e0), 1);
                 const u64 dx0 = pack2(sub_rn(hi2(e0), lo2(e0)), sub_rn(lo2(e1), hi2(e0)));
                 const u64 dx1 = pack2(sub_rn(hi2(e1), lo2(e1)), sub_rn(right3, hi2(e1)));
@@ -338,6 +386,15 @@ __device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const Wa
                 store22(p.out[0] + o, AR[K][0]);
                 store22(p.out[1] + o, AR[K][1]);
                 store22(p.out[2] + o, AR[K][2]);
+                if (BAND) {  // the same rows into the neighbour slab's ghost rows
+                    float* const q0 = peer_field(p, bside, 0);
+                    if (q0) {
+                        const long long po = o + peer_shift(p, bside);
+                        store22(q0 + po, AR[K][0]);
+                        store22(peer_field(p, bside, 1) + po, AR[K][1]);
+                        store22(peer_field(p, bside, 2) + po, AR[K][2]);
+                    }
+                }
             }
         };
         int j = 0;
@@ -348,14 +405,19 @@ __device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const Wa
         }
         if (j < n) iter(X, Y, j);
         cp_async_wait<0>();
+        if (BAND) {
+            __threadfence_system();
+            __syncwarp();
+            if (l == 0) band_done(p, bside);
+        }
         __syncwarp();  // the ring is reused by the next run
     }
 }
 
-// The kernel: warps take runs from one ticket; with RING the ring-strip runs come first in the task list (they are the
-// heavier ones) and go through the LR instantiation of the run, everything else through the plain one -- two separate
-// loops in one kernel, so the plain strips pay nothing for the ring code and one launch balances both.
-template <int K, bool UCH, int P, bool RING = false>
+// The kernel: warps take runs from one ticket; with RING the ring-strip runs go through the LR instantiation of the run,
+// with SLAB the band runs through the BAND one, everything else through the plain one -- separate loops in one kernel,
+// so the plain strips pay nothing for the ring / band code and one launch balances everything.
+template <int K, bool UCH, int P, bool RING, bool SLAB>
 __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const PassParams<float> p, const WaveTask* tasks, const int n_tasks, int* ticket, const float ch_uniform, const u64 negzero) {
     constexpr int TW = WAVE_TW, NF = WAVE_NF, NC = WAVE_NC, CS = UCH ? 1 : 2;  // CS: coefficient maps kept in the ring
     static_assert((NF & (NF - 1)) == 0 && NF > P && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
@@ -370,10 +432,17 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const Pa
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n_tasks) break;
         const WaveTask tk = tasks[t];
-        if (RING && tk.side != 0)
-            wave_run_x2<K, UCH, P, true>(p, tk, fring, cring, l, chu, negzero);
-        else
-            wave_run_x2<K, UCH, P, false>(p, tk, fring, cring, l, chu, negzero);
+        if (RING && tk.side != 0) {
+            if (SLAB && tk.band)
+                wave_run_x2<K, UCH, P, true, true>(p, tk, fring, cring, l, chu, negzero);
+            else
+                wave_run_x2<K, UCH, P, true, false>(p, tk, fring, cring, l, chu, negzero);
+        } else {
+            if (SLAB && tk.band)
+                wave_run_x2<K, UCH, P, false, true>(p, tk, fring, cring, l, chu, negzero);
+            else
+                wave_run_x2<K, UCH, P, false, false>(p, tk, fring, cring, l, chu, negzero);
+        }
     }
 }
 

@@ -27,6 +27,12 @@ __device__ __forceinline__ void ldg4(const double* p, double* a) {
     const double2 u = __ldg(reinterpret_cast<const double2*>(p)), v = __ldg(reinterpret_cast<const double2*>(p + 2));
     a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y;
 }
+// (L2 only: a slab's ghost rows are written by the neighbour GPU while this kernel may already be running)
+__device__ __forceinline__ void ldcg4(const float* p, float* a) { unpack4(__ldcg(reinterpret_cast<const float4*>(p)), a); }
+__device__ __forceinline__ void ldcg4(const double* p, double* a) {
+    const double2 u = __ldcg(reinterpret_cast<const double2*>(p)), v = __ldcg(reinterpret_cast<const double2*>(p + 2));
+    a[0] = u.x, a[1] = u.y, a[2] = v.x, a[3] = v.y;
+}
 __device__ __forceinline__ void store4(float* p, const float* a) {
     *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1], a[2], a[3]);
 }
@@ -51,10 +57,17 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
     const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
     const int k = p.k;
     const int li0 = w * MR, lj = 4 * l;
-    const int lr0 = ty * p.CH - k, lc0 = tx * p.CW - p.hx;
+    const int lr0 = p.org + ty * p.CH - k, lc0 = tx * p.CW - p.hx;
     const int gr0 = lr0 + p.row0;
     const int Rg = p.Rg, C = p.C;
     const long long base = (long long)b * p.grid_stride + (long long)(lr0 + li0) * p.pitch + (lc0 + lj);
+    // y-slabs: a tile whose core holds band rows reads the ghost rows of that side -- wait for the neighbour -- and
+    // mirrors those rows into the neighbour's ghost rows when it stores (common.cuh)
+    const int core_lo = lr0 + k, core_hi = min(core_lo + p.CH, p.store_hi);
+    const bool band0 = core_lo < p.band_hi[0] && core_hi > p.band_lo[0];
+    const bool band1 = core_lo < p.band_hi[1] && core_hi > p.band_lo[1];
+    if (band0) band_wait(p, 0);
+    if (band1) band_wait(p, 1);
 
     // ---- load (zero outside the local array) ------------------------------------------------
     T e[MR][4], hx[MR][4], hy[MR][4], ce[MR][4], ch[MR][4];
@@ -66,9 +79,9 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
         for (int q = 0; q < 4; ++q) e[r][q] = hx[r][q] = hy[r][q] = ce[r][q] = ch[r][q] = (T)0;
         if (col_in && row >= 0 && row < p.Rl) {
             const long long o = base + (long long)r * p.pitch;
-            ldg4(p.in[0] + o, e[r]);
-            ldg4(p.in[1] + o, hx[r]);
-            ldg4(p.in[2] + o, hy[r]);
+            ldcg4(p.in[0] + o, e[r]);
+            ldcg4(p.in[1] + o, hx[r]);
+            ldcg4(p.in[2] + o, hy[r]);
             ldg4(p.ce + o, ce[r]);
             ldg4(p.ch + o, ch[r]);
         }
@@ -221,17 +234,35 @@ __global__ void __launch_bounds__(NW * 32, 1) tile_edge_kernel(const PassParams<
         }
     }
 
-    // ---- store the core (inside the local array) ----------------------------------------------
+    // ---- store the core (owned rows only; band rows also go to the neighbour slab) --------------------------
     if (lj >= p.hx && lj < p.hx + p.CW && lc0 + lj < p.pitch) {
 #pragma unroll
         for (int r = 0; r < MR; ++r) {
-            const int li = li0 + r;
-            if (li >= k && li < k + p.CH && lr0 + li < p.Rl) {
+            const int li = li0 + r, row = lr0 + li;
+            if (li >= k && li < k + p.CH && row < p.store_hi) {
                 const long long o = base + (long long)r * p.pitch;
                 store4(p.out[0] + o, e[r]);
                 store4(p.out[1] + o, hx[r]);
                 store4(p.out[2] + o, hy[r]);
+                const int bs = band_of_row(p, row);
+                if (bs >= 0) {
+                    T* const q0 = peer_field(p, bs, 0);
+                    if (q0) {
+                        const long long po = o + peer_shift(p, bs);
+                        store4(q0 + po, e[r]);
+                        store4(peer_field(p, bs, 1) + po, hx[r]);
+                        store4(peer_field(p, bs, 2) + po, hy[r]);
+                    }
+                }
             }
+        }
+    }
+    if (band0 || band1) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            if (band0) band_done(p, 0);
+            if (band1) band_done(p, 1);
         }
     }
 }

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(NT) tile_generic_kernel(const PassParams<T> p)
     const int ty = rem / p.tiles_x;
     const int tx = rem - ty * p.tiles_x;
     const int k = p.k;
-    const int lr0 = ty * p.CH - k;      // local row held in shared row 0
+    const int lr0 = p.org + ty * p.CH - k;  // local row held in shared row 0
     const int lc0 = tx * p.CW - p.hx;   // column held in shared column 0
     const int gr0 = lr0 + p.row0;       // its global row
     const long long gbase = (long long)b * p.grid_stride;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(NT) tile_generic_kernel(const PassParams<T> p)
         const int ci = v / CWV, cv = v - ci * CWV;
         const int li = k + ci, lj = p.hx + cv * VN;
         const int r = lr0 + li, c = lc0 + lj;
-        if (r < p.Rl && c < p.pitch) {
+        if (r < p.store_hi && c < p.pitch) {
             const long long off = gbase + (long long)r * p.pitch + c;
             const int so = li * TW + lj;
             *reinterpret_cast<V*>(p.out[0] + off) = *reinterpret_cast<const V*>(cur + so);

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
         const int tile = p.tile_list[t];
         const int b = tile / per_grid, rem = tile - b * per_grid;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int x = tx * p.CW - p.hx, y = b * p.Rl + ty * p.CH - k;
+        const int x = tx * p.CW - p.hx, y = b * p.Rl + p.org + ty * p.CH - k;
         mbar_expect_tx(&full_bar, STAGE_BYTES);
         tma_load_2d(stage + 0 * N, &maps.ez, x, y, &full_bar);
         tma_load_2d(stage + 1 * N, &maps.hx, x, y, &full_bar);
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
         const int tile = p.tile_list[t];
         const int b = tile / per_grid, rem = tile - b * per_grid;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int lr0 = ty * p.CH - k, lc0 = tx * p.CW - p.hx;
+        const int lr0 = p.org + ty * p.CH - k, lc0 = tx * p.CW - p.hx;
 
         // ---- tile switch: staging area -> registers ------------------------------------------
         mbar_wait(&full_bar, parity);

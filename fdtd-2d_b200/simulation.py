@@ -123,6 +123,30 @@ class Simulation:
     def synchronize(self):
         check(lib().fdtd2d_sync(self._h))
 
+    @property
+    def cuda_stream(self) -> int:
+        """The CUDA stream handle the simulation's work is ordered on."""
+        p = ctypes.c_void_p()
+        check(lib().fdtd2d_get_stream(self._h, ctypes.byref(p)))
+        return p.value or 0
+
+    # ---- tuning options (per handle; defaults come from FDTD2D_<KEY> when the handle is created) ----
+    def set_option(self, key: str, value: int):
+        check(lib().fdtd2d_set_option(self._h, key.encode(), int(value)))
+
+    def get_option(self, key: str) -> int:
+        v = ctypes.c_int()
+        check(lib().fdtd2d_get_option(self._h, key.encode(), ctypes.byref(v)))
+        return v.value
+
+    def plan_info(self, k: int = 8) -> dict:
+        """What a k-step pass of this handle consists of (see fdtd2d_plan_info)."""
+        a = (ctypes.c_int32 * _lib.PLAN_INFO_WORDS)()
+        check(lib().fdtd2d_plan_info(self._h, k, a, _lib.PLAN_INFO_WORDS))
+        names = ("tiles_y", "tiles_x", "core_rows", "core_cols", "edge_tiles", "edge_band_tiles", "tma_tiles", "wave_runs",
+                 "wave_band_runs", "ring_strips", "band_tasks_top", "band_tasks_bottom")
+        return dict(zip(names, (int(v) for v in a)))
+
     # ---- state ------------------------------------------------------------------------------
     def set_state(self, Ez, Hx, Hy):
         """Upload Ez (R,C), Hx (R,C-1), Hy (R-1,C) -- the shapes grid_init returns (main.py:79-85)."""
@@ -150,6 +174,34 @@ class Simulation:
 
     def zero_state(self):
         check(lib().fdtd2d_zero_state(self._h))
+
+    # ---- non-blocking copies (PINNED host arrays; see fdtd2d_upload_state_async) -------------------
+    def set_state_async(self, Ez, Hx, Hy):
+        """Like set_state, but returns at once: the arrays must be pinned, of the run dtype, and stay alive until
+        copy_wait() / synchronize()."""
+        for a, (r, c), name in ((Ez, (self.local_rows, self.cols), "Ez"), (Hx, (self.local_rows, self.cols - 1), "Hx"),
+                                (Hy, (self._hy_rows, self.cols), "Hy")):
+            self._check_raw(a, r, c, name)
+        check(lib().fdtd2d_upload_state_async(self._h, _p(Ez), _p(Hx), _p(Hy)))
+
+    def read_Ez_async(self, out):
+        self._check_raw(out, self.local_rows, self.cols, "out")
+        check(lib().fdtd2d_download_state_async(self._h, _p(out), None, None))
+        return out
+
+    def set_materials_async(self, eps, mu):
+        self._check_raw(eps, self.local_rows, self.cols, "eps")
+        self._check_raw(mu, self.local_rows, self.cols, "mu")
+        check(lib().fdtd2d_set_materials_async(self._h, _p(eps), _p(mu), self.dt, self.dx))
+
+    def copy_wait(self):
+        check(lib().fdtd2d_copy_wait(self._h))
+
+    def _check_raw(self, a, rows, cols, name):
+        if not (isinstance(a, np.ndarray) and a.dtype == self.dtype and a.flags.c_contiguous and
+                a.shape in (self._shape(rows, cols), (self.batch, rows, cols))):
+            raise ValueError(f"{name} must be a C-contiguous {self.dtype} array of shape {self._shape(rows, cols)} "
+                             "(the non-blocking copies take the caller's buffer as it is)")
 
     # ---- materials --------------------------------------------------------------------------
     def set_materials(self, eps, mu):
@@ -232,8 +284,22 @@ class Simulation:
         return out
 
     # ---- time stepping ----------------------------------------------------------------------
-    def step(self, n_steps: int = 1, k: int = 0):
-        """Advance n_steps leapfrog steps (asynchronous), k steps per HBM round trip (0 = default)."""
+    def step(self, n_steps: int = 1, k: int = 0, strict: bool = True):
+        """Advance n_steps leapfrog steps (asynchronous), k steps per HBM round trip (0 = default).
+
+        The reference injects its source for as long as its loop runs (fdtd.py:34) and a readout has no end; here the
+        waveform tables and probe traces have the length they were given, and the library adds nothing / records nothing
+        beyond it.  strict=True (default) refuses to step past either instead of silently running on."""
+        if strict and n_steps > 0:
+            nc, ns, cap = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+            check(lib().fdtd2d_source_steps(self._h, ctypes.byref(nc), ctypes.byref(ns), ctypes.byref(cap)))
+            end = self.step_index + n_steps
+            if nc.value and end > ns.value:
+                raise ValueError(f"stepping to step {end} but the source tables hold {ns.value} steps: pass a longer table to "
+                                 "set_sources / set_point_source (or strict=False to run on without a source)")
+            if cap.value and end > cap.value:
+                raise ValueError(f"stepping to step {end} but the probe traces hold {cap.value} steps: raise capacity_steps "
+                                 "in set_probes (or strict=False to stop recording)")
         check(lib().fdtd2d_step(self._h, n_steps, k))
 
     run = step
@@ -296,6 +362,25 @@ class Simulation:
     def pass_end(self):
         """Launch the rest of the open pass and make its result the current state."""
         check(lib().fdtd2d_pass_end(self._h))
+
+    def peer_export(self) -> bytes:
+        """This slab's blob for its neighbours' peer_attach (geometry, device pointers, CUDA IPC handles)."""
+        buf = ctypes.create_string_buffer(_lib.PEER_BLOB_BYTES)
+        check(lib().fdtd2d_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_attach(self, side: int, blob: bytes):
+        """Link the neighbour slab on `side` (0 top, 1 bottom): the halo exchange then happens inside the kernels."""
+        check(lib().fdtd2d_peer_attach(self._h, side, ctypes.create_string_buffer(blob, _lib.PEER_BLOB_BYTES)))
+
+    def peer_detach(self):
+        check(lib().fdtd2d_peer_detach(self._h))
+
+    def peer_status(self) -> dict:
+        a = (ctypes.c_uint32 * 8)()
+        check(lib().fdtd2d_peer_status(self._h, a))
+        return {"attached_top": bool(a[0] & 1), "attached_bottom": bool(a[0] & 2), "passes": int(a[1]), "in_top": int(a[2]),
+                "in_bottom": int(a[3]), "error": int(a[4])}
 
     def device_field(self, field: int) -> int:
         p = ctypes.c_void_p()

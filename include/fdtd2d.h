@@ -36,7 +36,7 @@ extern "C" {
 
 /* error codes */
 #define FDTD2D_OK 0
-#define FDTD2D_EINVAL (-1) /* bad argument (shape < 11, null pointer, k out of range, ...) */
+#define FDTD2D_EINVAL (-1) /* bad argument (shape < 6, null pointer, k out of range, ...) */
 #define FDTD2D_ECUDA (-2)  /* CUDA runtime error / no device */
 #define FDTD2D_ENOMEM (-3) /* device or host allocation failed */
 #define FDTD2D_ESTATE (-4) /* call sequence error (e.g. step before coefficients are set) */
@@ -55,7 +55,9 @@ int fdtd2d_device_count(int* count);
 
 /* ---- handle: replaces grid_init (main.py:79-85) -------------------------------------------- */
 /* `batch` independent rows x cols grids in `dtype` on CUDA device `device`; zero state.
- * rows, cols >= 11 (the staged Mur/corner dataflow equals the reference only from 11). */
+ * rows, cols >= 6: the smallest grid on which the reference's own boundary code (main.py:33-61) indexes inside its
+ * arrays.  Below 11 the five-deep Mur strips of opposite sides overlap and the step is executed statement by
+ * statement in the reference's order (one CTA per grid); from 11 on the staged dataflow of SURVEY A.3 applies. */
 int fdtd2d_create(fdtd2d_sim** out, int rows, int cols, int dtype, int device, int batch);
 /* One y-slab of a global_rows x cols grid: this handle owns global rows [row_begin, row_end) and
  * keeps `halo` ghost rows on each side that has a neighbour slab. batch = 1. */
@@ -66,7 +68,21 @@ int fdtd2d_destroy(fdtd2d_sim* s);
  * legacy default stream).  fdtd2d_reset_stream goes back to the handle's own non-blocking stream. */
 int fdtd2d_set_stream(fdtd2d_sim* s, void* cuda_stream);
 int fdtd2d_reset_stream(fdtd2d_sim* s);
+/* The stream the handle's work is currently ordered on (cudaStream_t as void*). */
+int fdtd2d_get_stream(const fdtd2d_sim* s, void** cuda_stream);
+/* Waits for the handle's stream (and its copy stream); on a slab with peer links also until both neighbours have
+ * delivered the ghost rows of the current state, and reports a halo wait that timed out inside a kernel (FDTD2D_ESTATE). */
 int fdtd2d_sync(fdtd2d_sim* s);
+
+/* ---- tuning options (no reference counterpart) ----------------------------------------------------------- */
+/* A handle copies its options when it is created; the defaults come from the environment variables FDTD2D_<KEY>
+ * (upper case), read once at that moment.  fdtd2d_set_option changes one option of this handle and drops its cached
+ * plans.  Keys: "wavefront" (1), "wave_min_tiles" (-1 = automatic), "ring_min_tiles" (-1), "ring_strips" (1),
+ * "wave_run_rows" (640), "auto_k12" (0), "uniform_ch" (1), "resident" (1), "resident_cfg" (0), "resident_cluster" (0),
+ * "resident_trim" (-1), "tma_pair" (0), "f64_k" (0 = automatic), "debug" (0).  Every setting is covered by the parity
+ * tests: options change which kernel runs, never a result bit. */
+int fdtd2d_set_option(fdtd2d_sim* s, const char* key, int value);
+int fdtd2d_get_option(const fdtd2d_sim* s, const char* key, int* value);
 
 /* geometry queries: local_rows includes ghost rows; row0 = global index of local row 0 */
 int fdtd2d_geometry(const fdtd2d_sim* s, int* local_rows, int* cols, int* row0, int* global_rows, int* batch,
@@ -78,6 +94,13 @@ int fdtd2d_geometry(const fdtd2d_sim* s, int* local_rows, int* cols, int* row0, 
 int fdtd2d_upload_state(fdtd2d_sim* s, const void* Ez, const void* Hx, const void* Hy);
 int fdtd2d_download_state(fdtd2d_sim* s, void* Ez, void* Hx, void* Hy);
 int fdtd2d_zero_state(fdtd2d_sim* s);
+/* Non-blocking forms for PINNED host arrays: the copy is ordered after the stepping work issued so far and before the
+ * stepping work issued afterwards, on the handle's own copy stream, and the call returns at once -- one host thread
+ * can keep the copies of one handle overlapped with the kernels of another.  The host arrays must stay valid until
+ * fdtd2d_copy_wait (or fdtd2d_sync) returns. */
+int fdtd2d_upload_state_async(fdtd2d_sim* s, const void* Ez, const void* Hx, const void* Hy);
+int fdtd2d_download_state_async(fdtd2d_sim* s, void* Ez, void* Hx, void* Hy);
+int fdtd2d_copy_wait(fdtd2d_sim* s);
 
 /* ---- materials: replaces the per-step dt/(eps*dx), dt/(mu*dx), Mur coef (main.py:27,30-31,70,74) */
 /* Host-precomputed maps in the run dtype, (R, C) each, batch-major; mur_coef: one scalar per grid. */
@@ -85,6 +108,8 @@ int fdtd2d_set_coeffs(fdtd2d_sim* s, const void* ce, const void* ch, const void*
 /* eps/mu maps ((R, C) each, run dtype, batch-major) -> device forms ce = dt/(eps*dx), ch = dt/(mu*dx)
  * and the Mur coefficient from cell (0,0) with the reference's operation order, bit-identically. */
 int fdtd2d_set_materials(fdtd2d_sim* s, const void* eps, const void* mu, double dt, double dx);
+/* fdtd2d_set_materials without blocking the host (pinned eps / mu, see fdtd2d_upload_state_async). */
+int fdtd2d_set_materials_async(fdtd2d_sim* s, const void* eps, const void* mu, double dt, double dx);
 /* Mur coefficient(s) only (one scalar per grid, run dtype).  Needed by slab handles that do not hold
  * global cell (0,0): fdtd2d_set_materials leaves their coefficient unset. */
 int fdtd2d_set_mur_coef(fdtd2d_sim* s, const void* mur_coef);
@@ -126,8 +151,8 @@ int fdtd2d_read_probes(fdtd2d_sim* s, void* out, int64_t first_step, int n_steps
 
 /* ---- time stepping: replaces the loop body fdtd.py:31-34 ------------------------------------- */
 /* n_steps leapfrog steps (H -> Ez+Mur+corners -> source -> probe sample), k_temporal steps per HBM
- * round trip (1 <= k <= FDTD2D_MAX_K; for slabs k <= halo and the caller exchanges halos every k).
- * k_temporal = 0 picks the library default (fp64: 4; fp32: 8).  k = 12 has a row-streaming wavefront instance for
+ * round trip (1 <= k <= FDTD2D_MAX_K; for slabs k <= halo, and without peer links the caller exchanges halos every k).
+ * k_temporal = 0 picks the library default (fp32: 8; fp64: 8 where the wavefront kernel takes the grid, else 4).  k = 12 has a row-streaming wavefront instance for
  * grids with uniform permeability; on B200 it is no faster than k = 8 (latency-bound at 255 registers), so it is not
  * chosen automatically. */
 #define FDTD2D_MAX_K 12
@@ -136,6 +161,9 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal);
  * update_Hx_Hy (main.py:66-76), with PHASE_E alone update_Ez (main.py:12-63).  Does not advance the
  * step counter unless PHASE_SRC is included. */
 int fdtd2d_step_phases(fdtd2d_sim* s, int phases);
+/* How far the handle can be stepped before its source tables / probe traces run out: number of source cells, steps
+ * per waveform table (sources add nothing from that step index on), rows of the probe trace (0 = no probes). */
+int fdtd2d_source_steps(const fdtd2d_sim* s, int* n_cells, int* n_steps, int64_t* probe_capacity);
 int fdtd2d_get_step_index(const fdtd2d_sim* s, int64_t* step);
 int fdtd2d_set_step_index(fdtd2d_sim* s, int64_t step);
 /* Select the tile kernel: 0 = automatic, 1 = generic shared-memory tiles only,
@@ -154,6 +182,21 @@ int fdtd2d_pass_count(const fdtd2d_sim* s, int64_t* passes);
  * (nearly equal) runs of stretch i, *run_rows the plain run length chosen.  No reference counterpart. */
 int fdtd2d_plan_wave_runs(int n_stretches, const int32_t* rows, const uint8_t* ring, int warps, int cap_rows, int k,
                           int32_t* parts, int32_t* run_rows);
+/* Host-only: the whole plan of a k-step pass for a geometry, without a handle or a GPU (the CPU tests check that every
+ * owned cell is produced exactly once, for whole grids and slabs, fp32 and fp64).  geom[15] = dtype, batch, global rows,
+ * cols, row_begin, row_end, halo, k, SM count, kernel variant, wave_min_tiles, ring_min_tiles, wavefront, ring_strips,
+ * uniform permeability (1 / 0).  src / probe: n x (grid, global row, col).  plan[16] receives tile rows, tile columns,
+ * core rows, core columns, column halo, first owned local row, local rows, edge tiles, of which band tiles, TMA tiles,
+ * wavefront runs, of which band runs, ring strips present, band tasks top / bottom, pitch; tile_kind[tiles] (optional)
+ * 0 edge / 1 wavefront / 2 ring strip / 3 TMA per tile; tasks[runs][8] (optional) the runs: grid, first column, first
+ * row, end row, first / end stored column of the strip, ring side, band. */
+int fdtd2d_plan_host(const int32_t* geom, int n_src, const int32_t* src, int n_probe, const int32_t* probe, int32_t* plan,
+                     int32_t* tile_kind, int cap_tiles, int32_t* tasks, int cap_tasks);
+/* What a k-step pass of this handle consists of (builds and caches the plan; needs the materials): info[0..11] =
+ * tile rows, tile columns, core rows, core columns, edge tiles, of which band tiles, TMA tiles, wavefront runs, of
+ * which band runs, ring strips present, band tasks next to the top / bottom neighbour. */
+#define FDTD2D_PLAN_INFO_WORDS 12
+int fdtd2d_plan_info(fdtd2d_sim* s, int k, int32_t* info, int n_info);
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 int fdtd2d_launch_count(const fdtd2d_sim* s, int64_t* launches);
 
@@ -179,6 +222,24 @@ int fdtd2d_halo_block(fdtd2d_sim* s, int field, int side, void** send_ptr, void*
 int fdtd2d_pass_begin(fdtd2d_sim* s, int k);
 int fdtd2d_pass_end(fdtd2d_sim* s);
 int fdtd2d_halo_block_next(fdtd2d_sim* s, int field, int side, void** send_ptr, void** recv_ptr, size_t* nbytes);
+/* Peer links: the halo exchange INSIDE the stepping kernels.  Each slab exports a blob (its geometry, device
+ * pointers and CUDA IPC handles of its two field sets and its flag block); after fdtd2d_peer_attach of the blobs of
+ * its neighbours (side 0 = top, 1 = bottom; the same or another process on the same box) the tasks of a pass that
+ * produce the `halo` rows next to a neighbour store them straight into that neighbour's ghost rows (peer stores over
+ * NVLink), the last one raises the neighbour's flag, and the tasks that read ghost rows wait for their own flag -- no
+ * host work and no collective per pass, and fdtd2d_step may advance any number of steps.  Rules: attach every
+ * neighbour before the first step; every slab steps the same sequence of passes; one slab per GPU runs its passes on
+ * its own stream, slabs that SHARE a GPU must share one stream and be stepped pass by pass in turn (a kernel that
+ * waited for a kernel queued behind it on the same GPU would never finish; the wait gives up after 2 s and the next
+ * fdtd2d_sync reports it); synchronise all slabs (fdtd2d_sync on each, then a barrier between the processes) before
+ * uploading a new state, detaching or destroying. */
+#define FDTD2D_PEER_BLOB_BYTES 640
+int fdtd2d_peer_export(fdtd2d_sim* s, void* blob);
+int fdtd2d_peer_attach(fdtd2d_sim* s, int side, const void* blob);
+int fdtd2d_peer_detach(fdtd2d_sim* s);
+/* out[0] = attached sides (bit 0 top, bit 1 bottom), out[1] = passes stepped with a peer attached, out[2], out[3] =
+ * newest state delivered by the top / bottom neighbour, out[4] != 0: a halo wait timed out. */
+int fdtd2d_peer_status(fdtd2d_sim* s, uint32_t* out);
 /* Raw device pointer of a field of the current state (local_rows x pitch elements per grid). */
 int fdtd2d_device_field(fdtd2d_sim* s, int field, void** ptr);
 

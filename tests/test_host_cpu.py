@@ -50,8 +50,10 @@ def test_no_cpu_fallback_without_gpu(lib):
 
 def test_argument_validation_needs_no_gpu(lib):
     h = ctypes.c_void_p()
-    assert lib.fdtd2d_create(ctypes.byref(h), 10, 64, 0, 0, 1) == -1  # rows < 11
-    assert b"11" in lib.fdtd2d_last_error()
+    assert lib.fdtd2d_create(ctypes.byref(h), 5, 64, 0, 0, 1) == -1  # rows < 6: the reference itself indexes out of range
+    assert b">= 6" in lib.fdtd2d_last_error()
+    assert lib.fdtd2d_create_slab(ctypes.byref(h), 10, 64, 0, 5, 4, 0, 0) == -1  # slabs need the staged form (>= 11)
+    assert lib.fdtd2d_set_option(None, b"wavefront", 0) == -1 and lib.fdtd2d_peer_detach(None) == -1
     assert lib.fdtd2d_create(ctypes.byref(h), 64, 64, 7, 0, 1) == -1  # bad dtype
     assert lib.fdtd2d_create_slab(ctypes.byref(h), 64, 64, 10, 5, 4, 0, 0) == -1  # empty slab
     assert lib.fdtd2d_step(None, 1, 1) == -1 and lib.fdtd2d_sync(None) == -1

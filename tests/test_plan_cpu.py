@@ -1,0 +1,162 @@
+"""The pass planner on the CPU (fdtd2d_plan_host: host arithmetic only, no GPU): for whole grids and y-slabs, fp32 and
+fp64, with sources and probes in awkward places, every owned cell must be produced by exactly one task (edge tile, TMA
+tile or wavefront run), every wavefront run must stay inside the rows / columns it may read, band rows of a slab must
+be produced by band tasks, and the band-task counts the kernels wait for must match the lists."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import fdtd2d_b200 as fd
+from fdtd2d_b200 import _lib
+
+RING, SM = 5, 148
+
+
+@pytest.fixture(scope="module")
+def lib():
+    fd.build()
+    return _lib.lib()
+
+
+def plan(lib, dtype, Rg, C, k, *, rows=None, halo=0, batch=1, src=(), probe=(), wave_min=-1, ring_min=-1, wavefront=1,
+         ring_strips=1, variant=0, uniform=1):
+    rb, re = rows if rows else (0, Rg)
+    geom = np.array([dtype, batch, Rg, C, rb, re, halo, k, SM, variant, wave_min, ring_min, wavefront, ring_strips, uniform], np.int32)
+    s = np.ascontiguousarray(np.array(src, np.int32).reshape(-1, 3))
+    p = np.ascontiguousarray(np.array(probe, np.int32).reshape(-1, 3))
+    out = np.zeros(16, np.int32)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.fdtd2d_plan_host(vp(geom), len(s), vp(s), len(p), vp(p), vp(out), None, 0, None, 0)
+    assert rc == 0, lib.fdtd2d_last_error()
+    names = ("tiles_y", "tiles_x", "CH", "CW", "hx", "org", "Rl", "n_edge", "n_edge_band", "n_tma", "n_wave", "n_wave_band", "ring",
+             "exp_top", "exp_bot", "pitch")
+    info = dict(zip(names, (int(v) for v in out)))
+    kind = np.zeros(max(1, batch * info["tiles_y"] * info["tiles_x"]), np.int32)
+    tasks = np.zeros((max(1, info["n_wave"]), 8), np.int32)
+    rc = lib.fdtd2d_plan_host(vp(geom), len(s), vp(s), len(p), vp(p), vp(out), vp(kind), len(kind), vp(tasks), len(tasks))
+    assert rc == 0, lib.fdtd2d_last_error()
+    info.update(kind=kind.reshape(batch, info["tiles_y"], info["tiles_x"]), tasks=tasks[:info["n_wave"]], k=k, Rg=Rg, C=C, rb=rb, re=re,
+                halo=halo, batch=batch, dtype=dtype, src=s, probe=p)
+    return info
+
+
+def check(pl):
+    k, Rg, C, rb, re, halo, B = pl["k"], pl["Rg"], pl["C"], pl["rb"], pl["re"], pl["halo"], pl["batch"]
+    top, bot = rb > 0, re < Rg
+    row0 = rb - (halo if top else 0)
+    Rl, org, own_hi = pl["Rl"], pl["org"], pl["org"] + (re - rb)
+    assert org == rb - row0 and Rl == (re + (halo if bot else 0)) - row0
+    CH, CW, hx, pitch = pl["CH"], pl["CW"], pl["hx"], pl["pitch"]
+    W = 128 if pl["dtype"] == 0 else 64  # strip width
+    TH = 64 if pl["dtype"] == 0 else 32
+    band = [(org, org + (halo if top else 0)), (own_hi - (halo if bot else 0), own_hi)]
+    cover = np.zeros((B, Rl, pitch), np.int16)
+    n_edge = n_edge_band = n_tma = 0
+    exp = [0, 0]
+    for b in range(B):
+        for ty in range(pl["tiles_y"]):
+            r0, r1 = org + ty * CH, min(org + (ty + 1) * CH, own_hi)
+            for tx in range(pl["tiles_x"]):
+                kd = pl["kind"][b, ty, tx]
+                c0, c1 = tx * CW, min(tx * CW + CW, pitch)
+                in_band = [r0 < band[s][1] and r1 > band[s][0] for s in (0, 1)]
+                if kd in (0, 3):
+                    cover[b, r0:r1, c0:c1] += 1
+                if kd == 0:
+                    n_edge += 1
+                    n_edge_band += any(in_band)
+                    exp[0] += in_band[0]
+                    exp[1] += in_band[1]
+                if kd == 3:  # TMA tile: the whole window exists, full core, plain, never a band tile
+                    n_tma += 1
+                    assert pl["dtype"] == 0 and not any(in_band) and r1 - r0 == CH
+                    assert r0 - k >= 0 and r0 - k + TH <= Rl
+                    assert row0 + r0 - k >= RING and row0 + r0 - k + TH <= Rg - RING
+                    assert tx * CW - hx >= RING and tx * CW - hx + 128 <= C - RING
+    assert (n_edge, n_edge_band, n_tma) == (pl["n_edge"], pl["n_edge_band"], pl["n_tma"])
+    t = pl["tasks"]
+    assert np.all(t[:pl["n_wave_band"], 7] != 0) and np.all(t[pl["n_wave_band"]:, 7] == 0), "band runs come first"
+    for b_, x0, y0, y1, c0, c1, side, bnd in t:
+        assert y0 < y1 and y0 - k >= 0 and y1 + k <= Rl, "a run reads k rows above and below what it stores"
+        assert row0 + y0 - k >= RING and row0 + y1 + k <= Rg - RING, "no top / bottom ring within reach"
+        assert org <= y0 and y1 <= own_hi, "only owned rows are stored"
+        q = 4 if pl["dtype"] == 0 else 2
+        assert x0 % q == 0 and c0 % q == 0 and c1 % q == 0 and 0 <= c0 < c1 <= W and x0 >= 0 and x0 + W <= pitch
+        if side == 0:
+            assert c0 >= k and W - c1 >= k, "column halo"
+            assert x0 >= RING and x0 + W <= C - RING, "no left / right ring within a plain strip"
+        else:
+            assert pl["ring"] == 1 and pl["dtype"] == 0 and k == 8
+            assert (x0 == 0 and c0 == 0 and W - c1 >= k) if side == 1 else (x0 == (C + 3) // 4 * 4 - 128 and c1 == W and c0 >= k)
+        for g, r, c in pl["src"]:
+            assert not (g == b_ and y0 - k <= r - row0 < y1 + k and x0 <= c < x0 + W), "a source inside a run's window"
+        for g, r, c in pl["probe"]:
+            assert not (g == b_ and y0 <= r - row0 < y1 and x0 + c0 <= c < x0 + c1), "a probe inside a run"
+        if bnd:
+            lo, hi = band[bnd - 1]
+            assert lo <= y0 and y1 <= hi and hi > lo
+            exp[bnd - 1] += 1
+        else:
+            assert all(not (y0 < hi and y1 > lo) for lo, hi in band), "band rows belong to band runs"
+        cover[b_, y0:y1, x0 + c0:x0 + c1] += 1
+    owned = cover[:, org:own_hi, :C]
+    assert owned.min() == 1 and owned.max() == 1, f"cells produced {owned.min()}..{owned.max()} times"
+    assert cover[:, :org].sum() == 0 and cover[:, own_hi:].sum() == 0, "ghost rows are never stored locally"
+    if top or bot:
+        assert exp == [pl["exp_top"], pl["exp_bot"]]
+    else:
+        assert pl["exp_top"] == pl["exp_bot"] == 0
+
+
+GRIDS = [(300, 517), (1024, 1024), (203, 600), (2000, 260), (700, 1500), (97, 225), (11, 11), (4096, 4096), (129, 1000)]
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("k", [1, 3, 4, 6, 8, 12])
+def test_whole_grids_are_covered_once(lib, dtype, k):
+    if dtype == 1 and k > 8:
+        pytest.skip("fp64 tiles are 32 rows high: k <= 8")
+    for R, C in GRIDS:
+        src = [(0, R // 2, C // 2), (0, R // 3, C // 4), (0, 7, 9), (0, R - 1, 0)]
+        probe = [(0, R // 2, C // 2 + 3), (0, 0, 0), (0, R - 1, C - 1), (0, R // 4, C // 3)]
+        for wave_min in (-1, 0):
+            for ring_min in (-1, 0):
+                check(plan(lib, dtype, R, C, k, src=src, probe=probe, wave_min=wave_min, ring_min=ring_min))
+    check(plan(lib, dtype, 400, 900, k, batch=3, src=[(b, 200 + 10 * b, 450 - 50 * b) for b in range(3)], probe=[(1, 133, 307)], wave_min=0, ring_min=0))
+    check(plan(lib, dtype, 16384, 16384, k, src=[(0, 8192, 8192)], probe=[(0, 8192, 8208), (0, 8, 8192)]))
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("world,k,halo", [(2, 8, 8), (3, 8, 8), (4, 5, 8), (2, 4, 8), (8, 8, 8), (2, 12, 12), (3, 6, 12), (2, 1, 1)])
+def test_slabs_are_covered_once_and_bands_are_band_tasks(lib, dtype, world, k, halo):
+    if dtype == 1 and k > 8:
+        pytest.skip("fp64 tiles are 32 rows high: k <= 8")
+    for R, C in [(700, 900), (4096, 3000), (65536 // 8 * world, 2048), (34 * world + 5, 640)]:
+        for r in range(world):
+            rb, re = fd.slab_rows(R, world, r)
+            b1 = fd.slab_rows(R, world, 1)[0]
+            src = [(0, R // 2, C // 2), (0, b1, 100), (0, b1 - 1, 300), (0, b1 + 3, 500), (0, 7, 7)]
+            probe = [(0, b1, 101), (0, b1 - 2, 301), (0, R - 1, C - 1), (0, 0, 0), (0, R // 2, C // 2)]
+            for wave_min in (-1, 0):
+                pl = plan(lib, dtype, R, C, k, rows=(rb, re), halo=halo, src=src, probe=probe, wave_min=wave_min, ring_min=0 if wave_min == 0 else -1)
+                check(pl)
+                # every band row is produced by a task that knows it is a band task
+                assert (pl["exp_top"] > 0) == (r > 0) and (pl["exp_bot"] > 0) == (r < world - 1)
+
+
+def test_wavefront_takes_large_grids_and_both_dtypes(lib):
+    """The default choice: 16384^2 fp32 runs on the wavefront with ring strips; a 8192-row slab of 65536 columns has its
+    band rows on band runs; 8192^2 fp64 runs on 64-column strips, two per tile column."""
+    pl = plan(lib, 0, 16384, 16384, 8)
+    assert pl["n_wave"] > 1000 and pl["ring"] == 1 and pl["n_tma"] == 0
+    pl = plan(lib, 0, 65536, 65536, 8, rows=(8192, 16384), halo=8)
+    assert pl["n_wave_band"] >= 2 * (65536 // 112) and pl["n_edge"] == 0, "a middle slab without sources is all wavefront"
+    pl = plan(lib, 1, 8192, 8192, 8)
+    assert pl["n_wave"] > 1000 and pl["CW"] == 96 and pl["ring"] == 0
+    t = pl["tasks"]
+    assert set(np.unique(t[:, 5] - t[:, 4])) == {48}
+    pl = plan(lib, 1, 8192, 8192, 8, wavefront=0)
+    assert pl["n_wave"] == 0 and pl["n_tma"] == 0 and pl["n_edge"] == pl["tiles_y"] * pl["tiles_x"]
+    pl = plan(lib, 0, 1024, 1024, 8)  # small grid: persistent TMA tiles
+    assert pl["n_wave"] == 0 and pl["n_tma"] > 0
