@@ -145,8 +145,11 @@ struct fdtd2d_sim {
     unsigned* d_slab_flags = nullptr;
     PeerLink peer[2];
     unsigned pass_seq = 0;
-    cudaEvent_t ev_copy = nullptr;  // fdtd2d_*_async: the last asynchronous copy
+    // fdtd2d_*_async: copies run on a stream of their own, ordered against this handle's stepping work by two events
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr;  // the last asynchronous copy
+    cudaEvent_t ev_work = nullptr;  // the last work this handle put on its stream
+    bool copy_pending = false;      // the next work on the stream has to wait for ev_copy first
 };
 
 static size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
@@ -167,6 +170,21 @@ struct DeviceGuard {
 #define USE_DEVICE(s)               \
     DeviceGuard guard_((s)->device); \
     if (guard_.err != cudaSuccess) return fail(FDTD2D_ECUDA, "cudaSetDevice(%d) failed: %s", (s)->device, cudaGetErrorString(guard_.err))
+
+// Work that reads or writes the handle's buffers is bracketed by these two: begin_work makes the stream wait for an
+// asynchronous copy that is still in flight, mark_work remembers where this handle's work ends on a stream it may
+// share with other handles (an asynchronous copy waits for that point, not for whatever else was queued since).
+static int begin_work(fdtd2d_sim* s) {
+    if (s->copy_pending) {
+        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_copy, 0));
+        s->copy_pending = false;
+    }
+    return 0;
+}
+static int mark_work(fdtd2d_sim* s) {
+    if (s->ev_work) CUDA_TRY(cudaEventRecord(s->ev_work, s->stream));
+    return 0;
+}
 
 static int sm_count(fdtd2d_sim* s) {
     if (!s->sm_count) cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
@@ -971,6 +989,15 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
 // part: 0 = everything, 1 = only the tasks that hold band rows of a slab, 2 = everything else.
 template <typename T> static int launch_hybrid_t(fdtd2d_sim* s, int k, int part) {
     PassPlan& pl = s->hybrid[k];
+    if (pl.valid && k == 12 && s->ch_uniform < 0) {
+        // the 12-level wavefront exists for uniform permeability only, and the maps have changed since the plan was made
+        if (int rc = check_ch_uniform(s)) return rc;
+        if ((pl.n_wave > 0) != (s->ch_uniform == 1)) {
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            cudaFree(pl.d_edge), cudaFree(pl.d_fast), cudaFree(pl.d_wave), cudaFree(pl.d_ticket);
+            pl = PassPlan();
+        }
+    }
     if (!pl.valid)
         if (int rc = classify_tiles(s, k, &pl)) return rc;
     PassParams<T> p;
@@ -1204,6 +1231,17 @@ static void peer_close(fdtd2d_sim* s, int side) {
     pe = PeerLink();
 }
 
+// Host wait for THIS handle's work: its own stream entirely; on a stream it was given (and may share with other handles,
+// whose queued work is none of its business) up to the last work it put there; and its copies.
+static int wait_own_work(fdtd2d_sim* s) {
+    if (s->stream == s->own_stream)
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    else
+        CUDA_TRY(cudaEventSynchronize(s->ev_work));
+    CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+    return 0;
+}
+
 // Read the flag block; wait (on the host) until both attached neighbours have delivered the ghost rows of the current
 // state, so that a download that follows sees them.  A timeout inside a kernel or here is an error.
 static int peer_settle(fdtd2d_sim* s) {
@@ -1211,8 +1249,8 @@ static int peer_settle(fdtd2d_sim* s) {
     const auto t0 = std::chrono::steady_clock::now();
     for (;;) {
         unsigned f[FLAG_WORDS];
-        CUDA_TRY(cudaMemcpyAsync(f, s->d_slab_flags, sizeof f, cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        CUDA_TRY(cudaMemcpyAsync(f, s->d_slab_flags, sizeof f, cudaMemcpyDeviceToHost, s->copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
         if (f[FLAG_ERR]) return fail(FDTD2D_ESTATE, "halo wait timed out: the %s neighbour slab did not deliver its rows (are all slabs stepping the same passes?)",
                                      f[FLAG_ERR] == 1 ? "top" : "bottom");
         const bool top_ok = !s->peer[0].attached || (int)(f[FLAG_IN_TOP] - s->pass_seq) >= 0;
@@ -1336,6 +1374,12 @@ static int create_impl(fdtd2d_sim** out, int Rg, int C, int row_begin, int row_e
         return fail(FDTD2D_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
     }
     s->stream = s->own_stream;
+    if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_work, cudaEventDisableTiming) != cudaSuccess) {
+        fdtd2d_destroy(s);
+        return fail(FDTD2D_ECUDA, "stream / event creation failed");
+    }
     void** bufs[10] = {&s->field[0][0], &s->field[0][1], &s->field[0][2], &s->field[1][0], &s->field[1][1],
                        &s->field[1][2], &s->ce,          &s->ch,          &s->mur,         reinterpret_cast<void**>(&s->d_slab_flags)};
     for (int i = 0; i < 10; ++i) {
@@ -1395,6 +1439,7 @@ int fdtd2d_destroy(fdtd2d_sim* s) {
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
+    if (s->ev_work) cudaEventDestroy(s->ev_work);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
     return 0;
@@ -1446,8 +1491,7 @@ int fdtd2d_get_stream(const fdtd2d_sim* s, void** cuda_stream) {
 int fdtd2d_sync(fdtd2d_sim* s) {
     REQUIRE(s, "handle is null");
     USE_DEVICE(s);
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    if (s->copy_stream) CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+    if (int rc = wait_own_work(s)) return rc;
     return peer_settle(s);
 }
 
@@ -1475,13 +1519,19 @@ static int upload_state_on(fdtd2d_sim* s, const void* Ez, const void* Hx, const 
 int fdtd2d_upload_state(fdtd2d_sim* s, const void* Ez, const void* Hx, const void* Hy) {
     REQUIRE(s && Ez && Hx && Hy, "null argument");
     USE_DEVICE(s);
-    return upload_state_on(s, Ez, Hx, Hy, s->stream);
+    if (int rc = begin_work(s)) return rc;
+    if (int rc = upload_state_on(s, Ez, Hx, Hy, s->stream)) return rc;
+    return mark_work(s);
 }
 
 int fdtd2d_download_state(fdtd2d_sim* s, void* Ez, void* Hx, void* Hy) {
     REQUIRE(s, "handle is null");
     USE_DEVICE(s);
-    if (int rc = peer_settle(s)) return rc;  // (a slab's ghost rows are written by its neighbours)
+    if (int rc = begin_work(s)) return rc;
+    if (peer_mode(s)) {  // a slab's ghost rows are written by its neighbours
+        if (int rc = wait_own_work(s)) return rc;
+        if (int rc = peer_settle(s)) return rc;
+    }
     void** f = s->field[s->cur];
     if (Ez)
         if (int rc = transfer_field(s, f[0], Ez, s->Rl, s->C, false, s->stream)) return rc;
@@ -1499,17 +1549,16 @@ int fdtd2d_download_state(fdtd2d_sim* s, void* Ez, void* Hx, void* Hy) {
 // stepping work issued AFTER the call is ordered behind the copy.  The host does not block; fdtd2d_copy_wait (or
 // fdtd2d_sync) does.
 static int copy_fork(fdtd2d_sim* s) {
-    if (!s->copy_stream) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming));
-    }
-    CUDA_TRY(cudaEventRecord(s->ev_copy, s->stream));
-    CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->ev_copy, 0));
+    if (s->stream == s->own_stream)
+        if (int rc = mark_work(s)) return rc;  // a private stream: its tail is exactly this handle's work
+    CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->ev_work, 0));
     return 0;
 }
+// (the stream does not wait here: the handle's NEXT work does, in begin_work -- work of other handles that share the
+// stream and is queued in between has no reason to wait for this copy)
 static int copy_join(fdtd2d_sim* s) {
     CUDA_TRY(cudaEventRecord(s->ev_copy, s->copy_stream));
-    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_copy, 0));
+    s->copy_pending = true;
     return 0;
 }
 
@@ -1538,25 +1587,27 @@ int fdtd2d_download_state_async(fdtd2d_sim* s, void* Ez, void* Hx, void* Hy) {
 int fdtd2d_copy_wait(fdtd2d_sim* s) {
     REQUIRE(s, "handle is null");
     USE_DEVICE(s);
-    if (s->copy_stream) CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
     return 0;
 }
 
 int fdtd2d_zero_state(fdtd2d_sim* s) {
     REQUIRE(s, "handle is null");
     USE_DEVICE(s);
+    if (int rc = begin_work(s)) return rc;
     const size_t bytes = s->grid_elems * s->esize * (size_t)s->batch;
     for (int h = 0; h < 2; ++h)
         for (int f = 0; f < 3; ++f) CUDA_TRY(cudaMemsetAsync(s->field[h][f], 0, bytes, s->stream));
     s->step = 0;
-    return 0;
+    return mark_work(s);
 }
 
-// the maps changed: the permeability check and every cached plan that depends on it start over
+// the maps changed: the permeability check starts over (the cached plans stay -- a job that uploads new maps for every run
+// must not pay a cudaFree, which waits for the whole device; the one plan that depends on the check, the 12-level
+// wavefront, is re-examined when it is next used: launch_hybrid_t)
 static void materials_changed(fdtd2d_sim* s) {
     s->coeffs_set = true;
     s->ch_uniform = -1;
-    free_plans(s);
 }
 
 int fdtd2d_set_mur_coef(fdtd2d_sim* s, const void* mur_coef) {
@@ -1571,6 +1622,7 @@ int fdtd2d_set_mur_coef(fdtd2d_sim* s, const void* mur_coef) {
 int fdtd2d_set_coeffs(fdtd2d_sim* s, const void* ce, const void* ch, const void* mur_coef) {
     REQUIRE(s && ce && ch, "null argument");
     USE_DEVICE(s);
+    if (int rc = begin_work(s)) return rc;
     if (int rc = transfer_field(s, s->ce, const_cast<void*>(ce), s->Rl, s->C, true, s->stream)) return rc;
     if (int rc = transfer_field(s, s->ch, const_cast<void*>(ch), s->Rl, s->C, true, s->stream)) return rc;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1584,6 +1636,7 @@ static int finish_materials(fdtd2d_sim* s, double dt, double dx, bool wait);
 int fdtd2d_set_materials(fdtd2d_sim* s, const void* eps, const void* mu, double dt, double dx) {
     REQUIRE(s && eps && mu, "null argument");
     USE_DEVICE(s);
+    if (int rc = begin_work(s)) return rc;
     // stage eps in ce and mu in ch, then transform in place on the device
     if (int rc = transfer_field(s, s->ce, const_cast<void*>(eps), s->Rl, s->C, true, s->stream)) return rc;
     if (int rc = transfer_field(s, s->ch, const_cast<void*>(mu), s->Rl, s->C, true, s->stream)) return rc;
@@ -1607,6 +1660,7 @@ double fdtd2d_hash_uniform(uint64_t seed, uint32_t grid, uint32_t row, uint32_t 
 int fdtd2d_set_materials_random(fdtd2d_sim* s, uint64_t seed, double span, double dt, double dx) {
     REQUIRE(s, "handle is null");
     USE_DEVICE(s);
+    if (int rc = begin_work(s)) return rc;
     const double eps0 = 8.85418e-12, mu0 = 4 * 3.141592653589793 * 1e-7;  // main.py:100-101
     const long long n = (long long)s->Rl * s->C * s->batch;
     const int blocks = (int)std::min<long long>((n + 255) / 256, sm_count(s) * 16);
@@ -1622,12 +1676,13 @@ int fdtd2d_set_materials_random(fdtd2d_sim* s, uint64_t seed, double span, doubl
     s->launches += 1;
     materials_changed(s);
     s->mur_set = true;
-    return 0;
+    return mark_work(s);
 }
 
 // eps/mu are staged in ce/ch: form the Mur coefficient(s) and the coefficient maps in place (device-side tail of
 // every fdtd2d_set_materials* entry point)
 static int finish_materials(fdtd2d_sim* s, double dt, double dx, bool wait) {
+    if (int rc = begin_work(s)) return rc;  // (an asynchronous upload of eps / mu may still be in flight)
     const long long n = (long long)s->grid_elems * s->batch;
     const int blocks = (int)std::min<long long>((n + 255) / 256, sm_count(s) * 16);
     const bool has_corner = s->row0 == 0;
@@ -1649,12 +1704,13 @@ static int finish_materials(fdtd2d_sim* s, double dt, double dx, bool wait) {
     s->launches += has_corner ? 2 : 1;
     materials_changed(s);
     if (has_corner) s->mur_set = true;
-    return 0;
+    return mark_work(s);
 }
 
 int fdtd2d_set_materials_gray(fdtd2d_sim* s, const unsigned char* gray, double black_point, double dt, double dx) {
     REQUIRE(s && gray, "null argument");
     USE_DEVICE(s);
+    if (int rc = begin_work(s)) return rc;
     const double eps0 = 8.85418e-12, mu0 = 4 * 3.141592653589793 * 1e-7;  // main.py:100-101
     const size_t n = (size_t)s->Rl * s->C * s->batch;
     unsigned char* d_g = nullptr;
@@ -1685,6 +1741,7 @@ int fdtd2d_generate_materials_blobs(fdtd2d_sim* s, uint64_t seed, const float* w
     REQUIRE(s && weights, "null argument");
     REQUIRE(!s->has_top_nb && !s->has_bot_nb, "the blob generator works on whole grids, not slabs");
     USE_DEVICE(s);
+    if (int rc = begin_work(s)) return rc;
     float* d_w = nullptr;
     const size_t wbytes = sizeof(float) * BLOB_K * BLOB_K * (size_t)s->batch;
     CUDA_TRY(cudaMalloc(&d_w, wbytes));
@@ -1714,6 +1771,7 @@ int fdtd2d_generate_materials_blobs(fdtd2d_sim* s, uint64_t seed, const float* w
 int fdtd2d_download_coeffs(fdtd2d_sim* s, void* ce, void* ch, void* mur_coef) {
     REQUIRE(s, "handle is null");
     USE_DEVICE(s);
+    if (int rc = begin_work(s)) return rc;
     if (ce)
         if (int rc = transfer_field(s, s->ce, ce, s->Rl, s->C, false, s->stream)) return rc;
     if (ch)
@@ -1842,9 +1900,10 @@ int fdtd2d_read_probes(fdtd2d_sim* s, void* out, int64_t first_step, int n_steps
     USE_DEVICE(s);
     const size_t row_bytes = (size_t)s->n_probe * s->esize;
     std::vector<char> tmp(row_bytes * (size_t)n_steps);
+    if (int rc = copy_fork(s)) return rc;  // behind this handle's stepping work, not behind whatever else shares its stream
     CUDA_TRY(cudaMemcpyAsync(tmp.data(), static_cast<char*>(s->d_trace) + (size_t)first_step * row_bytes, tmp.size(),
-                             cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
+                             cudaMemcpyDeviceToHost, s->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
     // device columns are in sorted order; give them back in the caller's order
     char* o = static_cast<char*>(out);
     for (int t = 0; t < n_steps; ++t)
@@ -1860,17 +1919,18 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
     REQUIRE(k_temporal >= 0 && k_temporal <= FDTD2D_MAX_K, "k_temporal must be in [0, %d]", FDTD2D_MAX_K);
     if (!s->coeffs_set || !s->mur_set) return fail(FDTD2D_ESTATE, "coefficients / Mur coefficient not set");
     USE_DEVICE(s);
+    if (int rc = begin_work(s)) return rc;
     if (n_steps > 0 && small_grid(s)) {
         // rows or cols below 11: the reference's boundary statements overlap, so they are executed one by one
         if (int rc = launch_small(s, n_steps)) return rc;
         s->step += n_steps;
-        return 0;
+        return mark_work(s);
     }
     if (n_steps > 0 && (s->variant == 0 || s->variant == 4) && resident_eligible(s)) {
         // the whole run in one launch, the grid resident on chip (k_temporal does not apply)
         if (int rc = launch_resident(s, n_steps)) return rc;
         s->step += n_steps;
-        return 0;
+        return mark_work(s);
     }
     if (s->variant == 4 && n_steps > 0) return fail(FDTD2D_EINVAL, "variant 4 (cluster-resident) needs fp32, 16..256 columns, 16..384 rows, no slabs");
     const bool slab = s->has_top_nb || s->has_bot_nb;
@@ -1915,7 +1975,7 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
         s->step += kk;
         left -= kk;
     }
-    return 0;
+    return mark_work(s);
 }
 
 int fdtd2d_step_phases(fdtd2d_sim* s, int phases) {
@@ -1923,13 +1983,14 @@ int fdtd2d_step_phases(fdtd2d_sim* s, int phases) {
     REQUIRE(phases > 0 && phases < 8, "phases must be a non-empty FDTD2D_PHASE_* mask");
     if (!s->coeffs_set || !s->mur_set) return fail(FDTD2D_ESTATE, "coefficients / Mur coefficient not set");
     USE_DEVICE(s);
+    if (int rc = begin_work(s)) return rc;
     if (small_grid(s)) {
         if (int rc = launch_small(s, 1, phases)) return rc;
     } else if (int rc = run_pass(s, 1, phases)) {
         return rc;
     }
     if (phases & FDTD2D_PHASE_SRC) s->step += 1;
-    return 0;
+    return mark_work(s);
 }
 
 int fdtd2d_get_step_index(const fdtd2d_sim* s, int64_t* step) {
@@ -2069,6 +2130,7 @@ int fdtd2d_pass_begin(fdtd2d_sim* s, int k) {
     REQUIRE(s->open_pass_k == 0, "a pass is already open");
     if (!s->coeffs_set || !s->mur_set) return fail(FDTD2D_ESTATE, "coefficients / Mur coefficient not set");
     USE_DEVICE(s);
+    if (int rc = begin_work(s)) return rc;
     const int all = FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC;
     int rc;
     if (uses_hybrid(s, all))
@@ -2092,7 +2154,7 @@ int fdtd2d_pass_end(fdtd2d_sim* s) {
     s->passes += 1;
     if (peer_mode(s)) s->pass_seq += 1;
     s->step += k;
-    return 0;
+    return mark_work(s);
 }
 
 // ---- peer links: the halo exchange inside the stepping kernels (NVLink peer stores + flags) ----------------------
@@ -2182,8 +2244,8 @@ int fdtd2d_peer_status(fdtd2d_sim* s, uint32_t* flags_out) {
     flags_out[1] = s->pass_seq;
     unsigned f[FLAG_WORDS] = {0};
     if (s->d_slab_flags) {
-        CUDA_TRY(cudaMemcpyAsync(f, s->d_slab_flags, sizeof f, cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        CUDA_TRY(cudaMemcpyAsync(f, s->d_slab_flags, sizeof f, cudaMemcpyDeviceToHost, s->copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
     }
     flags_out[2] = f[FLAG_IN_TOP], flags_out[3] = f[FLAG_IN_BOT], flags_out[4] = f[FLAG_ERR];
     return 0;
@@ -2208,6 +2270,7 @@ int fdtd2d_render_snapshot(fdtd2d_sim* s, int grid, double vmin, double vmax, un
     REQUIRE(s && out_rgb && grid >= 0 && grid < s->batch, "bad argument");
     if (!s->d_gray) return fail(FDTD2D_ESTATE, "snapshot background not set");
     USE_DEVICE(s);
+    if (int rc = begin_work(s)) return rc;
     const long long n = (long long)s->Rl * s->C;
     const int blocks = (int)std::min<long long>((n + 255) / 256, sm_count(s) * 8);
     const unsigned char* gray = s->d_gray + (size_t)grid * n;

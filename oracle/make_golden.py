@@ -132,13 +132,46 @@ def make_material_and_sources(ref):
     np.savez_compressed(os.path.join(GOLDEN, "material_sources.npz"), **out)
 
 
+SMALL_SIZES = [(6, 6), (6, 23), (7, 9), (10, 10), (8, 40), (40, 7), (10, 11), (11, 10), (9, 300)]
+
+
+def make_small_grids(ref):
+    """Grids with fewer than 11 rows or columns: the Mur strips of opposite sides overlap, so the reference's statements
+    read what earlier statements of the same step wrote.  6 is the smallest size the reference's own
+    indexing allows.  One update_Hx_Hy / update_Ez call and a 30-step run per size and dtype."""
+    rng = np.random.default_rng(611)
+    out = {"numpy_version": np.__version__, "sizes": np.array(SMALL_SIZES)}
+    for dtype in (np.float32, np.float64):
+        for (R, C) in SMALL_SIZES:
+            key = f"{np.dtype(dtype).name}_{R}x{C}"
+            eps, mu, Ez, Hx, Hy = random_case(ref, rng, R, C, dtype)
+            Ez *= dtype(1e-2)
+            for n, a in zip(("eps", "mu", "Ez0", "Hx0", "Hy0"), (eps, mu, Ez, Hx, Hy)):
+                out[f"{key}_{n}"] = a.copy()
+            e1, h1, h2 = Ez.copy(), Hx.copy(), Hy.copy()
+            ref.update_Hx_Hy(e1, h1, h2, mu, eps, DT, DX)
+            out[f"{key}_Hx1"], out[f"{key}_Hy1"] = h1.copy(), h2.copy()
+            e1 = ref.update_Ez(e1, h1, h2, mu, eps, DT, DX)
+            out[f"{key}_Ez1"] = e1.copy()
+            probes = [(R // 2, C // 2), (0, 0), (R - 1, C - 1), (1, C - 2), (R - 2, 1)]
+            src = (R // 2, C // 3)
+            Ez, Hx, Hy, trace = drive(ref, Ez, Hx, Hy, mu, eps, 30, src, probes, "ricker", step0=650)
+            out[f"{key}_probes"], out[f"{key}_src"], out[f"{key}_trace"] = np.array(probes), np.array(src), trace
+            out[f"{key}_Ez"], out[f"{key}_Hx"], out[f"{key}_Hy"] = Ez.copy(), Hx.copy(), Hy.copy()
+    np.savez_compressed(os.path.join(GOLDEN, "small_grids.npz"), **out)
+
+
 def main():
+    import sys
+
     ref = load_reference_main()
     os.makedirs(GOLDEN, exist_ok=True)
-    make_single_call(ref)
-    make_demo(ref)
-    make_random_runs(ref)
-    make_material_and_sources(ref)
+    if "--small-only" not in sys.argv:
+        make_single_call(ref)
+        make_demo(ref)
+        make_random_runs(ref)
+        make_material_and_sources(ref)
+    make_small_grids(ref)
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

@@ -1,7 +1,7 @@
-"""Multi-process y-slab parity check over NCCL (run under torchrun, one rank per GPU):
-    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/mp_slab_check.py
-Every rank steps its slab with NCCL halo exchange; rank 0 also runs the single-domain simulation and
-compares the gathered owned rows bit for bit."""
+"""Multi-process y-slab parity check (run under torchrun, one rank per GPU):
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/mp_slab_check.py [p2p|nccl]
+Every rank steps its slab -- halo rows moved by the kernels themselves over peer links (p2p, default) or by NCCL
+send/recv -- rank 0 also runs the single-domain simulation and compares the gathered owned rows bit for bit."""
 import os
 import sys
 
@@ -17,10 +17,13 @@ DT, DX, FC = 5e-14, 1e-4, 30e9
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    mode = sys.argv[1] if len(sys.argv) > 1 else "p2p"
+    if mode == "nccl":
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     R, C, n, k = 2048 * world, 3000, 44, 8
-    sim = fd.SlabSimulation(R, C, np.float32, dt=DT, dx=DX, rank=rank, world=world, device=local, halo=8)
+    sim = fd.SlabSimulation(R, C, np.float32, dt=DT, dx=DX, rank=rank, world=world, device=local, halo=8, exchange=mode)
     sim.set_stream(torch.cuda.current_stream().cuda_stream)
     sim.set_materials_random(9, 9.0)
     sim.set_point_source(R // 2, C // 2, 700, FC)
@@ -28,6 +31,7 @@ def main():
     sim.step_index = 640
     sim.step(n // 2, k, overlap=False)  # first half: exchange after each pass
     sim.step(n - n // 2, k, overlap=True)  # second half: exchange overlapped with the rest of the pass
+    sim.synchronize()
     torch.cuda.synchronize()
     Ez, Hx, Hy = sim.state()
     lo, cnt = sim.row_begin - sim.row0, sim.row_end - sim.row_begin
@@ -54,7 +58,7 @@ def main():
         for b, e, gEz, gHx, gHy in gathered:
             ok &= np.array_equal(gEz, full[0][b:e]) and np.array_equal(gHx, full[1][b:e])
             ok &= np.array_equal(gHy, full[2][b:min(e, R - 1)])
-        print(f"mp_slab_check world={world}: {'OK bit-exact' if ok else 'MISMATCH'}", flush=True)
+        print(f"mp_slab_check world={world} exchange={mode}: {'OK bit-exact' if ok else 'MISMATCH'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     sim.close()

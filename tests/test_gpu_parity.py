@@ -246,9 +246,11 @@ def test_temporal_blocking_invariance_large(fd):
                 assert_bits(a, b, f"k={k} vs k=1")
 
 
-def test_window_locality_vs_oracle_large(fd, oracle):
+@pytest.mark.parametrize("k", [4, 8])
+def test_window_locality_vs_oracle_large(fd, oracle, k):
     """Full-size check through locality: after n steps a window of a 4096 x 4096 fp32 run equals the
-    oracle run on the window grown by n+8 cells (interior dependency radius is 1 cell per step)."""
+    oracle run on the window grown by n+8 cells (interior dependency radius is 1 cell per step).  k = 4 runs on the
+    persistent TMA tiles, k = 8 on the wavefront strips."""
     c_oracle, npo = oracle
     R = C = 4096
     n, m = 20, 28
@@ -260,7 +262,8 @@ def test_window_locality_vs_oracle_large(fd, oracle):
         Hy0 = (1e-6 * rng.standard_normal((R - 1, C))).astype(np.float32)
         sim.set_state(Ez0, Hx0, Hy0)
         ce, ch, _ = sim.coefficients()
-        sim.step(n, 4)
+        assert (sim.plan_info(k)["wave_runs"] > 0) == (k == 8)
+        sim.step(n, k)
         Ez, Hx, Hy = sim.state()
     for (r0, c0, h, w) in [(1000, 2000, 96, 160), (3000, 100, 64, 64), (2040, 2040, 40, 40)]:
         a, b_, c_, d = r0 - m, r0 + h + m, c0 - m, c0 + w + m
@@ -298,7 +301,7 @@ def test_random_medium_matches_host_definition(fd):
 # --------------------------------------------------------------------------------------------
 def test_errors(fd):
     with pytest.raises(fd.Fdtd2dError) as e:
-        fd.Simulation(10, 200, np.float32, dt=DT, dx=DX)
+        fd.Simulation(5, 200, np.float32, dt=DT, dx=DX)  # below 6 the reference itself indexes out of range
     assert e.value.code == -1
     with fd.Simulation(32, 32, np.float32, dt=DT, dx=DX) as sim:
         with pytest.raises(fd.Fdtd2dError) as e:
@@ -313,6 +316,13 @@ def test_errors(fd):
             sim.set_sources([(0, 4, 3, 0), (0, 4, 3, 0)], np.zeros((1, 4)))  # duplicate cell
         with pytest.raises(ValueError):
             sim.set_state(np.zeros((32, 32), np.float32), np.zeros((32, 32), np.float32), np.zeros((31, 32), np.float32))
+        sim.set_point_source(16, 16, 10, FC)
+        sim.step(10)
+        with pytest.raises(ValueError):  # the reference's source never ends; a table does: stepping past it is refused
+            sim.step(1)
+        sim.step(1, strict=False)
+        with pytest.raises(fd.Fdtd2dError):
+            sim.set_option("no_such_option", 1)
     with pytest.raises(ValueError):
         fd.update_Hx_Hy(np.zeros((20, 20)), np.zeros((20, 20)), np.zeros((19, 20)), np.ones((20, 20)), np.ones((20, 20)), DT, DX)
 
@@ -382,33 +392,35 @@ def test_kernel_variants_agree(fd, variant):
 @pytest.mark.parametrize("shape,nsteps", [((300, 517), 40), ((1024, 1024), 24), ((203, 600), 17), ((2000, 260), 32),
                                           ((700, 1500), 8)])
 @pytest.mark.parametrize("uniform_mu", [False, True])
-@pytest.mark.parametrize("k,x2", [(8, "1"), (8, "0"), (10, "1"), (12, "1"), (12, "0")])
-def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, uniform_mu, k, x2, monkeypatch):
+@pytest.mark.parametrize("dtype,k", [("float32", 8), ("float32", 12), ("float64", 4), ("float64", 6), ("float64", 8)])
+def test_wavefront_kernel_vs_oracle(fd, oracle, shape, nsteps, uniform_mu, dtype, k, monkeypatch):
     """Forced onto small grids (FDTD2D_WAVE_MIN_TILES=0) so the oracle can check it: runs of plain tiles broken by
-    sources and probes, ragged sizes, the remainder pass (nsteps % k) on the tile kernel; the packed (FADD2 / FFMA2,
-    x2 = 1) and the scalar instantiations; 12 levels exist for uniform permeability (otherwise those passes run on the
-    tile kernels, which is checked all the same)."""
+    sources and probes, ragged sizes, the remainder pass (nsteps % k) on the tile kernel.  fp32: the packed (FADD2 /
+    FFMA2) kernel with 8 levels and, for uniform permeability, 12 (otherwise those passes run on the tile kernels, which
+    is checked all the same); fp64: the scalar kernel on 64-column strips with 4, 6 and 8 levels."""
     monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", "0")
     monkeypatch.setenv("FDTD2D_RING_MIN_TILES", "0")  # ring strips (left / right Mur ring on the wavefront) where C >= 512
-    monkeypatch.setenv("FDTD2D_WAVE_X2", x2)
     c_oracle, npo = oracle
     R, C = shape
     rng = np.random.default_rng(R * 31 + C)
-    eps, mu, Ez, Hx, Hy = _random_problem(rng, R, C, "float32")
+    eps, mu, Ez, Hx, Hy = _random_problem(rng, R, C, dtype)
     if uniform_mu:  # every material_init output: the kernel then takes dt/(mu*dx) as a scalar and skips the map
-        mu[...] = np.float32(4 * np.pi * 1e-7)
-    ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(np.float32))
+        mu[...] = np.dtype(dtype).type(4 * np.pi * 1e-7)
+    ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(dtype))
     cells = [(R // 2, C // 2), (R // 3, C // 4), (7, 9)]
     amp = npo.source_table("ricker", nsteps, DT, FC) + 0.125
     probes = [(R // 2, C // 2 + 3), (0, 0), (R - 1, C - 1), (R // 4, C // 3), (3 * R // 4, 2 * C // 3)]
     oEz, oHx, oHy = Ez.copy(), Hx.copy(), Hy.copy()
     otrace = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, nsteps, amp, cells, probes, omp=True)
-    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
+    with fd.Simulation(R, C, dtype, dt=DT, dx=DX) as sim:
         sim.set_kernel_variant(2)  # tile kernels (the cluster-resident kernel would take the small ones)
         sim.set_coefficients(ce, ch, coef)
         sim.set_state(Ez, Hx, Hy)
         sim.set_sources([(0, r, c, 0) for r, c in cells], amp[None, :])
         sim.set_probes(probes, nsteps)
+        info = sim.plan_info(k)
+        if nsteps >= k and (dtype == "float64" or k == 8 or uniform_mu) and min(R, C) >= 260:
+            assert info["wave_runs"] > 0, info  # the kernel under test really runs
         sim.step(nsteps, k)
         gEz, gHx, gHy = sim.state()
         gtrace = sim.read_probes()
@@ -456,13 +468,13 @@ def test_wavefront_batched_grids_vs_oracle(fd, oracle, monkeypatch):
 
 
 def test_wavefront_equals_tile_kernel_large(fd, monkeypatch):
-    """6000 x 5000 fp32, 40 steps near the Ricker peak: the wavefront strips (packed and scalar, 8 and 12 levels, and
-    whatever k = 0 picks) and the persistent TMA tile kernel (FDTD2D_WAVE_MIN_TILES huge) must agree bit for bit."""
+    """6000 x 5000 fp32, 40 steps near the Ricker peak: the wavefront strips (8 and 12 levels, with and without the ring
+    strips, and whatever k = 0 picks) and the persistent TMA tile kernel (wavefront option off) must agree bit for bit."""
     outs = []
-    for min_tiles, x2, k in (("100000000", "1", 8), ("0", "1", 8), ("0", "0", 8), ("0", "1", 12), ("0", "0", 12), ("0", "1", 0)):
-        monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", min_tiles)
-        monkeypatch.setenv("FDTD2D_WAVE_X2", x2)
+    for wavefront, ring, k in ((0, 1, 8), (1, 1, 8), (1, 0, 8), (1, 1, 12), (1, 1, 0)):
         with fd.Simulation(6000, 5000, np.float32, dt=DT, dx=DX) as sim:
+            sim.set_option("wavefront", wavefront)  # per-handle options instead of environment variables
+            sim.set_option("ring_strips", ring)
             sim.set_materials_random(seed=5, span=9.0)
             sim.set_point_source(3000, 2500, 700, FC)
             sim.set_probes([(3000, 2510), (10, 10), (5990, 4990)], 700)
@@ -522,3 +534,164 @@ def test_two_handles_in_two_host_threads(fd, monkeypatch):
     for r in res:
         for a, b in zip(r, ref):
             assert_bits(a, b, "two threads vs one handle alone")
+
+
+# --------------------------------------------------------------------------------------------
+# the default path at the size the bench runs it
+# --------------------------------------------------------------------------------------------
+def _window_check(c_oracle, state0, state, ce, ch, coef, n, windows, m, what):
+    """A window of a big run equals the oracle run on the window grown by m >= n + 6 cells.  Windows that touch the left
+    or right edge of the grid keep that edge (Mur columns included: they read only inward); the other sides are cut m
+    cells outside the window, far enough for nothing stale to arrive."""
+    Ez0, Hx0, Hy0 = state0
+    Ez, Hx, Hy = state
+    R, C = Ez0.shape
+    for (r0, c0, h, w) in windows:
+        a, b_ = r0 - m, r0 + h + m
+        c_, d = max(0, c0 - m), min(C, c0 + w + m)
+        wEz, wHx, wHy = Ez0[a:b_, c_:d].copy(), Hx0[a:b_, c_:d - 1].copy(), Hy0[a:b_ - 1, c_:d].copy()
+        c_oracle.run(wEz, wHx, wHy, ce[a:b_, c_:d].copy(), ch[a:b_, c_:d].copy(), coef, n)
+        ro, co = r0 - a, c0 - c_
+        assert_bits(Ez[r0:r0 + h, c0:c0 + w], wEz[ro:ro + h, co:co + w], f"Ez window {what} at {(r0, c0)}")
+        wx = min(w, Hx.shape[1] - c0)
+        assert_bits(Hx[r0:r0 + h, c0:c0 + wx], wHx[ro:ro + h, co:co + wx], f"Hx window {what} at {(r0, c0)}")
+        assert_bits(Hy[r0:r0 + h, c0:c0 + w], wHy[ro:ro + h, co:co + w], f"Hy window {what} at {(r0, c0)}")
+
+
+def test_default_path_at_bench_size_vs_oracle(fd, oracle, engine):
+    """8192 x 16384 fp32, default options, k_temporal = 0, 24 steps from a random state: what bench.py's cfg3 runs (the
+    packed wavefront with ring strips, automatic run lengths).  Three windows against the C oracle: one in the middle,
+    one on the left ring strip (Mur columns included), one straddling the boundary between two runs of rows."""
+    if engine == "tiled":
+        pytest.skip("one kernel choice is enough for a 8192 x 16384 grid")
+    c_oracle, npo = oracle
+    R, C, n, m = 8192, 16384, 24, 32
+    rng = np.random.default_rng(8)
+    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
+        sim.set_materials_random(seed=2026, span=9.0)
+        Ez0 = (1e-3 * rng.standard_normal((R, C), dtype=np.float32))
+        Hx0 = (1e-6 * rng.standard_normal((R, C - 1), dtype=np.float32))
+        Hy0 = (1e-6 * rng.standard_normal((R - 1, C), dtype=np.float32))
+        sim.set_state(Ez0, Hx0, Hy0)
+        ce, ch, mur = sim.coefficients()
+        info = sim.plan_info(8)
+        assert info["wave_runs"] > 1000 and info["ring_strips"] == 1 and info["tma_tiles"] == 0, info
+        sim.step(n, 0)
+        assert sim.pass_count == 3
+        Ez, Hx, Hy = sim.state()
+    # run boundaries: the planner cuts the ~8000 plain rows into equal runs; rows 2000..2100 and 4000..4100 hold several
+    windows = [(5000, 9000, 64, 96), (3000, 0, 64, 40), (2000, 12000, 100, 64), (4000, 16384 - 40, 100, 40)]
+    _window_check(c_oracle, (Ez0, Hx0, Hy0), (Ez, Hx, Hy), ce, ch, mur[0], n, windows, m, "default path")
+
+
+def test_fp64_wavefront_large_vs_oracle_windows(fd, oracle, engine):
+    """4096 x 4096 fp64 with the default choice (8 levels on 64-column strips): windows against the C oracle, and the
+    whole state against the tile kernel (wavefront option off)."""
+    if engine == "tiled":
+        pytest.skip("one kernel choice is enough")
+    c_oracle, npo = oracle
+    R = C = 4096
+    n, m = 16, 24
+    rng = np.random.default_rng(9)
+    Ez0 = 1e-3 * rng.standard_normal((R, C))
+    Hx0 = 1e-6 * rng.standard_normal((R, C - 1))
+    Hy0 = 1e-6 * rng.standard_normal((R - 1, C))
+    outs = []
+    for wavefront in (1, 0):
+        with fd.Simulation(R, C, np.float64, dt=DT, dx=DX) as sim:
+            sim.set_option("wavefront", wavefront)
+            sim.set_materials_random(seed=31, span=9.0)
+            sim.set_state(Ez0, Hx0, Hy0)
+            if wavefront:
+                ce, ch, mur = sim.coefficients()
+                assert sim.plan_info(8)["wave_runs"] > 1000
+            sim.step(n, 0)
+            assert sim.pass_count == (2 if wavefront else 4)
+            outs.append(sim.state())
+    for a, b in zip(*outs):
+        assert_bits(a, b, "fp64 wavefront vs tile kernel")
+    _window_check(c_oracle, (Ez0, Hx0, Hy0), outs[0], ce, ch, mur[0], n, [(2000, 2000, 64, 96), (1000, 0, 48, 40)], m, "fp64 wavefront")
+
+
+# --------------------------------------------------------------------------------------------
+# grids below 11 rows / columns: the reference's statement order (grid_small.cuh) against the reference's own outputs
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_small_grids_vs_reference_golden(fd, golden_dir, dtype):
+    g = np.load(os.path.join(golden_dir, "small_grids.npz"))
+    for R, C in (tuple(int(v) for v in sz) for sz in g["sizes"]):
+        k = f"{dtype}_{R}x{C}"
+        eps, mu = g[k + "_eps"], g[k + "_mu"]
+        Ez, Hx, Hy = g[k + "_Ez0"].copy(), g[k + "_Hx0"].copy(), g[k + "_Hy0"].copy()
+        fd.update_Hx_Hy(Ez, Hx, Hy, mu, eps, DT, DX)
+        assert_bits(Hx, g[k + "_Hx1"], f"Hx after update_Hx_Hy {R}x{C}")
+        assert_bits(Hy, g[k + "_Hy1"], f"Hy after update_Hx_Hy {R}x{C}")
+        fd.update_Ez(Ez, Hx, Hy, mu, eps, DT, DX)
+        assert_bits(Ez, g[k + "_Ez1"], f"Ez after update_Ez {R}x{C}")
+        src = tuple(int(v) for v in g[k + "_src"])
+        for pieces in ((30,), (1, 7, 22)):
+            with fd.Simulation(R, C, dtype, dt=DT, dx=DX) as sim:
+                sim.set_materials(eps, mu)
+                sim.set_state(g[k + "_Ez0"], g[k + "_Hx0"], g[k + "_Hy0"])
+                sim.set_point_source(src[0], src[1], 680, FC)
+                sim.set_probes([tuple(p) for p in g[k + "_probes"]], 680)
+                sim.step_index = 650
+                for n in pieces:
+                    sim.step(n, 3)  # (k_temporal does not apply to these grids)
+                Ez, Hx, Hy = sim.state()
+                trace = sim.read_probes(650, 30)
+            assert_bits(trace, g[k + "_trace"], f"probe trace {R}x{C}")
+            assert_bits(Ez, g[k + "_Ez"], f"Ez {R}x{C}")
+            assert_bits(Hx, g[k + "_Hx"], f"Hx {R}x{C}")
+            assert_bits(Hy, g[k + "_Hy"], f"Hy {R}x{C}")
+    fd.release_handles()
+
+
+def test_small_grids_batched_vs_oracle(fd, oracle):
+    c_oracle, npo = oracle
+    B, R, C, n = 5, 9, 14, 25
+    rng = np.random.default_rng(77)
+    probs = [_random_problem(rng, R, C, "float32") for _ in range(B)]
+    eps, mu, Ez, Hx, Hy = (np.stack([p_[i] for p_ in probs]) for i in range(5))
+    tables = np.stack([npo.source_table("ricker", n, DT, FC + 1e9 * b) + 0.5 for b in range(B)])
+    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX, batch=B) as sim:
+        sim.set_materials(eps, mu)
+        sim.set_state(Ez, Hx, Hy)
+        sim.set_sources([(b, 4, 5 + b, b) for b in range(B)], tables)
+        sim.set_probes([(b, 4, 6) for b in range(B)], n)
+        sim.step(n)
+        gEz, gHx, gHy = sim.state()
+        gtrace = sim.read_probes()
+    for b in range(B):
+        ce, ch, coef = c_oracle.coefficients(eps[b], mu[b], DT, DX, np.dtype(np.float32))
+        oEz, oHx, oHy = Ez[b].copy(), Hx[b].copy(), Hy[b].copy()
+        otr = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, n, tables[b], [(4, 5 + b)], [(4, 6)])
+        assert_bits(gEz[b], oEz, f"Ez grid {b}")
+        assert_bits(gHx[b], oHx, f"Hx grid {b}")
+        assert_bits(gHy[b], oHy, f"Hy grid {b}")
+        assert_bits(gtrace[:, b], otr[:, 0], f"probe grid {b}")
+
+
+# --------------------------------------------------------------------------------------------
+# per-handle options (fdtd2d_set_option): they choose kernels, never result bits
+# --------------------------------------------------------------------------------------------
+def test_options_are_per_handle_and_change_only_the_kernel(fd, monkeypatch):
+    monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", "7")  # defaults are read when a handle is created ...
+    R, C, n = 1500, 2100, 24
+    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as a, fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as b:
+        monkeypatch.setenv("FDTD2D_WAVE_MIN_TILES", "100000000")  # ... not afterwards
+        assert a.get_option("wave_min_tiles") == 7 and b.get_option("wave_min_tiles") == 7
+        b.set_option("wavefront", 0)
+        assert a.get_option("wavefront") == 1 and b.get_option("wavefront") == 0
+        outs = []
+        for sim in (a, b):
+            sim.set_kernel_variant(2)
+            sim.set_materials_random(4, 9.0)
+            sim.set_point_source(R // 2, C // 2, 700, FC)
+            sim.step_index = 640
+            sim.step(n, 8)
+            outs.append(sim.state())
+        assert a.plan_info(8)["wave_runs"] > 0 and a.plan_info(8)["tma_tiles"] == 0
+        assert b.plan_info(8)["wave_runs"] == 0 and b.plan_info(8)["tma_tiles"] > 0
+    for x, y in zip(*outs):
+        assert_bits(x, y, "wavefront option on vs off")

@@ -1,6 +1,9 @@
 """y-slab decomposition on the GPU: 2, 3 and 4 slabs must reproduce the single-domain result bit for bit
 (no reduction is involved).  Runs the slabs of one grid from one process (InProcessSlabs) so that it
-also works on a one-GPU box; with several GPUs visible the slabs are spread over them (peer copies)."""
+also works on a one-GPU box; with several GPUs visible the slabs are spread over them.  Every test runs with both
+ways of moving the halo rows: "p2p" -- peer links, the band tasks of the stepping kernels store into the neighbour's
+ghost rows and raise its flag, exactly the production path of the one-process-per-GPU layout -- and "copy" -- device
+copies of the halo blocks between passes."""
 import numpy as np
 import pytest
 
@@ -24,9 +27,14 @@ def plain_tile_kernel(request, monkeypatch):
     return request.param
 
 
+@pytest.fixture(params=["p2p", "copy"])
+def exchange(request):
+    return request.param
+
+
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
 @pytest.mark.parametrize("world,k", [(2, 4), (3, 8), (4, 5)])
-def test_slabs_match_single_domain_and_oracle(world, k, dtype):
+def test_slabs_match_single_domain_and_oracle(world, k, dtype, exchange):
     import fdtd2d_b200 as fd
     from oracle import c_oracle, numpy_oracle as npo
 
@@ -46,7 +54,7 @@ def test_slabs_match_single_domain_and_oracle(world, k, dtype):
     oEz, oHx, oHy = Ez.copy(), Hx.copy(), Hy.copy()
     otrace = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, n, amp, cells, probes, omp=True)
 
-    grp = fd.InProcessSlabs(R, C, dtype, dt=DT, dx=DX, world=world, devices=_devices(), halo=8)
+    grp = fd.InProcessSlabs(R, C, dtype, dt=DT, dx=DX, world=world, devices=_devices(), halo=8, exchange=exchange)
     try:
         for s in grp.slabs:
             lo, hi = s.row0, s.row0 + s.local_rows
@@ -57,6 +65,10 @@ def test_slabs_match_single_domain_and_oracle(world, k, dtype):
         grp.step(n, k)
         gEz, gHx, gHy = grp.gather()
         traces = [s.read_probes(0, n) for s in grp.slabs]
+        if exchange == "p2p":
+            for s in grp.slabs:
+                st = s.sim.peer_status()
+                assert st["error"] == 0 and st["passes"] == -(-n // k), st
     finally:
         grp.close()
     assert np.array_equal(gEz, oEz) and np.array_equal(gHx, oHx) and np.array_equal(gHy, oHy)
@@ -69,18 +81,19 @@ def test_slabs_match_single_domain_and_oracle(world, k, dtype):
     assert np.array_equal(total, otrace)
 
 
-def test_large_slabs_vs_single_domain_fast_path():
-    """4 slabs of a 4096 x 3000 fp32 grid (fast kernel on the plain tiles) == single domain, k = 8."""
+def test_large_slabs_vs_single_domain_fast_path(exchange, plain_tile_kernel):
+    """4 slabs of a 4096 x 3000 fp32 grid (wavefront runs incl. the band runs, or TMA tiles) == single domain, k = 8,
+    with a remainder pass (44 = 5 x 8 + 4)."""
     import fdtd2d_b200 as fd
 
-    R, C, n = 4096, 3000, 40
+    R, C, n = 4096, 3000, 44
     with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
         sim.set_materials_random(9, 9.0)
         sim.set_point_source(R // 2, C // 2, 700, FC)
         sim.step_index = 640
         sim.step(n, 8)
         ref = sim.state()
-    grp = fd.InProcessSlabs(R, C, np.float32, dt=DT, dx=DX, world=4, devices=_devices(), halo=8)
+    grp = fd.InProcessSlabs(R, C, np.float32, dt=DT, dx=DX, world=4, devices=_devices(), halo=8, exchange=exchange)
     try:
         for s in grp.slabs:
             s.set_materials_random(9, 9.0)
@@ -88,14 +101,19 @@ def test_large_slabs_vs_single_domain_fast_path():
             s.step_index = 640
         grp.step(n, 8)
         got = grp.gather()
+        mid = grp.slabs[1].sim.plan_info(8)
+        if plain_tile_kernel == "wavefront":  # a middle slab: every band row on a band run (the source tile aside)
+            assert mid["wave_band_runs"] > 0 and mid["band_tasks_top"] > 0 and mid["band_tasks_bottom"] > 0, mid
     finally:
         grp.close()
     for a, b in zip(got, ref):
         assert np.array_equal(a, b)
 
 
-def test_multiprocess_nccl_slabs():
-    """One rank per GPU over NCCL (the production layout).  Needs >= 2 GPUs; skipped on a 1-GPU box."""
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_multiprocess_slabs(mode):
+    """One rank per GPU (the production layout): peer links over CUDA IPC, or NCCL send/recv.  Needs >= 2 GPUs; skipped
+    on a 1-GPU box (bench.py prints the same check as `slab_parity` on whatever box it runs on)."""
     import os
     import subprocess
     import sys
@@ -108,6 +126,6 @@ def test_multiprocess_nccl_slabs():
     n = 2 if n < 4 else 4
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
-           "127.0.0.1", "--master-port", "29611", os.path.join(root, "tests", "mp_slab_check.py")]
+           "127.0.0.1", "--master-port", "29611" if mode == "p2p" else "29612", os.path.join(root, "tests", "mp_slab_check.py"), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK bit-exact" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

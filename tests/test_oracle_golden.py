@@ -111,6 +111,42 @@ def test_random_runs(golden_dir, case, dtype, impl):
     assert np.array_equal(Ez, g[k + "_Ez"]) and np.array_equal(Hx, g[k + "_Hx"]) and np.array_equal(Hy, g[k + "_Hy"])
 
 
+SMALL = [(6, 6), (6, 23), (7, 9), (10, 10), (8, 40), (40, 7), (10, 11), (11, 10), (9, 300)]
+
+
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("shape", SMALL)
+def test_small_grids(golden_dir, shape, dtype, impl):
+    """Below 11 rows / columns the reference's boundary statements overlap (statement order matters); 6 is the smallest
+    grid its indexing allows.  One call of each function and a 30-step run against the reference's own outputs."""
+    g = np.load(os.path.join(golden_dir, "small_grids.npz"))
+    k = f"{dtype}_{shape[0]}x{shape[1]}"
+    eps, mu = g[k + "_eps"], g[k + "_mu"]
+    ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(dtype))
+    Ez, Hx, Hy = g[k + "_Ez0"].copy(), g[k + "_Hx0"].copy(), g[k + "_Hy0"].copy()
+    if impl == "numpy":
+        npo.update_Hx_Hy(Ez, Hx, Hy, mu, eps, DT, DX)
+    else:
+        c_oracle.update_h(Ez, Hx, Hy, ch)
+    assert np.array_equal(Hx, g[k + "_Hx1"]) and np.array_equal(Hy, g[k + "_Hy1"])
+    if impl == "numpy":
+        npo.update_Ez(Ez, Hx, Hy, mu, eps, DT, DX)
+    else:
+        c_oracle.update_e(Ez, Hx, Hy, ce, coef)
+    assert np.array_equal(Ez, g[k + "_Ez1"])
+    Ez, Hx, Hy = g[k + "_Ez0"].copy(), g[k + "_Hx0"].copy(), g[k + "_Hy0"].copy()
+    probes = [tuple(p) for p in g[k + "_probes"]]
+    src = tuple(int(v) for v in g[k + "_src"])
+    if impl == "numpy":
+        _, _, _, trace = npo.run(Ez, Hx, Hy, mu, eps, DT, DX, 30, source=(src[0], src[1], FC, "ricker"), step0=650, probes=probes)
+    else:
+        amp = npo.source_table("ricker", 30, DT, FC, step0=650)
+        trace = c_oracle.run(Ez, Hx, Hy, ce, ch, coef, 30, amp, [src], probes)
+    assert np.array_equal(trace, g[k + "_trace"])
+    assert np.array_equal(Ez, g[k + "_Ez"]) and np.array_equal(Hx, g[k + "_Hx"]) and np.array_equal(Hy, g[k + "_Hy"])
+
+
 def test_material_and_sources(golden_dir):
     g = np.load(os.path.join(golden_dir, "material_sources.npz"))
     png = os.path.join(golden_dir, "structure.png")
