@@ -535,12 +535,11 @@ def main():
         barrier()
         strong_line = strong_scaling(args, fd, torch, dist, rank, world, local_rank)
         barrier()
-        if rank == 0:
+        if world == 1:  # (the other configurations are single-GPU workloads: measured by the N = 1 run only)
             others = other_configs(args, fd, torch)
-        barrier()
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if world == 1 and not args.no_cpu:  # the CPU baseline is timed by the N = 1 run only
         crow = min(4096, wl["rows"])
         n = max(2, int(6e8 / (crow * cols)))  # ~10 s of numpy work at ~60-90 Mcell/s
         v, el = cpu_reference_rate(crow, cols, n)

@@ -210,8 +210,11 @@ def courant(eps, mu, dt, dx):
 def seismic_lut(n: int = 256):
     """matplotlib's "seismic" lookup table rebuilt from its published construction: five anchor colours
     (matplotlib/_cm.py `_seismic_data`) evenly spaced on [0, 1], `LinearSegmentedColormap.from_list`
-    -> `_create_lookup_table(N=256, gamma=1)`.  matplotlib itself is absent from the authoring
-    container, so this table is UNPINNED against the real library (tests compare when it is importable)."""
+    -> `_create_lookup_table(N=256, gamma=1)`.  matplotlib itself is absent from the authoring container; the table
+    is PINNED by images the reference's own colour pipeline wrote (python-src/Ez.png, assets/ring_resonator.png,
+    assets/Ez_tiled.png): every distinct pixel colour in them is reproduced bit for bit by this table and the blend of
+    main.py:171-177, 240 of the 256 entries being exercised (oracle/make_golden_colormap.py ->
+    tests/golden/seismic_pixels.npz -> tests/test_host_cpu.py); tests also compare with matplotlib when it is importable."""
     anchors = np.array([(0.0, 0.0, 0.3), (0.0, 0.0, 1.0), (1.0, 1.0, 1.0), (1.0, 0.0, 0.0), (0.5, 0.0, 0.0)])
     x = np.linspace(0, 1, len(anchors)) * (n - 1)
     xind = (n - 1) * np.linspace(0, 1, n)

@@ -135,10 +135,47 @@ def test_seismic_lut_construction():
         cm = matplotlib.colormaps["seismic"]
         assert np.array_equal(cm(np.arange(256))[:, :3], lut)
     except ImportError:
-        pass  # matplotlib is not installed here: the table is pinned only to its published construction
+        pass  # matplotlib is not installed here: the table is pinned by the reference's own images (next test)
     g = fd.eps_background(np.array([[8.85418e-12, 2 * 8.85418e-12], [10 * 8.85418e-12, 8.85418e-12]]))
     assert g.dtype == np.uint8 and g[0, 0] == 255 and g[1, 0] == 128
     assert (fd.eps_background(np.full((3, 3), 8.85418e-12)) == 255).all()
+
+
+def _blend_colours(lut, grays):
+    """Every colour the reference's pipeline can write: trunc((lut * 0.7 + gray / 255 * (1 - 0.7)) * 255), main.py:171-177."""
+    out = set()
+    for g in grays:
+        c = ((lut * 0.7 + (g / 255) * (1 - 0.7)) * 255).astype(np.uint8)
+        out.update(map(tuple, c.tolist()))
+    return out
+
+
+def test_seismic_lut_pinned_by_the_references_own_images(golden_dir):
+    """matplotlib is not installed, but the reference ships frames written by its colour pipeline (utils.plot_Ez, the
+    twin of capture_snapshot): every distinct pixel colour of three such 1000 x 1000 images (tests/golden/
+    seismic_pixels.npz, made by oracle/make_golden_colormap.py) must come out of the rebuilt table + blend formula, bit for
+    bit.  The white background alone exercises 240 of the 256 entries; plausible wrong constructions of the table fail."""
+    g = np.load(os.path.join(golden_dir, "seismic_pixels.npz"))
+    lut = fd.seismic_lut()
+    everything = _blend_colours(lut, range(128, 256))  # backgrounds are 128..255 (main.py:165), 255 where eps is uniform
+    white = {c: i for i, c in enumerate(map(tuple, ((lut * 0.7 + 0.3) * 255).astype(np.uint8).tolist()))}
+    used = set()
+    for i in range(len(g["images"])):
+        cols = list(map(tuple, g[f"colours_{i}"].tolist()))
+        missing = [c for c in cols if c not in everything]
+        assert not missing, f"{g['images'][i]}: {len(missing)} of {len(cols)} colours cannot come from this table, e.g. {missing[:5]}"
+        used |= {white[c] for c in cols if c in white}
+        # the commonest colour is a zero field on white: table index 128 (x = 0.5 -> 0.5 * 256 = 128)
+        top = tuple(g[f"colours_{i}"][np.argmax(g[f"counts_{i}"])].tolist())
+        assert top == tuple(((lut[128] * 0.7 + 0.3) * 255).astype(np.uint8).tolist())
+    assert len(used) >= 240, len(used)
+    # negative controls: tables sampled half a step off, or over 255 intervals with a wrong end point, do not explain the images
+    anchors = np.asarray(fd.snapshot.SEISMIC_ANCHORS)
+    for xs in ((np.arange(256) + 0.5) / 256, np.arange(256) / 256):
+        wrong = np.stack([np.interp(xs, np.linspace(0, 1, 5), anchors[:, ch]) for ch in range(3)], axis=1)
+        bad = _blend_colours(wrong, range(128, 256))
+        cols = list(map(tuple, g["colours_2"].tolist()))
+        assert sum(c not in bad for c in cols) > 50
 
 
 def test_bench_reference_arm_prints_the_contract_line():
