@@ -16,7 +16,8 @@ from .api import (EPSILON0, MU0, capture_snapshot, grid_init, material_init, rel
                   update_Hx_Hy)
 from .build import LIB_PATH, build
 from .distributed import HaloExchange, InProcessSlabs, SlabSimulation, exchange_peer_blobs, slab_rows
-from . import dataset, driver
+from . import dataset, driver, snapshot, structure
+from .structure import RegionDrawer
 from .dataset import generate_data
 from .snapshot import eps_background, make_video_from_frames, seismic_lut
 from .simulation import (Simulation, courant_number, ricker_amplitude, sinusoidal_amplitude, source_table)
@@ -25,5 +26,5 @@ __all__ = [
     "grid_init", "material_init", "update_Hx_Hy", "update_Ez", "ricker", "sinusoidal", "Simulation",
     "capture_snapshot", "make_video_from_frames", "seismic_lut", "eps_background",
     "courant_number", "ricker_amplitude", "sinusoidal_amplitude", "source_table", "build", "LIB_PATH",
-    "Fdtd2dError", "EXPORTED_SYMBOLS", "generate_data", "dataset", "driver", "SlabSimulation", "InProcessSlabs", "HaloExchange", "slab_rows", "exchange_peer_blobs", "DEFAULT_K", "EPSILON0", "MU0", "release_handles",
+    "Fdtd2dError", "EXPORTED_SYMBOLS", "generate_data", "dataset", "driver", "structure", "RegionDrawer", "SlabSimulation", "InProcessSlabs", "HaloExchange", "slab_rows", "exchange_peer_blobs", "DEFAULT_K", "EPSILON0", "MU0", "release_handles",
 ]

@@ -49,6 +49,12 @@ _SIGNATURES = {
     "fdtd2d_set_mur_coef": ([_vp, _vp], _i),
     "fdtd2d_set_materials_random": ([_vp, _u64, _d, _d, _d], _i),
     "fdtd2d_set_materials_gray": ([_vp, _vp, _d, _d, _d], _i),
+    "fdtd2d_canvas_clear": ([_vp, _i], _i),
+    "fdtd2d_canvas_rect": ([_vp, _i, _i, _i, _i, _i, _i], _i),
+    "fdtd2d_canvas_ellipse": ([_vp, _i, _i, _i, _i, _i, _i, _i], _i),
+    "fdtd2d_canvas_segment": ([_vp, _i, _d, _d, _d, _d, _d, _i], _i),
+    "fdtd2d_canvas_download": ([_vp, _vp], _i),
+    "fdtd2d_canvas_apply": ([_vp, _d, _d, _d], _i),
     "fdtd2d_generate_materials_blobs": ([_vp, _u64, _vp, _d, _d, _d, _d, _d, _vp], _i),
     "fdtd2d_hash_uniform": ([_u64, _u32, _u32, _u32], _d),
     "fdtd2d_download_coeffs": ([_vp, _vp, _vp, _vp], _i),

@@ -24,6 +24,7 @@
 #include "grid_resident.cuh"
 #include "strip_wave.cuh"
 #include "grid_small.cuh"
+#include "structure.cuh"
 
 using namespace fdtd2d;
 
@@ -141,6 +142,7 @@ struct fdtd2d_sim {
     unsigned char* d_gray = nullptr;  // snapshot background (Rl x C per grid)
     unsigned char* d_rgb = nullptr;   // one rendered frame (Rl x C x 3)
     double* d_lut = nullptr;          // 256 x 3 colormap
+    unsigned char* d_canvas = nullptr;  // structure canvas (Rl x C per grid), fdtd2d_canvas_*
     // y-slabs: flag block (common.cuh FLAG_*), the neighbours' buffers, passes stepped with a peer attached
     unsigned* d_slab_flags = nullptr;
     PeerLink peer[2];
@@ -1431,6 +1433,7 @@ int fdtd2d_destroy(fdtd2d_sim* s) {
     cudaFree(s->d_gray);
     cudaFree(s->d_rgb);
     cudaFree(s->d_lut);
+    cudaFree(s->d_canvas);
     cudaFree(s->d_flag);
     cudaFree(s->d_slab_flags);
     free_plans(s);
@@ -2249,6 +2252,106 @@ int fdtd2d_peer_status(fdtd2d_sim* s, uint32_t* flags_out) {
     }
     flags_out[2] = f[FLAG_IN_TOP], flags_out[3] = f[FLAG_IN_BOT], flags_out[4] = f[FLAG_ERR];
     return 0;
+}
+
+// ---- structure drawing on the device (structure.cuh): replaces RegionDrawer (region_drawer.py:5-87) + the image -> eps
+// mapping of material_init (main.py:109-123) ------------------------------------------------------------------
+static Canvas canvas_of(const fdtd2d_sim* s) {
+    Canvas cv;
+    cv.px = s->d_canvas, cv.Rl = s->Rl, cv.C = s->C, cv.row0 = s->row0, cv.grid_stride = (long long)s->Rl * s->C;
+    return cv;
+}
+static int canvas_blocks(fdtd2d_sim* s, long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)sm_count(s) * 16)); }
+
+int fdtd2d_canvas_clear(fdtd2d_sim* s, int value) {
+    REQUIRE(s && value >= 0 && value <= 255, "bad argument");
+    USE_DEVICE(s);
+    const long long n = (long long)s->Rl * s->C * s->batch;
+    if (!s->d_canvas) CUDA_TRY(cudaMalloc(&s->d_canvas, (size_t)n));
+    canvas_fill_kernel<<<canvas_blocks(s, n), 256, 0, s->stream>>>(s->d_canvas, n, (unsigned char)value);
+    CUDA_TRY(cudaGetLastError());
+    s->launches += 1;
+    return 0;
+}
+
+int fdtd2d_canvas_rect(fdtd2d_sim* s, int grid, int x0, int y0, int x1, int y1, int value) {
+    REQUIRE(s && grid >= 0 && grid < s->batch && value >= 0 && value <= 255, "bad argument");
+    if (!s->d_canvas) return fail(FDTD2D_ESTATE, "no canvas: call fdtd2d_canvas_clear first");
+    USE_DEVICE(s);
+    // clip to the canvas of this handle (y in global rows)
+    x0 = std::max(x0, 0), x1 = std::min(x1, s->C - 1), y0 = std::max(y0, s->row0), y1 = std::min(y1, s->row0 + s->Rl - 1);
+    if (x0 > x1 || y0 > y1) return 0;
+    const long long n = (long long)(x1 - x0 + 1) * (y1 - y0 + 1);
+    canvas_rect_kernel<<<canvas_blocks(s, n), 256, 0, s->stream>>>(canvas_of(s), grid, x0, y0, x1, y1, (unsigned char)value);
+    CUDA_TRY(cudaGetLastError());
+    s->launches += 1;
+    return 0;
+}
+
+int fdtd2d_canvas_ellipse(fdtd2d_sim* s, int grid, int x0, int y0, int x1, int y1, int width, int value) {
+    REQUIRE(s && grid >= 0 && grid < s->batch && value >= 0 && value <= 255, "bad argument");
+    if (!s->d_canvas) return fail(FDTD2D_ESTATE, "no canvas: call fdtd2d_canvas_clear first");
+    if (x1 < x0 || y1 < y0 || (x1 - x0) + (y1 - y0) < 1) return 0;  // (PIL draws nothing for an inverted or a one-cell box)
+    USE_DEVICE(s);
+    const int a = x1 - x0, b = y1 - y0;
+    int ix0 = 0, iy0 = 0, ix1 = -1, iy1 = -1;  // inner box of a ring (empty: filled ellipse)
+    if (width > 0 && a - 2 * width >= 0 && b - 2 * width >= 0 && a + b - 4 * width >= 1) ix0 = x0 + width, iy0 = y0 + width, ix1 = x1 - width, iy1 = y1 - width;
+    const int rows = b / 2 + 1, irows = ix1 >= ix0 ? (iy1 - iy0) / 2 + 1 : 0;
+    int* d_half = nullptr;
+    CUDA_TRY(cudaMalloc(&d_half, sizeof(int) * (size_t)(rows + irows + 1)));
+    ellipse_walk_kernel<<<1, 32, 0, s->stream>>>(a, b, d_half);
+    if (irows) ellipse_walk_kernel<<<1, 32, 0, s->stream>>>(ix1 - ix0, iy1 - iy0, d_half + rows);
+    const long long n = (long long)(a + 1) * (b + 1);
+    canvas_ellipse_kernel<<<canvas_blocks(s, n), 256, 0, s->stream>>>(canvas_of(s), grid, x0, y0, x1, y1, d_half, ix0, iy0, ix1, iy1, d_half + rows,
+                                                                   (unsigned char)value);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_half);
+    if (e != cudaSuccess) return fail(FDTD2D_ECUDA, "ellipse kernels failed: %s", cudaGetErrorString(e));
+    s->launches += irows ? 3 : 2;
+    return 0;
+}
+
+int fdtd2d_canvas_segment(fdtd2d_sim* s, int grid, double x0, double y0, double x1, double y1, double width, int value) {
+    REQUIRE(s && grid >= 0 && grid < s->batch && value >= 0 && value <= 255 && width >= 0, "bad argument");
+    if (!s->d_canvas) return fail(FDTD2D_ESTATE, "no canvas: call fdtd2d_canvas_clear first");
+    USE_DEVICE(s);
+    const double hw = 0.5 * width + 1.0;
+    const int bx0 = std::max(0, (int)floor(std::min(x0, x1) - hw)), bx1 = std::min(s->C - 1, (int)ceil(std::max(x0, x1) + hw));
+    const int by0 = std::max(s->row0, (int)floor(std::min(y0, y1) - hw)), by1 = std::min(s->row0 + s->Rl - 1, (int)ceil(std::max(y0, y1) + hw));
+    if (bx0 > bx1 || by0 > by1) return 0;
+    const long long n = (long long)(bx1 - bx0 + 1) * (by1 - by0 + 1);
+    canvas_segment_kernel<<<canvas_blocks(s, n), 256, 0, s->stream>>>(canvas_of(s), grid, x0, y0, x1, y1, width, bx0, by0, bx1, by1, (unsigned char)value);
+    CUDA_TRY(cudaGetLastError());
+    s->launches += 1;
+    return 0;
+}
+
+int fdtd2d_canvas_download(fdtd2d_sim* s, unsigned char* gray) {
+    REQUIRE(s && gray, "null argument");
+    if (!s->d_canvas) return fail(FDTD2D_ESTATE, "no canvas: call fdtd2d_canvas_clear first");
+    USE_DEVICE(s);
+    CUDA_TRY(cudaMemcpyAsync(gray, s->d_canvas, (size_t)s->Rl * s->C * s->batch, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int fdtd2d_canvas_apply(fdtd2d_sim* s, double black_point, double dt, double dx) {
+    REQUIRE(s, "handle is null");
+    if (!s->d_canvas) return fail(FDTD2D_ESTATE, "no canvas: call fdtd2d_canvas_clear first");
+    USE_DEVICE(s);
+    if (int rc = begin_work(s)) return rc;
+    const double eps0 = 8.85418e-12, mu0 = 4 * 3.141592653589793 * 1e-7;  // main.py:100-101
+    const long long n = (long long)s->Rl * s->C * s->batch;
+    if (s->dtype == FDTD2D_F32)
+        gray_materials_kernel<float><<<canvas_blocks(s, n), 256, 0, s->stream>>>(s->d_canvas, (float*)s->ce, (float*)s->ch, s->Rl, s->C, (int)s->pitch,
+                                                                               (long long)s->grid_elems, s->batch, black_point, eps0, mu0);
+    else
+        gray_materials_kernel<double><<<canvas_blocks(s, n), 256, 0, s->stream>>>(s->d_canvas, (double*)s->ce, (double*)s->ch, s->Rl, s->C, (int)s->pitch,
+                                                                                (long long)s->grid_elems, s->batch, black_point, eps0, mu0);
+    CUDA_TRY(cudaGetLastError());
+    s->launches += 1;
+    return finish_materials(s, dt, dx, true);
 }
 
 int fdtd2d_set_snapshot_background(fdtd2d_sim* s, const unsigned char* gray, const double* lut) {

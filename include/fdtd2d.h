@@ -122,6 +122,23 @@ int fdtd2d_set_materials_random(fdtd2d_sim* s, uint64_t seed, double span, doubl
  * eps = (1 + (black_point - 1) * (1 - gray/255)) * eps0 in float64, casts to the run dtype, sets mu = mu0 and
  * then the coefficient maps exactly as fdtd2d_set_materials does.  1 byte per cell crosses PCIe. */
 int fdtd2d_set_materials_gray(fdtd2d_sim* s, const unsigned char* gray, double black_point, double dt, double dx);
+/* Structure drawing on the device: replaces RegionDrawer (region_drawer.py:5-87, PIL ImageDraw on an "L" canvas) together
+ * with the image -> permittivity mapping of material_init (main.py:109-123), so that a structure for a grid too large for
+ * the host never leaves the GPU.  The canvas has one uint8 cell per grid cell (x = column, y = GLOBAL row; a slab handle
+ * draws its local rows of the global picture), starts white (255 = eps0) and is drawn black (0 = black_point * eps0).
+ *   fdtd2d_canvas_rect     inclusive rectangle: what ImageDraw.line(width) paints for a horizontal / vertical segment;
+ *   fdtd2d_canvas_ellipse  width <= 0: ImageDraw.ellipse(box, fill) bit for bit (Pillow's integer quarter walk);
+ *                          width > 0: the ring between that ellipse and the one of the box shrunk by `width` on each side
+ *                          (ImageDraw.ellipse(box, outline, width) up to a few cells along the inner edge);
+ *   fdtd2d_canvas_segment  slanted thick segment: the cells whose centre lies in the rectangle of that width;
+ *   fdtd2d_canvas_apply    canvas -> eps = (1 + (black_point - 1)(1 - g/255)) eps0 (float64, cast to the run dtype),
+ *                          mu = mu0, then the coefficient maps and the Mur coefficient as fdtd2d_set_materials. */
+int fdtd2d_canvas_clear(fdtd2d_sim* s, int value);
+int fdtd2d_canvas_rect(fdtd2d_sim* s, int grid, int x0, int y0, int x1, int y1, int value);
+int fdtd2d_canvas_ellipse(fdtd2d_sim* s, int grid, int x0, int y0, int x1, int y1, int width, int value);
+int fdtd2d_canvas_segment(fdtd2d_sim* s, int grid, double x0, double y0, double x1, double y1, double width, int value);
+int fdtd2d_canvas_download(fdtd2d_sim* s, unsigned char* gray);
+int fdtd2d_canvas_apply(fdtd2d_sim* s, double black_point, double dt, double dx);
 /* Random two-phase media of the dataset generator (diffusion_training.py:54-93), one per batch grid, generated
  * on the device: u = fdtd2d_hash_uniform(seed, grid, row, col) blurred with the grid's 15 x 15 kernel
  * weights[grid][15*15] (float32, zero padding, row-major accumulation, no FMA), eps = blur > 0.5 ? eps_hi : eps_lo,
