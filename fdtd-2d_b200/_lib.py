@@ -68,6 +68,7 @@ _SIGNATURES = {
     "fdtd2d_source_steps": ([_vp, _ip, _ip, ctypes.POINTER(_i64)], _i),
     "fdtd2d_set_kernel_variant": ([_vp, _i], _i),
     "fdtd2d_plan_host": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i], _i),
+    "fdtd2d_plan_host_fused": ([_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i], _i),
     "fdtd2d_plan_info": ([_vp, _i, _vp, _i], _i),
     "fdtd2d_launch_count": ([_vp, ctypes.POINTER(_i64)], _i),
     "fdtd2d_pass_count": ([_vp, ctypes.POINTER(_i64)], _i),

@@ -86,6 +86,13 @@ struct PassPlan {
     bool wave_ring = false;           // the list holds runs of the strips with the left / right Mur ring
     int band_expected[2] = {0, 0};    // band tasks (runs + edge tiles) next to the top / bottom neighbour
     int* d_ticket = nullptr;          // next run to hand out (reset before every launch)
+    // fused double pass (strip_wave.cuh): the runs of two consecutive passes in one ticket order; the phase-1 pieces next to
+    // edge tiles wait for a second, short launch
+    int n_fused = 0, n_deferred = 0, fuse_nblk = 0;
+    WaveTask* d_fused = nullptr;
+    WaveTask* d_deferred = nullptr;
+    unsigned* d_fuse_flags = nullptr;
+    size_t fuse_flag_bytes = 0;
 };
 
 // one neighbour slab as this process sees it
@@ -147,6 +154,7 @@ struct fdtd2d_sim {
     unsigned* d_slab_flags = nullptr;
     PeerLink peer[2];
     unsigned pass_seq = 0;
+    long long fused_pairs = 0, fused_checked = 0;  // fused double passes launched / covered by the last look at the error flag
     // fdtd2d_*_async: copies run on a stream of their own, ordered against this handle's stepping work by two events
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy = nullptr;  // the last asynchronous copy
@@ -491,14 +499,14 @@ static int check_ch_uniform(fdtd2d_sim* s) {
 // ---- wavefront launches --------------------------------------------------------------------------
 // One instantiation of the packed fp32 wavefront kernel: K levels, scalar or mapped dt/(mu*dx), P rows of prefetch, with /
 // without the ring-strip and the slab-band forms of the run.
-template <int K, bool UCH, int P, bool RING, bool SLAB>
+template <int K, bool UCH, int P, bool RING, int FLAVOUR>
 static int launch_wave_x2_t(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, int grid) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[s->device % MAX_DEVICES];
     const size_t smem = wave_smem_bytes(WAVE_NW, UCH);
-    if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_x2_kernel<K, UCH, P, RING, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_x2_kernel<K, UCH, P, RING, FLAVOUR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = true;
-    strip_wave_x2_kernel<K, UCH, P, RING, SLAB><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, UCH ? (float)s->ch_value : 0.0f,
+    strip_wave_x2_kernel<K, UCH, P, RING, FLAVOUR><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, UCH ? (float)s->ch_value : 0.0f,
                                                                                        0x8000000080000000ull);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -531,20 +539,30 @@ static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask
     const bool slab = s->has_top_nb || s->has_bot_nb;
     if (k == 12) {  // (runs for k = 12 are only built when the permeability is uniform)
         if (!uch || slab) return fail(FDTD2D_EINVAL, "the 12-level wavefront kernel needs uniform permeability and a whole grid");
-        return launch_wave_x2_t<12, true, 2, false, false>(s, p, tasks, n_tasks, ticket, grid);
+        return launch_wave_x2_t<12, true, 2, false, 0>(s, p, tasks, n_tasks, ticket, grid);
     }
     if (k != 8) return fail(FDTD2D_EINVAL, "no fp32 wavefront kernel for k=%d", k);
     const int sel = (uch ? 4 : 0) | (ring ? 2 : 0) | (slab ? 1 : 0);
     switch (sel) {
-        case 0: return launch_wave_x2_t<8, false, WAVE_P, false, false>(s, p, tasks, n_tasks, ticket, grid);
-        case 1: return launch_wave_x2_t<8, false, WAVE_P, false, true>(s, p, tasks, n_tasks, ticket, grid);
-        case 2: return launch_wave_x2_t<8, false, WAVE_P, true, false>(s, p, tasks, n_tasks, ticket, grid);
-        case 3: return launch_wave_x2_t<8, false, WAVE_P, true, true>(s, p, tasks, n_tasks, ticket, grid);
-        case 4: return launch_wave_x2_t<8, true, WAVE_P, false, false>(s, p, tasks, n_tasks, ticket, grid);
-        case 5: return launch_wave_x2_t<8, true, WAVE_P, false, true>(s, p, tasks, n_tasks, ticket, grid);
-        case 6: return launch_wave_x2_t<8, true, WAVE_P, true, false>(s, p, tasks, n_tasks, ticket, grid);
-        default: return launch_wave_x2_t<8, true, WAVE_P, true, true>(s, p, tasks, n_tasks, ticket, grid);
+        case 0: return launch_wave_x2_t<8, false, WAVE_P, false, 0>(s, p, tasks, n_tasks, ticket, grid);
+        case 1: return launch_wave_x2_t<8, false, WAVE_P, false, 1>(s, p, tasks, n_tasks, ticket, grid);
+        case 2: return launch_wave_x2_t<8, false, WAVE_P, true, 0>(s, p, tasks, n_tasks, ticket, grid);
+        case 3: return launch_wave_x2_t<8, false, WAVE_P, true, 1>(s, p, tasks, n_tasks, ticket, grid);
+        case 4: return launch_wave_x2_t<8, true, WAVE_P, false, 0>(s, p, tasks, n_tasks, ticket, grid);
+        case 5: return launch_wave_x2_t<8, true, WAVE_P, false, 1>(s, p, tasks, n_tasks, ticket, grid);
+        case 6: return launch_wave_x2_t<8, true, WAVE_P, true, 0>(s, p, tasks, n_tasks, ticket, grid);
+        default: return launch_wave_x2_t<8, true, WAVE_P, true, 1>(s, p, tasks, n_tasks, ticket, grid);
     }
+}
+
+// the fused double pass: phase-0 and phase-1 runs of a k = 8 pass pair in one launch (whole fp32 grids)
+static int launch_wave_fused(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, bool ring) {
+    if (int rc = check_ch_uniform(s)) return rc;
+    const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, sm_count(s));
+    CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int), s->stream));
+    const bool uch = s->ch_uniform == 1;
+    if (uch) return ring ? launch_wave_x2_t<8, true, WAVE_P, true, 2>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_x2_t<8, true, WAVE_P, false, 2>(s, p, tasks, n_tasks, ticket, grid);
+    return ring ? launch_wave_x2_t<8, false, WAVE_P, true, 2>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_x2_t<8, false, WAVE_P, false, 2>(s, p, tasks, n_tasks, ticket, grid);
 }
 
 template <int K> static int launch_wave_f64_k(fdtd2d_sim* s, const PassParams<double>& p, const WaveTask* tasks, int n_tasks, int* ticket, int grid) {
@@ -588,12 +606,15 @@ template <int TH> static int launch_generic_list_t(int dev, const PassParams<flo
     return 0;
 }
 
-template <typename T> static void fill_params(const fdtd2d_sim* s, const TilePlan& tp, int phases, PassParams<T>* pp, const PassPlan* pl = nullptr) {
+// second_pass: the parameters of the SECOND pass of a fused pair (it reads what the first one writes, k steps later)
+template <typename T> static void fill_params(const fdtd2d_sim* s, const TilePlan& tp, int phases, PassParams<T>* pp, const PassPlan* pl = nullptr,
+                                              bool second_pass = false) {
     PassParams<T>& p = *pp;
     memset(&p, 0, sizeof p);
+    const int cur = s->cur ^ (second_pass ? 1 : 0);
     for (int f = 0; f < 3; ++f) {
-        p.in[f] = static_cast<const T*>(s->field[s->cur][f]);
-        p.out[f] = static_cast<T*>(s->field[s->cur ^ 1][f]);
+        p.in[f] = static_cast<const T*>(s->field[cur][f]);
+        p.out[f] = static_cast<T*>(s->field[cur ^ 1][f]);
     }
     p.ce = static_cast<const T*>(s->ce);
     p.ch = static_cast<const T*>(s->ch);
@@ -618,7 +639,7 @@ template <typename T> static void fill_params(const fdtd2d_sim* s, const TilePla
     p.src_range = s->n_src ? s->d_src_range : nullptr;
     p.amp = s->d_amp;
     p.amp_steps = s->amp_steps;
-    p.step0 = s->step;
+    p.step0 = s->step + (second_pass ? tp.k : 0);
     p.probes = s->d_probe;
     p.probe_range = s->n_probe ? s->d_probe_range : nullptr;
     p.n_probe = s->n_probe;
@@ -634,6 +655,7 @@ template <typename T> static void fill_params(const fdtd2d_sim* s, const TilePla
     p.band_hi[1] = own_last(s);
     p.flags = s->d_slab_flags;
     p.seq = s->pass_seq;
+    if (pl) p.fuse_flags = pl->d_fuse_flags, p.fuse_nblk = pl->fuse_nblk;
     for (int side = 0; side < 2; ++side) {
         const PeerLink& pe = s->peer[side];
         if (!pe.attached) continue;
@@ -670,6 +692,9 @@ static void free_plans(fdtd2d_sim* s) {
         cudaFree(pl.d_fast);
         cudaFree(pl.d_wave);
         cudaFree(pl.d_ticket);
+        cudaFree(pl.d_fused);
+        cudaFree(pl.d_deferred);
+        cudaFree(pl.d_fuse_flags);
         pl = PassPlan();
     }
 }
@@ -720,6 +745,8 @@ struct PlanLists {
     int n_wave_band = 0;
     bool wave_ring = false;
     int band_expected[2] = {0, 0};
+    std::vector<WaveTask> fused, deferred;  // fused double pass: stage-1 ticket order (both phases), stage-2 phase-1 pieces
+    int fuse_nblk = 0;
 };
 
 // The planning itself: host arithmetic only (s->sm_count and s->ch_uniform are read as they are), so that the CPU
@@ -939,6 +966,76 @@ static int plan_pass(const fdtd2d_sim* s, int k, PlanLists* pl) {
         for (const WaveTask& t : band_tasks) pl->band_expected[t.band - 1] += 1;
         pl->n_wave_band = (int)band_tasks.size();
         tasks.insert(tasks.begin(), band_tasks.begin(), band_tasks.end());  // the band runs go first
+
+        // ---- fused double pass (strip_wave.cuh "two passes per launch"): whole fp32 grids, k = 8, tile rows that are
+        // whole 16-row blocks.  Phase 0 = every stretch, cut into runs at multiples of 16 rows; phase 1 = the same
+        // stretches, but only the tile rows whose 3 x 3 tile neighbourhood (the tile columns the strip's window covers,
+        // one tile row up and down) is produced by phase-0 RUNS are fused -- the rest are left to the second launch.
+        const bool fuse_on = s->opt.fuse > 0 || (s->opt.fuse < 0 && n_plain_cells >= (long long)6000 * 6000);
+        pl->fused.clear(), pl->deferred.clear();
+        if (fuse_on && !f64 && k == 8 && !slab && org == 0 && tp.CH % (1 << FUSE_BLOCK_LOG2) == 0 && band_tasks.empty()) {
+            const int B16 = 1 << FUSE_BLOCK_LOG2;
+            pl->fuse_nblk = (s->Rl + B16 - 1) / B16;
+            auto wave_tile = [&](int b, int ty, int tx) {
+                if (ty < 0 || ty >= tp.tiles_y || tx < 0 || tx >= tp.tiles_x) return false;
+                const int kd = kind[(size_t)b * per_grid + (size_t)ty * tp.tiles_x + tx];
+                return kd == 1 || kd == 2;
+            };
+            std::vector<WaveTask> phase0, phase1;
+            for (size_t i = 0; i < segs.size(); ++i) {
+                WaveTask g = segs[i];
+                g.tx = g.side == 0 ? (g.x0 + tp.hx) / tp.CW : (g.side == 1 ? 0 : tp.tiles_x - 1);
+                g.txlo = std::max(0, g.x0 / tp.CW), g.txhi = std::min(tp.tiles_x - 1, (g.x0 + TILE_TW - 1) / tp.CW);
+                const int rows = seg_rows[i], np = parts[i];
+                auto cut = [&](int q) { return q >= np ? g.y1 : g.y0 + (int)((long long)rows * q / np) / B16 * B16; };
+                // phase 0: the whole stretch
+                for (int q = 0; q < np; ++q) {
+                    WaveTask t = g;
+                    t.phase = 0, t.y0 = cut(q), t.y1 = cut(q + 1);
+                    if (t.y1 > t.y0) phase0.push_back(t);
+                }
+                // phase 1: maximal ranges of tile rows that can / cannot be fused
+                const int ta = g.y0 / tp.CH, tb = g.y1 / tp.CH;  // tile rows [ta, tb) (org = 0, stretches are whole tile rows)
+                auto fusable = [&](int ty) {
+                    for (int yy = ty - 1; yy <= ty + 1; ++yy)
+                        for (int xx = g.txlo; xx <= g.txhi; ++xx)
+                            if (!wave_tile(g.b, yy, xx)) return false;
+                    return true;
+                };
+                for (int ty = ta; ty < tb;) {
+                    const bool f = fusable(ty);
+                    int te = ty + 1;
+                    while (te < tb && fusable(te) == f) ++te;
+                    const int r0 = ty * tp.CH, r1 = te * tp.CH;
+                    const int len = std::max(B16, (rows + np - 1) / np / B16 * B16);  // the run length of phase 0
+                    for (int y = r0; y < r1; y += len) {
+                        WaveTask t = g;
+                        t.phase = 1, t.y0 = y, t.y1 = std::min(r1, y + len);
+                        if (r1 - t.y1 < 2 * k) t.y1 = r1;  // (no stub shorter than its own warm-up)
+                        (f ? phase1 : pl->deferred).push_back(t);
+                        if (t.y1 == r1) break;
+                    }
+                    ty = te;
+                }
+            }
+            if (!phase1.empty()) {
+                // one ticket order: a phase-1 run comes after every phase-0 run that starts above the end of its window
+                struct Keyed {
+                    long long key;
+                    WaveTask t;
+                };
+                std::vector<Keyed> all;
+                for (const WaveTask& t : phase0) all.push_back({((long long)t.b << 40) | ((long long)t.y0 << 8) | 0, t});
+                for (const WaveTask& t : phase1) all.push_back({((long long)t.b << 40) | ((long long)(t.y1 + k) << 8) | 1, t});
+                std::stable_sort(all.begin(), all.end(), [](const Keyed& a, const Keyed& b) {
+                    if (a.key != b.key) return a.key < b.key;
+                    return a.t.x0 < b.t.x0;
+                });
+                for (const Keyed& e : all) pl->fused.push_back(e.t);
+            } else {
+                pl->deferred.clear();
+            }
+        }
     }
     if (!slab) pl->band_expected[0] = pl->band_expected[1] = 0;
     pl->n_edge_band = (int)edge_band.size();
@@ -969,6 +1066,17 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
         // had landed (seen as an illegal address with two handles in two host threads)
         CUDA_TRY(cudaMemcpyAsync(pl->d_wave, L.tasks.data(), sizeof(WaveTask) * L.tasks.size(), cudaMemcpyHostToDevice, s->stream));
     }
+    pl->n_fused = (int)L.fused.size(), pl->n_deferred = (int)L.deferred.size(), pl->fuse_nblk = L.fuse_nblk;
+    if (pl->n_fused) {
+        CUDA_TRY(cudaMalloc(&pl->d_fused, sizeof(WaveTask) * L.fused.size()));
+        CUDA_TRY(cudaMemcpyAsync(pl->d_fused, L.fused.data(), sizeof(WaveTask) * L.fused.size(), cudaMemcpyHostToDevice, s->stream));
+        if (pl->n_deferred) {
+            CUDA_TRY(cudaMalloc(&pl->d_deferred, sizeof(WaveTask) * L.deferred.size()));
+            CUDA_TRY(cudaMemcpyAsync(pl->d_deferred, L.deferred.data(), sizeof(WaveTask) * L.deferred.size(), cudaMemcpyHostToDevice, s->stream));
+        }
+        pl->fuse_flag_bytes = sizeof(unsigned) * (size_t)s->batch * pl->tp.tiles_x * pl->fuse_nblk;
+        CUDA_TRY(cudaMalloc(&pl->d_fuse_flags, pl->fuse_flag_bytes));
+    }
     if (pl->n_edge) {
         CUDA_TRY(cudaMalloc(&pl->d_edge, sizeof(int) * L.edge.size()));
         CUDA_TRY(cudaMemcpyAsync(pl->d_edge, L.edge.data(), sizeof(int) * L.edge.size(), cudaMemcpyHostToDevice, s->stream));
@@ -980,9 +1088,9 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
     CUDA_TRY(cudaStreamSynchronize(s->stream));  // the host vectors die here
     const TilePlan& tp = pl->tp;
     if (s->opt.debug)
-        fprintf(stderr, "[fdtd2d] plan k=%d: tiles %d x %d (core %d x %d), edge %d (band %d), tma %d, wave runs %d (band %d, ring %d), band tasks %d | %d\n", k,
+        fprintf(stderr, "[fdtd2d] plan k=%d: tiles %d x %d (core %d x %d), edge %d (band %d), tma %d, wave runs %d (band %d, ring %d), band tasks %d | %d, fused %d + deferred %d\n", k,
                 tp.tiles_y, tp.tiles_x, tp.CH, tp.CW, pl->n_edge, pl->n_edge_band, pl->n_fast, pl->n_wave, pl->n_wave_band, (int)pl->wave_ring,
-                pl->band_expected[0], pl->band_expected[1]);
+                pl->band_expected[0], pl->band_expected[1], pl->n_fused, pl->n_deferred);
     pl->valid = true;
     return 0;
 }
@@ -997,6 +1105,7 @@ template <typename T> static int launch_hybrid_t(fdtd2d_sim* s, int k, int part)
         if ((pl.n_wave > 0) != (s->ch_uniform == 1)) {
             CUDA_TRY(cudaStreamSynchronize(s->stream));
             cudaFree(pl.d_edge), cudaFree(pl.d_fast), cudaFree(pl.d_wave), cudaFree(pl.d_ticket);
+            cudaFree(pl.d_fused), cudaFree(pl.d_deferred), cudaFree(pl.d_fuse_flags);
             pl = PassPlan();
         }
     }
@@ -1062,6 +1171,62 @@ template <typename T> static int launch_hybrid_t(fdtd2d_sim* s, int k, int part)
 
 static int launch_hybrid(fdtd2d_sim* s, int k, int part) {
     return s->dtype == FDTD2D_F64 ? launch_hybrid_t<double>(s, k, part) : launch_hybrid_t<float>(s, k, part);
+}
+
+// Can the next two k = 8 passes of this handle go out as one fused launch?  (Builds the k = 8 plan if need be.)
+static int fused_available(fdtd2d_sim* s, bool* yes) {
+    *yes = false;
+    if (s->dtype != FDTD2D_F32 || s->has_top_nb || s->has_bot_nb || s->variant == 1 || s->variant == 3 || !s->opt.wavefront || s->opt.fuse == 0) return 0;
+    PassPlan& pl = s->hybrid[8];
+    if (!pl.valid)
+        if (int rc = classify_tiles(s, 8, &pl)) return rc;
+    *yes = pl.n_fused > 0;
+    return 0;
+}
+
+// Two k = 8 passes: [edge tiles of pass 1 || all runs of pass 1 + the fusable runs of pass 2, in one ticket order], then
+// [edge tiles of pass 2 || the pass-2 runs next to edge tiles].  The state ends where it started (A -> B -> A).
+static int launch_fused_pair(fdtd2d_sim* s) {
+    const int k = 8;
+    PassPlan& pl = s->hybrid[k];
+    const int all = FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC;
+    if (!s->side_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+    }
+    for (int stage = 0; stage < 2; ++stage) {
+        PassParams<float> p;
+        fill_params(s, pl.tp, all, &p, &pl, stage == 1);
+        if (stage == 0) CUDA_TRY(cudaMemsetAsync(pl.d_fuse_flags, 0, pl.fuse_flag_bytes, s->stream));
+        const int n_wave = stage == 0 ? pl.n_fused : pl.n_deferred;
+        const bool both = pl.n_edge > 0 && n_wave > 0;
+        cudaStream_t estream = s->stream;
+        if (both) {
+            CUDA_TRY(cudaEventRecord(s->ev_fork, s->stream));
+            CUDA_TRY(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
+            estream = s->side_stream;
+        }
+        if (pl.n_edge) {
+            p.tile_list = pl.d_edge;
+            if (int rc = launch_edge(s->device, p, pl.n_edge, estream)) return rc;
+            s->launches += 1;
+        }
+        p.tile_list = nullptr;
+        if (n_wave) {
+            const int rc = stage == 0 ? launch_wave_fused(s, p, pl.d_fused, n_wave, pl.d_ticket, pl.wave_ring)
+                                      : launch_wave(s, p, pl.d_deferred, n_wave, pl.d_ticket, k, pl.wave_ring);
+            if (rc) return rc;
+            s->launches += 1;
+        }
+        if (both) {
+            CUDA_TRY(cudaEventRecord(s->ev_join, s->side_stream));
+            CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+        }
+    }
+    s->passes += 2;
+    s->fused_pairs += 1;
+    return 0;
 }
 
 // ---- cluster-resident path (grid_resident.cuh) ---------------------------------------------------
@@ -1495,6 +1660,13 @@ int fdtd2d_sync(fdtd2d_sim* s) {
     REQUIRE(s, "handle is null");
     USE_DEVICE(s);
     if (int rc = wait_own_work(s)) return rc;
+    if (s->fused_pairs != s->fused_checked) {  // a phase-1 run that gave up waiting for its producers leaves a mark
+        unsigned err = 0;
+        CUDA_TRY(cudaMemcpyAsync(&err, s->d_slab_flags + FLAG_ERR, sizeof err, cudaMemcpyDeviceToHost, s->copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+        s->fused_checked = s->fused_pairs;
+        if (err == 3) return fail(FDTD2D_ESTATE, "a fused double pass timed out waiting for its first pass (internal error)");
+    }
     return peer_settle(s);
 }
 
@@ -1972,7 +2144,16 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
         REQUIRE(linked || n_steps <= s->halo, "a slab handle without peer links can advance at most halo=%d steps between halo exchanges", s->halo);
     }
     int left = n_steps;
+    bool fuse = false;
+    if (k == 8 && left >= 16)
+        if (int rc = fused_available(s, &fuse)) return rc;
     while (left > 0) {
+        if (fuse && left >= 16) {  // two passes per launch, the second one fed from L2
+            if (int rc = launch_fused_pair(s)) return rc;
+            s->step += 16;
+            left -= 16;
+            continue;
+        }
         const int kk = std::min(k, left);
         if (int rc = run_pass(s, kk, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC)) return rc;
         s->step += kk;
@@ -2071,7 +2252,36 @@ int fdtd2d_plan_host(const int32_t* geom, int n_src, const int32_t* src, int n_p
     }
     if (tasks) {
         REQUIRE((size_t)cap_tasks >= L.tasks.size(), "tasks holds %d entries, %zu needed", cap_tasks, L.tasks.size());
-        memcpy(tasks, L.tasks.data(), sizeof(WaveTask) * L.tasks.size());
+        for (size_t i = 0; i < L.tasks.size(); ++i) memcpy(tasks + 8 * i, &L.tasks[i], 8 * sizeof(int32_t));
+    }
+    return 0;
+}
+
+int fdtd2d_plan_host_fused(const int32_t* geom, int fuse, int n_src, const int32_t* src, int n_probe, const int32_t* probe, int32_t* counts,
+                           int32_t* fused, int cap_fused, int32_t* deferred, int cap_deferred) {
+    REQUIRE(geom && counts && (n_src == 0 || src) && (n_probe == 0 || probe) && n_src >= 0 && n_probe >= 0, "bad argument");
+    fdtd2d_sim s;  // geometry only
+    s.dtype = geom[0], s.batch = geom[1], s.Rg = geom[2], s.C = geom[3], s.row_begin = 0, s.row_end = geom[2], s.halo = 0;
+    s.sm_count = geom[8], s.variant = geom[9];
+    s.opt = Options();
+    s.opt.wave_min_tiles = geom[10], s.opt.ring_min_tiles = geom[11], s.opt.wavefront = geom[12], s.opt.ring_strips = geom[13];
+    s.opt.fuse = fuse;
+    s.ch_uniform = geom[14];
+    REQUIRE(s.dtype == FDTD2D_F32 && s.batch >= 1 && s.Rg >= 2 * RING + 1 && s.C >= 2 * RING + 1 && s.sm_count > 0, "bad geometry");
+    s.row0 = 0, s.Rl = s.Rg, s.esize = 4;
+    s.pitch = round_up((size_t)s.C, 32);
+    for (int i = 0; i < n_src; ++i) s.h_src.push_back(Cell{src[3 * i], src[3 * i + 1], src[3 * i + 2], 0});
+    for (int i = 0; i < n_probe; ++i) s.h_probe.push_back(Cell{probe[3 * i], probe[3 * i + 1], probe[3 * i + 2], 0});
+    PlanLists L;
+    if (int rc = plan_pass(&s, 8, &L)) return rc;
+    counts[0] = (int32_t)L.fused.size(), counts[1] = (int32_t)L.deferred.size(), counts[2] = L.fuse_nblk, counts[3] = (int32_t)L.tasks.size();
+    if (fused) {
+        REQUIRE((size_t)cap_fused >= L.fused.size(), "fused holds %d entries, %zu needed", cap_fused, L.fused.size());
+        if (!L.fused.empty()) memcpy(fused, L.fused.data(), sizeof(WaveTask) * L.fused.size());
+    }
+    if (deferred) {
+        REQUIRE((size_t)cap_deferred >= L.deferred.size(), "deferred holds %d entries, %zu needed", cap_deferred, L.deferred.size());
+        if (!L.deferred.empty()) memcpy(deferred, L.deferred.data(), sizeof(WaveTask) * L.deferred.size());
     }
     return 0;
 }

@@ -91,6 +91,9 @@ template <typename T> struct PassParams {
     unsigned* peer_flag[2];   // the word of the neighbour's block that I raise (its IN word for my side)
     int band_expected[2];     // band tasks (wavefront runs + edge tiles) per side in this pass
     unsigned seq;             // sequence number of the state this pass reads (passes since the handle was created)
+    // fused double pass (strip_wave.cuh): one flag per (grid, tile column, 16-row block) of what phase 0 has stored
+    unsigned* fuse_flags;
+    int fuse_nblk;
 };
 
 // Flag block of a slab handle: 8 words of device memory.  IN_TOP / IN_BOT = sequence number of the newest state whose

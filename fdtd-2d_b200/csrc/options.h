@@ -24,6 +24,7 @@ struct Options {
     int resident_trim = -1;    // rows the first / last CTA of a cluster hold fewer than the others (-1: 4 x rows per thread)
     int tma_pair = 0;          // pairwise mbarriers instead of CTA barriers in the TMA tile kernel
     int f64_k = 0;             // default k_temporal of fp64 handles (0: 8 on the wavefront, else 4)
+    int fuse = -1;             // two k = 8 passes per launch, the second reading the first's output from L2 (-1: large grids, 0 off, 1 on)
     int debug = 0;             // print launch geometry to stderr
 };
 
@@ -47,6 +48,7 @@ inline const OptionKey* option_keys(int* n) {
         {"resident_trim", &Options::resident_trim},
         {"tma_pair", &Options::tma_pair},
         {"f64_k", &Options::f64_k},
+        {"fuse", &Options::fuse},
         {"debug", &Options::debug},
     };
     *n = (int)(sizeof(keys) / sizeof(keys[0]));

@@ -25,6 +25,18 @@
 // rows as well (peer stores over NVLink) and, when it is the last band task of its side, raises the neighbour's flag
 // (common.cuh: band_wait / band_done).  Band runs come first in the task list, so the exchange is over long before the
 // pass is.
+//
+// Two passes per launch (FUSE instantiations): at K = 8 the kernel moves 28 B per cell and pass at 94 % of the copy bandwidth;
+// the way past that wall is to let the SECOND pass of a pair read what the first one wrote while it is still in the 126 MB
+// L2.  One launch holds the runs of pass p (phase 0: set A -> set B) and of pass p + 1 (phase 1: set B -> set A) in one
+// ticket order in which every phase-1 run comes after the phase-0 runs it reads.  A phase-0 run publishes a flag per
+// 16-row block of its tile column as soon as the block is in memory (fence + store); a phase-1 run, before it prefetches
+// the first row of a block, waits for the flags of that block in the (up to three) tile columns its window covers.  So it
+// trails its producers by 16..32 rows: its 16 B per cell come from L2, and DRAM sees 16 B read + 12 B written by phase 0
+// and 12 B written by phase 1 per 16 steps -- 2.5 B per cell-step instead of 3.5.  Only runs whose whole window is
+// produced by phase-0 RUNS are fused; the pieces next to edge tiles (top / bottom ring, sources, probes) are left to a
+// short second launch, after the phase-0 edge tiles are done (api.cu).  Waiting is safe: a run only ever waits for runs
+// with smaller ticket numbers, which are running or done, and those never wait.
 #pragma once
 #include "common.cuh"
 #include "tile_edge.cuh"
@@ -45,7 +57,13 @@ struct WaveTask {
     int32_t c0, c1;
     int32_t side;  // 0 plain strip, 1 holds the left Mur ring (columns 0..4), 2 the right one
     int32_t band;  // 0, or 1 / 2: the rows are the band next to the top / bottom neighbour slab
+    // fused double pass (see "two passes per launch" below)
+    int32_t phase = 0;           // 0: first pass of the launch (producer), 1: second pass (consumer)
+    int32_t tx = 0;              // tile column whose cells this run stores (index of its progress flags)
+    int32_t txlo = 0, txhi = 0;  // tile columns its 128-column window reads: the producers a phase-1 run waits for
 };
+constexpr int WAVE_TASK_WORDS = 12;
+constexpr int FUSE_BLOCK_LOG2 = 4;  // progress is published per block of 16 rows
 
 // per warp: NF rows of the three fields + NC rows of dt/(eps*dx) (+ NC rows of dt/(mu*dx) unless that is a scalar)
 __host__ __device__ constexpr size_t wave_smem_bytes(int warps, bool no_ch_ring) {
@@ -222,6 +240,29 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassP
 // touched), so the product is written as fma.rn.f32x2(a, b, -0) with the -0 pair coming in as a kernel argument the
 // compiler cannot see through: rn(a*b + -0) = rn(a*b) for every input incl. signed zeros, and an FFMA2 that already
 // has an addend cannot absorb the add that follows.
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// A phase-1 run waits until block `blk` of the tile columns [txlo, txlo + ntx) of grid b has been published by phase 0.
+// Every lane polls (lane l the flag of column txlo + min(l, ntx - 1)); gives up after 2 s and reports through the flag
+// block instead of hanging the GPU.
+__device__ __forceinline__ void fuse_wait(const PassParams<float>& p, const WaveTask& tk, const int blk, const int l) {
+    const int ntx = tk.txhi - tk.txlo + 1;
+    const unsigned* f = p.fuse_flags + ((long long)tk.b * p.tiles_x + tk.txlo + (l < ntx ? l : ntx - 1)) * p.fuse_nblk + blk;
+    if (__all_sync(0xffffffffu, ld_acquire_gpu(f) != 0u)) return;
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+        __nanosleep(64);
+        if (__all_sync(0xffffffffu, ld_acquire_gpu(f) != 0u)) return;
+        if (globaltimer_ns() - t0 > HALO_WAIT_NS) {
+            if (l == 0) atomicExch(p.flags + FLAG_ERR, 3u);
+            return;
+        }
+    }
+}
+
 using u64 = unsigned long long;
 __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 c; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c; }
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 c; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b)); return c; }
@@ -240,14 +281,19 @@ __device__ __forceinline__ void store22(float* p, const u64* a) { *reinterpret_c
 // which is the reference's column-by-column loop with every read resolved (each column reads its inward neighbour
 // before that one is overwritten).  The reference's slice bounds (H: columns 0..C-2, Ez: 1..C-2) are imposed by selects
 // on the right strip, which also covers the pad columns >= C (kept as loaded: zero).
-// BAND = true: the rows are a slab's band (see the top of the file).
-template <int K, bool UCH, int P, bool LR, bool BAND>
+// MODE: 0 plain; 1 the rows are a slab's band; 2 / 3 phase 0 / phase 1 of a fused double pass (see the top of the file;
+// phase 1 reads what the launch's PassParams call `out` and writes what they call `in`).
+template <int K, bool UCH, int P, bool LR, int MODE>
 __device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const WaveTask& tk, float* fring, float* cring, const int l, const u64 chu, const u64 negzero) {
     constexpr int TW = WAVE_TW, NF = WAVE_NF, NC = WAVE_NC, CS = UCH ? 1 : 2;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr bool BAND = MODE == 1, PUB = MODE == 2, SUB = MODE == 3;
     const bool core = 4 * l >= tk.c0 && 4 * l < tk.c1;
     const int bside = tk.band - 1;
     if (BAND) band_wait(p, bside);
+    // (compile-time selects: the pointers stay constant-bank operands)
+    auto IN = [&](int f) -> const float* { return SUB ? p.out[f] : p.in[f]; };
+    auto OUT = [&](int f) -> float* { return SUB ? const_cast<float*>(p.in[f]) : p.out[f]; };
     {
         // ring strips: which of my four columns are ring columns / beyond the reference's slices, as all-ones masks for
         // bitwise selects (one LOP3 each; predicates would have to be recomputed at every use)
@@ -278,11 +324,15 @@ __device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const Wa
         // level K-1 in iteration j is K rows behind the arriving one, i.e. P + 1 + K rows behind `of`.
         const int n = tk.y1 - tk.y0 + 2 * K;  // level-0 rows [y0 - K, y1 + K)
         long long of = (long long)tk.b * p.grid_stride + tk.x0 + 4 * l + (long long)(tk.y0 - K) * p.pitch;
-        auto fetch = [&](int fs, int cs) {
+        auto fetch = [&](int fs, int cs, int jf) {  // jf = index of the fetched row among the run's level-0 rows
+            if (SUB) {  // entering a new 16-row block of what phase 0 produces: wait for it
+                const int row = tk.y0 - K + jf;
+                if (jf == 0 || (row & ((1 << FUSE_BLOCK_LOG2) - 1)) == 0) fuse_wait(p, tk, row >> FUSE_BLOCK_LOG2, l);
+            }
             const long long o = of;
-            cp_async16(fring + (fs * 3 + 0) * TW, p.in[0] + o);
-            cp_async16(fring + (fs * 3 + 1) * TW, p.in[1] + o);
-            cp_async16(fring + (fs * 3 + 2) * TW, p.in[2] + o);
+            cp_async16(fring + (fs * 3 + 0) * TW, IN(0) + o);
+            cp_async16(fring + (fs * 3 + 1) * TW, IN(1) + o);
+            cp_async16(fring + (fs * 3 + 2) * TW, IN(2) + o);
             cp_async16(cring + (cs * CS + 0) * TW, p.ce + o);
             if (!UCH) cp_async16(cring + (cs * CS + 1) * TW, p.ch + o);
         };
@@ -300,7 +350,7 @@ __device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const Wa
         }
 #pragma unroll
         for (int d = 0; d < P; ++d) {
-            fetch(fs, cs);
+            fetch(fs, cs, d);
             of += p.pitch;
             cp_async_commit();
             fs = (fs + 1) & (NF - 1);
@@ -308,7 +358,7 @@ __device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const Wa
         }
         int fr = 0, cr = 0;
         auto iter = [&](u64 (&ST)[K + 1][3][2], u64 (&AR)[K + 1][3][2], const int j) {
-            if (j + P < n) fetch(fs, cs);
+            if (j + P < n) fetch(fs, cs, j + P);
             of += p.pitch;
             cp_async_commit();
             fs = (fs + 1) & (NF - 1);
@@ -383,9 +433,9 @@ __device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const Wa
             cr = (cr + 1) & (NC - 1);
             if (core && j >= 2 * K) {  // row y0 + (j - 2K) < y1 has left level K-1, K steps on
                 const long long o = of - (long long)(P + 1 + K) * p.pitch;
-                store22(p.out[0] + o, AR[K][0]);
-                store22(p.out[1] + o, AR[K][1]);
-                store22(p.out[2] + o, AR[K][2]);
+                store22(OUT(0) + o, AR[K][0]);
+                store22(OUT(1) + o, AR[K][1]);
+                store22(OUT(2) + o, AR[K][2]);
                 if (BAND) {  // the same rows into the neighbour slab's ghost rows
                     float* const q0 = peer_field(p, bside, 0);
                     if (q0) {
@@ -393,6 +443,16 @@ __device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const Wa
                         store22(q0 + po, AR[K][0]);
                         store22(peer_field(p, bside, 1) + po, AR[K][1]);
                         store22(peer_field(p, bside, 2) + po, AR[K][2]);
+                    }
+                }
+            }
+            if (PUB && j >= 2 * K) {  // the last row of a 16-row block is in flight: publish the block (runs are cut at blocks)
+                const int row = tk.y0 + j - 2 * K;
+                if (((row + 1) & ((1 << FUSE_BLOCK_LOG2) - 1)) == 0) {
+                    __syncwarp();  // the other lanes' stores happen before lane 0's fence, which is cumulative
+                    if (l == 0) {
+                        __threadfence();
+                        *(volatile unsigned*)(p.fuse_flags + ((long long)tk.b * p.tiles_x + tk.tx) * p.fuse_nblk + (row >> FUSE_BLOCK_LOG2)) = 1u;
                     }
                 }
             }
@@ -417,7 +477,8 @@ __device__ __forceinline__ void wave_run_x2(const PassParams<float>& p, const Wa
 // The kernel: warps take runs from one ticket; with RING the ring-strip runs go through the LR instantiation of the run,
 // with SLAB the band runs through the BAND one, everything else through the plain one -- separate loops in one kernel,
 // so the plain strips pay nothing for the ring / band code and one launch balances everything.
-template <int K, bool UCH, int P, bool RING, bool SLAB>
+// FLAVOUR: 0 whole grid, one pass; 1 y-slab (band runs); 2 fused double pass (phase-0 and phase-1 runs).
+template <int K, bool UCH, int P, bool RING, int FLAVOUR>
 __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const PassParams<float> p, const WaveTask* tasks, const int n_tasks, int* ticket, const float ch_uniform, const u64 negzero) {
     constexpr int TW = WAVE_TW, NF = WAVE_NF, NC = WAVE_NC, CS = UCH ? 1 : 2;  // CS: coefficient maps kept in the ring
     static_assert((NF & (NF - 1)) == 0 && NF > P && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
@@ -432,16 +493,28 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const Pa
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n_tasks) break;
         const WaveTask tk = tasks[t];
-        if (RING && tk.side != 0) {
-            if (SLAB && tk.band)
-                wave_run_x2<K, UCH, P, true, true>(p, tk, fring, cring, l, chu, negzero);
+        if (FLAVOUR == 2) {
+            if (RING && tk.side != 0) {
+                if (tk.phase)
+                    wave_run_x2<K, UCH, P, true, 3>(p, tk, fring, cring, l, chu, negzero);
+                else
+                    wave_run_x2<K, UCH, P, true, 2>(p, tk, fring, cring, l, chu, negzero);
+            } else {
+                if (tk.phase)
+                    wave_run_x2<K, UCH, P, false, 3>(p, tk, fring, cring, l, chu, negzero);
+                else
+                    wave_run_x2<K, UCH, P, false, 2>(p, tk, fring, cring, l, chu, negzero);
+            }
+        } else if (RING && tk.side != 0) {
+            if (FLAVOUR == 1 && tk.band)
+                wave_run_x2<K, UCH, P, true, 1>(p, tk, fring, cring, l, chu, negzero);
             else
-                wave_run_x2<K, UCH, P, true, false>(p, tk, fring, cring, l, chu, negzero);
+                wave_run_x2<K, UCH, P, true, 0>(p, tk, fring, cring, l, chu, negzero);
         } else {
-            if (SLAB && tk.band)
-                wave_run_x2<K, UCH, P, false, true>(p, tk, fring, cring, l, chu, negzero);
+            if (FLAVOUR == 1 && tk.band)
+                wave_run_x2<K, UCH, P, false, 1>(p, tk, fring, cring, l, chu, negzero);
             else
-                wave_run_x2<K, UCH, P, false, false>(p, tk, fring, cring, l, chu, negzero);
+                wave_run_x2<K, UCH, P, false, 0>(p, tk, fring, cring, l, chu, negzero);
         }
     }
 }

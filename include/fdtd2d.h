@@ -79,7 +79,8 @@ int fdtd2d_sync(fdtd2d_sim* s);
  * (upper case), read once at that moment.  fdtd2d_set_option changes one option of this handle and drops its cached
  * plans.  Keys: "wavefront" (1), "wave_min_tiles" (-1 = automatic), "ring_min_tiles" (-1), "ring_strips" (1),
  * "wave_run_rows" (640), "auto_k12" (0), "uniform_ch" (1), "resident" (1), "resident_cfg" (0), "resident_cluster" (0),
- * "resident_trim" (-1), "tma_pair" (0), "f64_k" (0 = automatic), "debug" (0).  Every setting is covered by the parity
+ * "resident_trim" (-1), "tma_pair" (0), "f64_k" (0 = automatic), "fuse" (-1: two k = 8 passes per launch on large grids, the
+ * second fed from L2; 0 off; 1 on), "debug" (0).  Every setting is covered by the parity
  * tests: options change which kernel runs, never a result bit. */
 int fdtd2d_set_option(fdtd2d_sim* s, const char* key, int value);
 int fdtd2d_get_option(const fdtd2d_sim* s, const char* key, int* value);
@@ -209,6 +210,13 @@ int fdtd2d_plan_wave_runs(int n_stretches, const int32_t* rows, const uint8_t* r
  * row, end row, first / end stored column of the strip, ring side, band. */
 int fdtd2d_plan_host(const int32_t* geom, int n_src, const int32_t* src, int n_probe, const int32_t* probe, int32_t* plan,
                      int32_t* tile_kind, int cap_tiles, int32_t* tasks, int cap_tasks);
+/* Host-only: the task lists of a FUSED pair of k = 8 passes of a whole fp32 grid (geom as above, rows = the whole grid;
+ * fuse: -1 automatic, 0 off, 1 on).  counts[4] = runs in the fused launch, runs left to the second launch, 16-row blocks
+ * per tile column, runs of a single pass.  fused / deferred (optional): 12 words per run -- grid, first column, first
+ * row, end row, first / end stored column, ring side, band, phase (0 first pass, 1 second), tile column stored, first
+ * and last tile column read. */
+int fdtd2d_plan_host_fused(const int32_t* geom, int fuse, int n_src, const int32_t* src, int n_probe, const int32_t* probe, int32_t* counts,
+                           int32_t* fused, int cap_fused, int32_t* deferred, int cap_deferred);
 /* What a k-step pass of this handle consists of (builds and caches the plan; needs the materials): info[0..11] =
  * tile rows, tile columns, core rows, core columns, edge tiles, of which band tiles, TMA tiles, wavefront runs, of
  * which band runs, ring strips present, band tasks next to the top / bottom neighbour. */

@@ -695,3 +695,65 @@ def test_options_are_per_handle_and_change_only_the_kernel(fd, monkeypatch):
         assert b.plan_info(8)["wave_runs"] == 0 and b.plan_info(8)["tma_tiles"] > 0
     for x, y in zip(*outs):
         assert_bits(x, y, "wavefront option on vs off")
+
+
+# --------------------------------------------------------------------------------------------
+# the fused double pass: two k = 8 passes per launch, the second one reading the first one's rows from L2
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,nsteps", [((1024, 1024), 40), ((700, 1500), 33), ((2000, 640), 16)])
+@pytest.mark.parametrize("uniform_mu", [False, True])
+def test_fused_double_pass_vs_oracle(fd, oracle, shape, nsteps, uniform_mu):
+    """Forced onto small grids so the oracle can check it: sources and probes break the runs (pieces next to their tiles
+    go to the second launch), the remainder (nsteps % 16) runs as single passes."""
+    c_oracle, npo = oracle
+    R, C = shape
+    rng = np.random.default_rng(R * 37 + C)
+    eps, mu, Ez, Hx, Hy = _random_problem(rng, R, C, "float32")
+    if uniform_mu:
+        mu[...] = np.float32(4 * np.pi * 1e-7)
+    ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(np.float32))
+    cells = [(R // 2, C // 2), (R // 3, C // 4), (7, 9)]
+    amp = npo.source_table("ricker", nsteps, DT, FC) + 0.125
+    probes = [(R // 2, C // 2 + 3), (0, 0), (R - 1, C - 1), (R // 4, C // 3), (3 * R // 4, 2 * C // 3)]
+    oEz, oHx, oHy = Ez.copy(), Hx.copy(), Hy.copy()
+    otrace = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, nsteps, amp, cells, probes, omp=True)
+    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
+        sim.set_kernel_variant(2)
+        for key, v in (("wave_min_tiles", 0), ("ring_min_tiles", 0), ("fuse", 1)):
+            sim.set_option(key, v)
+        sim.set_coefficients(ce, ch, coef)
+        sim.set_state(Ez, Hx, Hy)
+        sim.set_sources([(0, r, c, 0) for r, c in cells], amp[None, :])
+        sim.set_probes(probes, nsteps)
+        before = sim.launch_count
+        sim.step(nsteps, 0)
+        sim.synchronize()
+        assert sim.pass_count == -(-nsteps // 8)
+        # a fused pair is 4 launches (2 x edge tiles, the fused runs, the deferred runs); a single pass 2
+        assert sim.launch_count - before <= 4 * (nsteps // 16) + 2 * -(-(nsteps % 16) // 8) + 1
+        gEz, gHx, gHy = sim.state()
+        gtrace = sim.read_probes()
+    assert_bits(gtrace, otrace, "probe trace")
+    assert_bits(gEz, oEz, "Ez")
+    assert_bits(gHx, oHx, "Hx")
+    assert_bits(gHy, oHy, "Hy")
+
+
+def test_fused_equals_single_passes_large(fd):
+    """6000 x 5000 fp32, 48 steps near the Ricker peak, fused pairs against single passes: not a bit may differ."""
+    outs = []
+    for fuse in (0, 1):
+        with fd.Simulation(6000, 5000, np.float32, dt=DT, dx=DX) as sim:
+            sim.set_option("fuse", fuse)
+            sim.set_materials_random(seed=5, span=9.0)
+            sim.set_point_source(3000, 2500, 700, FC)
+            sim.set_probes([(3000, 2510), (10, 10), (5990, 4990)], 700)
+            sim.step_index = 640
+            before = sim.launch_count
+            sim.step(48, 0)
+            sim.synchronize()
+            assert sim.pass_count == 6 and (sim.launch_count - before == 12)  # (the launch counts happen to agree: 3 x 4 = 6 x 2)
+            outs.append(sim.state() + (sim.read_probes(640, 48),))
+    assert np.abs(outs[0][0]).max() > 0.1
+    for a, b in zip(*outs):
+        assert_bits(a, b, "fused pairs vs single passes")

@@ -160,3 +160,64 @@ def test_wavefront_takes_large_grids_and_both_dtypes(lib):
     assert pl["n_wave"] == 0 and pl["n_tma"] == 0 and pl["n_edge"] == pl["tiles_y"] * pl["tiles_x"]
     pl = plan(lib, 0, 1024, 1024, 8)  # small grid: persistent TMA tiles
     assert pl["n_wave"] == 0 and pl["n_tma"] > 0
+
+
+# ---- the fused double pass (two k = 8 passes per launch, the second fed from L2) ----------------------------------------
+def plan_fused(lib, Rg, C, *, fuse=1, batch=1, src=(), probe=(), wave_min=-1, ring_min=-1):
+    geom = np.array([0, batch, Rg, C, 0, Rg, 0, 8, SM, 0, wave_min, ring_min, 1, 1, 1], np.int32)
+    s = np.ascontiguousarray(np.array(src, np.int32).reshape(-1, 3))
+    p = np.ascontiguousarray(np.array(probe, np.int32).reshape(-1, 3))
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    counts = np.zeros(4, np.int32)
+    assert lib.fdtd2d_plan_host_fused(vp(geom), fuse, len(s), vp(s), len(p), vp(p), vp(counts), None, 0, None, 0) == 0, lib.fdtd2d_last_error()
+    fused = np.zeros((max(1, counts[0]), 12), np.int32)
+    deferred = np.zeros((max(1, counts[1]), 12), np.int32)
+    assert lib.fdtd2d_plan_host_fused(vp(geom), fuse, len(s), vp(s), len(p), vp(p), vp(counts), vp(fused), len(fused), vp(deferred),
+                                      len(deferred)) == 0, lib.fdtd2d_last_error()
+    return fused[:counts[0]], deferred[:counts[1]], int(counts[2]), int(counts[3])
+
+
+@pytest.mark.parametrize("shape", [(4096, 4096), (3000, 4100), (16384, 2100), (1500, 2100)])
+def test_fused_double_pass_plan(lib, shape):
+    """Phase 0 of the fused launch is the single-pass plan with runs cut at 16-row blocks; phase 1 (fused + deferred pieces)
+    stores exactly the same cells; every fused phase-1 run comes after all phase-0 runs it can read, reads only cells that
+    phase-0 RUNS store (never an edge tile's), and names exactly the tile columns its window covers."""
+    R, C = shape
+    src = [(0, R // 2, C // 2), (0, R // 3, C // 4)]
+    probe = [(0, R // 2, C // 2 + 16), (0, R // 4, C // 4), (0, 8, C // 2)]
+    single = plan(lib, 0, R, C, 8, src=src, probe=probe, wave_min=0, ring_min=0)
+    fused, deferred, nblk, n_single = plan_fused(lib, R, C, src=src, probe=probe, wave_min=0, ring_min=0)
+    assert n_single == single["n_wave"] and nblk == -(-R // 16) and len(fused) > 0
+    CW, K, pitch = single["CW"], 8, single["pitch"]
+    p0, p1 = fused[fused[:, 8] == 0], fused[fused[:, 8] == 1]
+    cover0, cover1 = np.zeros((R, pitch), np.int8), np.zeros((R, pitch), np.int8)
+    for b_, x0, y0, y1, c0, c1, side, bnd, ph, tx, txlo, txhi in p0:
+        assert y0 % 16 == 0 and y1 % 16 == 0 and y0 < y1 and bnd == 0
+        assert tx * CW <= x0 + c0 and x0 + c1 <= max((tx + 1) * CW, pitch if tx == single["tiles_x"] - 1 else 0), "stores stay in its tile column"
+        cover0[y0:y1, x0 + c0:x0 + c1] += 1
+    for b_, x0, y0, y1, c0, c1, side, bnd, ph, tx, txlo, txhi in np.concatenate([p1, deferred]):
+        assert ph == 1 and y0 < y1
+        cover1[y0:y1, x0 + c0:x0 + c1] += 1
+    want = np.zeros((R, pitch), np.int8)
+    for b_, x0, y0, y1, c0, c1, side, bnd in single["tasks"]:
+        want[y0:y1, x0 + c0:x0 + c1] += 1
+    assert np.array_equal(cover0, want) and np.array_equal(cover1, want) and want.max() == 1
+    # order + windows of the fused phase-1 runs
+    first_p0_at_or_after = {}
+    pos = {i: t for i, t in enumerate(fused)}
+    p0_y0 = np.array([t[2] if t[8] == 0 else -1 for t in fused])
+    for i, (b_, x0, y0, y1, c0, c1, side, bnd, ph, tx, txlo, txhi) in enumerate(fused):
+        if ph == 0:
+            continue
+        later = p0_y0[i + 1:]
+        assert not np.any((later >= 0) & (later < y1 + K)), "a phase-0 run this one reads comes later in the ticket order"
+        assert txlo == max(0, x0 // CW) and txhi == min(single["tiles_x"] - 1, (x0 + 127) // CW)
+        win = want[y0 - K:y1 + K, x0:min(x0 + 128, C)]
+        assert win.min() == 1, "the window holds a cell no phase-0 run stores (an edge tile's)"
+    assert len(deferred) < 0.2 * len(p1) + 4 * single["tiles_x"]
+
+
+def test_fused_is_automatic_only_on_large_grids(lib):
+    assert len(plan_fused(lib, 16384, 16384, fuse=-1)[0]) > 2000
+    assert len(plan_fused(lib, 4096, 4096, fuse=-1)[0]) == 0
+    assert len(plan_fused(lib, 16384, 16384, fuse=0)[0]) == 0
