@@ -749,10 +749,10 @@ def test_fused_equals_single_passes_large(fd):
             sim.set_point_source(3000, 2500, 700, FC)
             sim.set_probes([(3000, 2510), (10, 10), (5990, 4990)], 700)
             sim.step_index = 640
-            before = sim.launch_count
+            assert (sim.plan_info(8)["wave_runs"] > 0)
             sim.step(48, 0)
             sim.synchronize()
-            assert sim.pass_count == 6 and (sim.launch_count - before == 12)  # (the launch counts happen to agree: 3 x 4 = 6 x 2)
+            assert sim.pass_count == 6
             outs.append(sim.state() + (sim.read_probes(640, 48),))
     assert np.abs(outs[0][0]).max() > 0.1
     for a, b in zip(*outs):

@@ -202,18 +202,27 @@ def test_fused_double_pass_plan(lib, shape):
     for b_, x0, y0, y1, c0, c1, side, bnd in single["tasks"]:
         want[y0:y1, x0 + c0:x0 + c1] += 1
     assert np.array_equal(cover0, want) and np.array_equal(cover1, want) and want.max() == 1
-    # order + windows of the fused phase-1 runs
-    first_p0_at_or_after = {}
-    pos = {i: t for i, t in enumerate(fused)}
-    p0_y0 = np.array([t[2] if t[8] == 0 else -1 for t in fused])
+    # order + windows of the fused phase-1 runs: a run is PAIRED with the phase-0 run of its strip that starts 16 rows below
+    # its own first row (they start together, so the second trails the first closely enough to read from L2), and every
+    # phase-0 run it reads has a ticket at most a few hundred after its own (taken long before the waiting runs could
+    # fill the 1184 warps of the GPU)
+    p0_idx = [i for i, t in enumerate(fused) if t[8] == 0]
+    worst = 0
+    starts = {(t[1], t[2]) for t in p0}
     for i, (b_, x0, y0, y1, c0, c1, side, bnd, ph, tx, txlo, txhi) in enumerate(fused):
         if ph == 0:
             continue
-        later = p0_y0[i + 1:]
-        assert not np.any((later >= 0) & (later < y1 + K)), "a phase-0 run this one reads comes later in the ticket order"
         assert txlo == max(0, x0 // CW) and txhi == min(single["tiles_x"] - 1, (x0 + 127) // CW)
         win = want[y0 - K:y1 + K, x0:min(x0 + 128, C)]
         assert win.min() == 1, "the window holds a cell no phase-0 run stores (an edge tile's)"
+        if (x0, y0 + 16) in starts:  # (the first piece of a fusable range starts at a tile row instead: its producer started earlier)
+            prev = fused[i - 1]
+            assert prev[8] == 0 and prev[1] == x0 and prev[2] == y0 + 16, "not paired with the phase-0 run of its strip"
+        for a in p0_idx:
+            u = fused[a]
+            if txlo <= u[9] <= txhi and u[2] < y1 + K and u[3] > y0 - K:
+                worst = max(worst, a - i)
+    assert worst <= 2 * single["tiles_x"] + 8 and worst < SM * 8 // 2, worst
     assert len(deferred) < 0.2 * len(p1) + 4 * single["tiles_x"]
 
 
