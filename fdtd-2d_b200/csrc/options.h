@@ -24,7 +24,8 @@ struct Options {
     int resident_trim = -1;    // rows the first / last CTA of a cluster hold fewer than the others (-1: 4 x rows per thread)
     int tma_pair = 0;          // pairwise mbarriers instead of CTA barriers in the TMA tile kernel
     int f64_k = 0;             // default k_temporal of fp64 handles (0: 8 on the wavefront, else 4)
-    int fuse = -1;             // two k = 8 passes per launch, the second reading the first's output from L2 (-1: large grids, 0 off, 1 on)
+    int fuse = 0;              // EXPERIMENT, off: two k = 8 passes per launch, the second reading the first's output from L2
+                               // (1 on, -1 on for large grids).  Bit-exact but slower on B200, see DESIGN.md 9.
     int debug = 0;             // print launch geometry to stderr
 };
 

@@ -226,7 +226,7 @@ def test_fused_double_pass_plan(lib, shape):
     assert len(deferred) < 0.2 * len(p1) + 4 * single["tiles_x"]
 
 
-def test_fused_is_automatic_only_on_large_grids(lib):
+def test_fused_automatic_mode_takes_only_large_grids(lib):
     assert len(plan_fused(lib, 16384, 16384, fuse=-1)[0]) > 2000
     assert len(plan_fused(lib, 4096, 4096, fuse=-1)[0]) == 0
     assert len(plan_fused(lib, 16384, 16384, fuse=0)[0]) == 0
