@@ -23,6 +23,7 @@
 #include "tile_generic.cuh"
 #include "grid_resident.cuh"
 #include "strip_wave.cuh"
+#include "strip_stage.cuh"
 #include "grid_small.cuh"
 #include "structure.cuh"
 
@@ -525,6 +526,20 @@ static int launch_wave_f64_t(fdtd2d_sim* s, const PassParams<double>& p, const W
     return 0;
 }
 
+// the staged wavefront: K = 12 as three warps of four levels (uniform permeability)
+template <int NG, bool RING>
+static int launch_stage_t(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket) {
+    static bool done_[MAX_DEVICES] = {};
+    bool& done = done_[s->device % MAX_DEVICES];
+    const size_t smem = (size_t)NG * stage_group_bytes();
+    if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_stage_kernel<NG, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = true;
+    const int grid = std::min((n_tasks + NG - 1) / NG, sm_count(s));
+    strip_stage_kernel<NG, RING><<<grid, NG * STAGE_S * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, (float)s->ch_value, 0x8000000080000000ull);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // levels for which a wavefront instantiation exists
 static bool wave_has_k(const fdtd2d_sim* s, int k) {
     if (s->dtype == FDTD2D_F64) return k == 4 || k == 6 || k == 8;
@@ -539,6 +554,10 @@ static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask
     const bool slab = s->has_top_nb || s->has_bot_nb;
     if (k == 12) {  // (runs for k = 12 are only built when the permeability is uniform)
         if (!uch || slab) return fail(FDTD2D_EINVAL, "the 12-level wavefront kernel needs uniform permeability and a whole grid");
+        if (s->opt.stage) {
+            if (s->opt.stage == 4) return ring ? launch_stage_t<4, true>(s, p, tasks, n_tasks, ticket) : launch_stage_t<4, false>(s, p, tasks, n_tasks, ticket);
+            return ring ? launch_stage_t<5, true>(s, p, tasks, n_tasks, ticket) : launch_stage_t<5, false>(s, p, tasks, n_tasks, ticket);
+        }
         return launch_wave_x2_t<12, true, 2, false, 0>(s, p, tasks, n_tasks, ticket, grid);
     }
     if (k != 8) return fail(FDTD2D_EINVAL, "no fp32 wavefront kernel for k=%d", k);
@@ -796,7 +815,7 @@ static int plan_pass(const fdtd2d_sim* s, int k, PlanLists* pl) {
 
     // Ring strips: the first / last 128 columns of the padded row.  A source / probe must be re-checked against them
     // (the right strip is not aligned with the tile grid).
-    const bool lr_ok = wave_k && !f64 && k == 8 && s->opt.ring_strips && s->C >= 4 * TILE_TW;
+    const bool lr_ok = wave_k && !f64 && (k == 8 || (k == 12 && s->opt.stage)) && s->opt.ring_strips && s->C >= 4 * TILE_TW;
     const int lr_x0[2] = {0, (s->C + 3) / 4 * 4 - TILE_TW};
     std::vector<unsigned char> lr_special((size_t)n_tiles, 0);
     if (lr_ok) {

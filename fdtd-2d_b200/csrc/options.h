@@ -26,6 +26,8 @@ struct Options {
     int f64_k = 0;             // default k_temporal of fp64 handles (0: 8 on the wavefront, else 4)
     int fuse = 0;              // EXPERIMENT, off: two k = 8 passes per launch, the second reading the first's output from L2
                                // (1 on, -1 on for large grids).  Bit-exact but slower on B200, see DESIGN.md 9.
+    int stage = 0;             // k = 12 passes on the staged wavefront (three warps of 4 levels each, strip_stage.cuh) instead of
+                               // the one-warp 12-level instance; 4 / 5 = groups per CTA
     int debug = 0;             // print launch geometry to stderr
 };
 
@@ -50,6 +52,7 @@ inline const OptionKey* option_keys(int* n) {
         {"tma_pair", &Options::tma_pair},
         {"f64_k", &Options::f64_k},
         {"fuse", &Options::fuse},
+        {"stage", &Options::stage},
         {"debug", &Options::debug},
     };
     *n = (int)(sizeof(keys) / sizeof(keys[0]));

@@ -757,3 +757,60 @@ def test_fused_equals_single_passes_large(fd):
     assert np.abs(outs[0][0]).max() > 0.1
     for a, b in zip(*outs):
         assert_bits(a, b, "fused pairs vs single passes")
+
+
+# --------------------------------------------------------------------------------------------
+# the staged wavefront: 12 levels as three warps of four (strip_stage.cuh)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,nsteps", [((300, 517), 40), ((1024, 1024), 24), ((203, 600), 17), ((2000, 260), 36), ((700, 1500), 12)])
+@pytest.mark.parametrize("groups", [4, 5])
+def test_staged_wavefront_vs_oracle(fd, oracle, shape, nsteps, groups):
+    """Forced onto small grids: runs broken by sources and probes, ring strips where C >= 512, ragged sizes, the remainder
+    pass (nsteps % 12) on the tile kernels; uniform permeability (what the 12-level kernels exist for)."""
+    c_oracle, npo = oracle
+    R, C = shape
+    rng = np.random.default_rng(R * 41 + C)
+    eps, mu, Ez, Hx, Hy = _random_problem(rng, R, C, "float32")
+    mu[...] = np.float32(4 * np.pi * 1e-7)
+    ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(np.float32))
+    cells = [(R // 2, C // 2), (R // 3, C // 4), (7, 9)]
+    amp = npo.source_table("ricker", nsteps, DT, FC) + 0.125
+    probes = [(R // 2, C // 2 + 3), (0, 0), (R - 1, C - 1), (R // 4, C // 3), (3 * R // 4, 2 * C // 3)]
+    oEz, oHx, oHy = Ez.copy(), Hx.copy(), Hy.copy()
+    otrace = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, nsteps, amp, cells, probes, omp=True)
+    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
+        sim.set_kernel_variant(2)
+        for key, v in (("wave_min_tiles", 0), ("ring_min_tiles", 0), ("stage", groups)):
+            sim.set_option(key, v)
+        sim.set_coefficients(ce, ch, coef)
+        sim.set_state(Ez, Hx, Hy)
+        sim.set_sources([(0, r, c, 0) for r, c in cells], amp[None, :])
+        sim.set_probes(probes, nsteps)
+        info = sim.plan_info(12)
+        assert info["wave_runs"] > 0 and (info["ring_strips"] == 1) == (C >= 512), info
+        sim.step(nsteps, 12)
+        gEz, gHx, gHy = sim.state()
+        gtrace = sim.read_probes()
+    assert_bits(gtrace, otrace, "probe trace")
+    assert_bits(gEz, oEz, "Ez")
+    assert_bits(gHx, oHx, "Hx")
+    assert_bits(gHy, oHy, "Hy")
+
+
+def test_staged_wavefront_equals_one_warp_kernels_large(fd):
+    """6000 x 5000 fp32, 48 steps near the Ricker peak: 12 levels staged over three warps (4 and 5 groups per CTA) against the
+    one-warp 8-level kernel."""
+    outs = []
+    for stage, k in ((0, 8), (4, 12), (5, 12)):
+        with fd.Simulation(6000, 5000, np.float32, dt=DT, dx=DX) as sim:
+            sim.set_option("stage", stage)
+            sim.set_materials_random(seed=5, span=9.0)
+            sim.set_point_source(3000, 2500, 700, FC)
+            sim.set_probes([(3000, 2510), (10, 10), (5990, 4990)], 700)
+            sim.step_index = 640
+            sim.step(48, k)
+            outs.append(sim.state() + (sim.read_probes(640, 48),))
+    assert np.abs(outs[0][0]).max() > 0.1
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert_bits(a, b, "staged 12 levels vs 8 levels")
