@@ -35,14 +35,16 @@ __host__ __device__ constexpr size_t stage_group_bytes() {
 }
 
 __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_cta(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
+    if (mbar_try_cta(bar, parity)) return;  // (the common case costs one instruction; the clock is only read when waiting)
     const unsigned long long t0 = globaltimer_ns();
-    for (;;) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return;
+    while (!mbar_try_cta(bar, parity))
         if (globaltimer_ns() - t0 > 4000000000ull) __trap();  // a protocol bug must not hang the GPU
-    }
 }
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(STAGE_S * 32) : "memory"); }
 

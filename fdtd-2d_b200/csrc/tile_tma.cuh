@@ -35,16 +35,23 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// (the bound is on TIME -- a spin count trips under a debugger, compute-sanitizer or heavy preemption -- and generous: a
+// wait of 10 s is a protocol bug, and a trap is better than a GPU that has to be reset)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok, spins = 0;
-    do {
-        if (++spins > (1u << 26)) __trap();  // never hang the GPU on a protocol bug
+    uint32_t ok;
+    unsigned long long t0 = 0;
+    for (;;) {
         asm volatile(
             "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
-    } while (!ok);
+        if (ok) return;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0) t0 = t;
+        if (t - t0 > 10000000000ull) __trap();
+    }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
