@@ -181,6 +181,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_cpus(index: int):
+    """Pin this process to the host cores next to GPU `index` (`nvidia-smi topo -m`, column "CPU Affinity") BEFORE any pinned
+    memory is allocated: with one rank per GPU and first-touch page placement the e2e copies then stay on the GPU's own
+    socket instead of crossing the inter-socket link.  Host tuning only; returns the affinity string or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        lines = [l for l in out.splitlines() if l.strip()]
+        head = next(l for l in lines if "CPU Affinity" in l)
+        cols = [c.strip() for c in head.replace("\x1b[4m", "").replace("\x1b[0m", "").split("\t")]
+        row = next(l for l in lines if l.replace("\x1b[4m", "").startswith(f"GPU{index}\t") or l.startswith(f"GPU{index} "))
+        cells = [c.strip() for c in row.split("\t")]
+        aff = cells[cols.index("CPU Affinity")]
+        cpus = set()
+        for part in aff.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return aff
+    except Exception:
+        pass
+    return None
+
+
 def synthetic_eps(rows, cols, seed, row0=0):
     """eps = eps0*(1+9*U[0,1)) (SURVEY 8d cfg2/cfg3 recipe), float32, generated band-wise."""
     rng = np.random.default_rng(seed + row0)
@@ -471,6 +496,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    cpu_affinity = bind_to_gpu_cpus(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         if args.exchange == "nccl":
@@ -563,7 +589,8 @@ def main():
                                        f"y-slabs x{world}, halo rows stored into the neighbour GPU by the stepping kernels (NVLink peer stores + flags)"
                                        if args.exchange == "p2p" else f"y-slabs x{world}, NCCL send/recv per pass") if world > 1 else "single GPU",
                        "l2": "state is larger than L2 (inputs larger than L2; no flush needed)",
-                       "seed": 2026, "source": "ricker fc=30e9 at centre", "probes": len(probes)},
+                       "seed": 2026, "source": "ricker fc=30e9 at centre", "probes": len(probes),
+                       "host_cpu_affinity": cpu_affinity},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "tile_kernel_launches": int(tile_launches),
             "clocks": clocks, "slab_parity": parity, "strong_scaling": strong_line, "other_configs": others,
         }

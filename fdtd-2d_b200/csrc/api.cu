@@ -514,14 +514,14 @@ static int launch_wave_x2_t(fdtd2d_sim* s, const PassParams<float>& p, const Wav
 }
 
 // the scalar form, used for fp64
-template <int K, bool UCH, bool SLAB>
+template <int K, bool UCH, bool SLAB, bool RING>
 static int launch_wave_f64_t(fdtd2d_sim* s, const PassParams<double>& p, const WaveTask* tasks, int n_tasks, int* ticket, int grid) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[s->device % MAX_DEVICES];
     const size_t smem = wave_smem_bytes(WAVE_NW, UCH);
-    if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_kernel<double, K, UCH, WAVE_P, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!done) CUDA_TRY(cudaFuncSetAttribute(strip_wave_kernel<double, K, UCH, WAVE_P, SLAB, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = true;
-    strip_wave_kernel<double, K, UCH, WAVE_P, SLAB><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, UCH ? s->ch_value : 0.0);
+    strip_wave_kernel<double, K, UCH, WAVE_P, SLAB, RING><<<grid, WAVE_NW * 32, smem, s->stream>>>(p, tasks, n_tasks, ticket, UCH ? s->ch_value : 0.0);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -542,7 +542,7 @@ static int launch_stage_t(fdtd2d_sim* s, const PassParams<float>& p, const WaveT
 
 // levels for which a wavefront instantiation exists
 static bool wave_has_k(const fdtd2d_sim* s, int k) {
-    if (s->dtype == FDTD2D_F64) return k == 4 || k == 6 || k == 8;
+    if (s->dtype == FDTD2D_F64) return k == 4 || k == 8;
     return k == 8 || (k == 12 && !s->has_top_nb && !s->has_bot_nb);  // (12 levels: whole grids with uniform permeability)
 }
 
@@ -584,20 +584,19 @@ static int launch_wave_fused(fdtd2d_sim* s, const PassParams<float>& p, const Wa
     return ring ? launch_wave_x2_t<8, false, WAVE_P, true, 2>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_x2_t<8, false, WAVE_P, false, 2>(s, p, tasks, n_tasks, ticket, grid);
 }
 
-template <int K> static int launch_wave_f64_k(fdtd2d_sim* s, const PassParams<double>& p, const WaveTask* tasks, int n_tasks, int* ticket, int grid) {
+template <int K, bool RING> static int launch_wave_f64_k(fdtd2d_sim* s, const PassParams<double>& p, const WaveTask* tasks, int n_tasks, int* ticket, int grid) {
     const bool uch = s->ch_uniform == 1, slab = s->has_top_nb || s->has_bot_nb;
-    if (uch) return slab ? launch_wave_f64_t<K, true, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_f64_t<K, true, false>(s, p, tasks, n_tasks, ticket, grid);
-    return slab ? launch_wave_f64_t<K, false, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_f64_t<K, false, false>(s, p, tasks, n_tasks, ticket, grid);
+    if (uch) return slab ? launch_wave_f64_t<K, true, true, RING>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_f64_t<K, true, false, RING>(s, p, tasks, n_tasks, ticket, grid);
+    return slab ? launch_wave_f64_t<K, false, true, RING>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_f64_t<K, false, false, RING>(s, p, tasks, n_tasks, ticket, grid);
 }
 
-static int launch_wave(fdtd2d_sim* s, const PassParams<double>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k, bool) {
+static int launch_wave(fdtd2d_sim* s, const PassParams<double>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k, bool ring) {
     if (int rc = check_ch_uniform(s)) return rc;
     const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, sm_count(s));
     CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int), s->stream));
     switch (k) {
-        case 4: return launch_wave_f64_k<4>(s, p, tasks, n_tasks, ticket, grid);
-        case 6: return launch_wave_f64_k<6>(s, p, tasks, n_tasks, ticket, grid);
-        case 8: return launch_wave_f64_k<8>(s, p, tasks, n_tasks, ticket, grid);
+        case 4: return launch_wave_f64_k<4, false>(s, p, tasks, n_tasks, ticket, grid);  // (ring strips are built for k = 8 only)
+        case 8: return ring ? launch_wave_f64_k<8, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_f64_k<8, false>(s, p, tasks, n_tasks, ticket, grid);
         default: return fail(FDTD2D_EINVAL, "no fp64 wavefront kernel for k=%d", k);
     }
 }
@@ -815,14 +814,18 @@ static int plan_pass(const fdtd2d_sim* s, int k, PlanLists* pl) {
 
     // Ring strips: the first / last 128 columns of the padded row.  A source / probe must be re-checked against them
     // (the right strip is not aligned with the tile grid).
-    const bool lr_ok = wave_k && !f64 && (k == 8 || (k == 12 && s->opt.stage)) && s->opt.ring_strips && s->C >= 4 * TILE_TW;
-    const int lr_x0[2] = {0, (s->C + 3) / 4 * 4 - TILE_TW};
+    // (fp32: 128-column strips at k = 8, and at k = 12 on the staged kernel; fp64: 64-column strips at k = 8)
+    const bool lr_ok = wave_k && (f64 ? k == 8 : (k == 8 || (k == 12 && s->opt.stage))) && s->opt.ring_strips && s->C >= 4 * TILE_TW;
+    const int SW = f64 ? 64 : TILE_TW, NQc = f64 ? 2 : 4;  // strip width, columns per 16 bytes
+    const int lr_x0[2] = {0, (s->C + NQc - 1) / NQc * NQc - SW};
     std::vector<unsigned char> lr_special((size_t)n_tiles, 0);
     if (lr_ok) {
         auto mark_lr = [&](const Cell& c, int row_pad) {
             for (int side = 0; side < 2; ++side) {
-                if (c.col < lr_x0[side] || c.col >= lr_x0[side] + TILE_TW) continue;
+                // (the whole tile column is given up for a source / probe near it: conservative, and rare)
                 const int tx = side ? tp.tiles_x - 1 : 0, lrow = c.row - s->row0;
+                const int w0 = std::min(lr_x0[side], tx * tp.CW - tp.hx), w1 = std::max(lr_x0[side] + SW, side ? s->C : tp.CW + tp.hx);
+                if (c.col < w0 || c.col >= w1) continue;
                 for (int ty = 0; ty < tp.tiles_y; ++ty)
                     if (lrow >= row_lo(ty) - row_pad && lrow < row_hi(ty) + row_pad)
                         lr_special[(size_t)c.grid * per_grid + (size_t)ty * tp.tiles_x + tx] = 1;
@@ -945,9 +948,29 @@ static int plan_pass(const fdtd2d_sim* s, int k, PlanLists* pl) {
                             t.b = b, t.y0 = y0, t.y1 = y1, t.side = side + 1, t.band = 0, t.x0 = lr_x0[side];
                             // stored columns: the tile's core, in strip coordinates (whole 16-byte groups; the last group
                             // may reach into the pad columns, which keep their zeros)
-                            t.c0 = side ? tx * tp.CW - t.x0 : 0;
-                            t.c1 = side ? TILE_TW : tp.CW;
-                            add_stretch(t);
+                            if (!f64) {
+                                t.c0 = side ? tx * tp.CW - t.x0 : 0;
+                                t.c1 = side ? TILE_TW : tp.CW;
+                                add_stretch(t);
+                            } else if (side == 0) {
+                                // fp64: the ring strip stores the first half of the tile column, a plain strip the second
+                                t.c0 = 0, t.c1 = sw;
+                                add_stretch(t);
+                                WaveTask u = t;
+                                u.side = 0, u.x0 = sw - hxw, u.c0 = hxw, u.c1 = hxw + sw;
+                                add_stretch(u);
+                            } else {
+                                // fp64, right: the ring strip stores what it can of the (narrower) last tile column -- it needs
+                                // hxw halo columns on its left -- and a plain strip the columns before that, if any
+                                const int X = tx * tp.CW, first = std::max(X, t.x0 + hxw);
+                                t.c0 = first - t.x0, t.c1 = SW;
+                                add_stretch(t);
+                                if (first > X) {
+                                    WaveTask u = t;
+                                    u.side = 0, u.x0 = X - hxw, u.c0 = hxw, u.c1 = hxw + (first - X);
+                                    add_stretch(u);
+                                }
+                            }
                             pl->wave_ring = true;
                         }
                     }

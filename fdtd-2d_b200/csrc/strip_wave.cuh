@@ -93,13 +93,30 @@ __device__ __forceinline__ void st16(double* p, const double (&a)[2]) { *reinter
 // ST[s] (s < K) is the row stored at level s (row i-s-1 when row i arrives), ST[K][1] the Hx of the last row that left;
 // AR[0] receives the arriving level-0 row and AR[s+1] the result of level s, i.e. the row arriving at level s+1.  After
 // the iteration the arrived rows ARE the stored rows: the sets swap.
-template <typename T, int K, bool UCH, int P, bool BAND>
+// LR: the strip holds the left (tk.side == 1) or right (2) Mur ring, which rides along exactly as in wave_run_x2 below: at
+// every level Ez[i, q] = S0[i, q+1] + coef * (S1[i, q+1] - S0[i, q]) on the five ring columns (mirrored on the right), and
+// the right strip keeps H beyond column C-2 and the pad columns as they were.
+template <typename T, int K, bool UCH, int P, bool BAND, bool LR = false>
 __device__ __forceinline__ void wave_run_scalar(const PassParams<T>& p, const WaveTask& tk, T* fring, T* cring, const int l, const T ch_uniform) {
     constexpr int NQ = 16 / (int)sizeof(T), TW = 32 * NQ, NF = WAVE_NF, NC = WAVE_NC, CS = UCH ? 1 : 2;
     constexpr unsigned FULL = 0xffffffffu;
     const bool core = NQ * l >= tk.c0 && NQ * l < tk.c1;
     const int side = tk.band - 1;
     if (BAND) band_wait(p, side);
+    bool ringc[NQ], hoffc[NQ], padc[NQ];
+    T coef = (T)0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) ringc[q] = hoffc[q] = padc[q] = false;
+    if (LR) {
+        coef = p.mur[tk.b];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int gj = tk.x0 + NQ * l + q;
+            ringc[q] = tk.side == 1 ? gj < RING : (gj >= p.C - RING && gj < p.C);
+            hoffc[q] = gj > p.C - 2;  // H is updated in columns 0..C-2 (main.py:70,74)
+            padc[q] = gj > p.C - 1;
+        }
+    }
     // j counts the level-0 rows of the run, `of` is the element offset of the next row to fetch and moves one row per
     // iteration; the row that leaves level K-1 in iteration j is K rows behind the arriving one, i.e. P + 1 + K rows behind `of`
     const int n = tk.y1 - tk.y0 + 2 * K;  // level-0 rows [y0 - K, y1 + K)
@@ -173,6 +190,31 @@ __device__ __forceinline__ void wave_run_scalar(const PassParams<T>& p, const Wa
                 const T curl = sub_rn(sub_rn(AR[s + 1][2][q], left), sub_rn(AR[s + 1][1][q], ST[s + 1][1][q]));
                 AR[s + 1][0][q] = add_rn(ST[s][0][q], mul_rn(curl, ce[q]));
             }
+            if (LR && tk.side != 0) {  // the left / right Mur ring (main.py:33-41)
+                T out[NQ];
+                if (tk.side == 1) {
+                    const T s1r = __shfl_down_sync(FULL, AR[s + 1][0][0], 1);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const T a0 = q < NQ - 1 ? ST[s][0][q < NQ - 1 ? q + 1 : q] : right_nb;
+                        const T a1 = q < NQ - 1 ? AR[s + 1][0][q < NQ - 1 ? q + 1 : q] : s1r;
+                        const T m = add_rn(a0, mul_rn(coef, sub_rn(a1, ST[s][0][q])));
+                        out[q] = ringc[q] ? m : AR[s + 1][0][q];
+                    }
+                } else {
+                    const T s0l = __shfl_up_sync(FULL, ST[s][0][NQ - 1], 1), s1l = __shfl_up_sync(FULL, AR[s + 1][0][NQ - 1], 1);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const T b0 = q > 0 ? ST[s][0][q > 0 ? q - 1 : 0] : s0l, b1 = q > 0 ? AR[s + 1][0][q > 0 ? q - 1 : 0] : s1l;
+                        const T m = add_rn(b0, mul_rn(coef, sub_rn(b1, ST[s][0][q])));
+                        out[q] = padc[q] ? ST[s][0][q] : (ringc[q] ? m : AR[s + 1][0][q]);
+                        AR[s + 1][1][q] = hoffc[q] ? ST[s][1][q] : AR[s + 1][1][q];
+                        AR[s + 1][2][q] = hoffc[q] ? ST[s][2][q] : AR[s + 1][2][q];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) AR[s + 1][0][q] = out[q];
+            }
         }
         cr = (cr + 1) & (NC - 1);
         if (core && j >= 2 * K) {  // row y0 + (j - 2K) < y1 has left level K-1, K steps on
@@ -207,7 +249,7 @@ __device__ __forceinline__ void wave_run_scalar(const PassParams<T>& p, const Wa
     __syncwarp();  // the ring is reused by the next run
 }
 
-template <typename T, int K, bool UCH, int P, bool SLAB>
+template <typename T, int K, bool UCH, int P, bool SLAB, bool RING = false>
 __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassParams<T> p, const WaveTask* tasks, const int n_tasks, int* ticket, const T ch_uniform) {
     constexpr int NQ = 16 / (int)sizeof(T), TW = 32 * NQ, NF = WAVE_NF, NC = WAVE_NC, CS = UCH ? 1 : 2;
     static_assert((NF & (NF - 1)) == 0 && NF > P && (NC & (NC - 1)) == 0 && NC >= K + P + 2, "ring sizes");
@@ -221,10 +263,16 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassP
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n_tasks) break;
         const WaveTask tk = tasks[t];
-        if (SLAB && tk.band)
+        if (RING && tk.side != 0) {
+            if (SLAB && tk.band)
+                wave_run_scalar<T, K, UCH, P, true, true>(p, tk, fring, cring, l, ch_uniform);
+            else
+                wave_run_scalar<T, K, UCH, P, false, true>(p, tk, fring, cring, l, ch_uniform);
+        } else if (SLAB && tk.band) {
             wave_run_scalar<T, K, UCH, P, true>(p, tk, fring, cring, l, ch_uniform);
-        else
+        } else {
             wave_run_scalar<T, K, UCH, P, false>(p, tk, fring, cring, l, ch_uniform);
+        }
     }
 }
 

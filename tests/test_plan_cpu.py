@@ -85,10 +85,10 @@ def check(pl):
         assert x0 % q == 0 and c0 % q == 0 and c1 % q == 0 and 0 <= c0 < c1 <= W and x0 >= 0 and x0 + W <= pitch
         if side == 0:
             assert c0 >= k and W - c1 >= k, "column halo"
-            assert x0 >= RING and x0 + W <= C - RING, "no left / right ring within a plain strip"
+            assert x0 + c0 - k >= RING and x0 + c1 + k <= C - RING, "a left / right ring cell within k columns of what a plain strip stores"
         else:
-            assert pl["ring"] == 1 and pl["dtype"] == 0 and k == 8
-            assert (x0 == 0 and c0 == 0 and W - c1 >= k) if side == 1 else (x0 == (C + 3) // 4 * 4 - 128 and c1 == W and c0 >= k)
+            assert pl["ring"] == 1 and k == 8
+            assert (x0 == 0 and c0 == 0 and W - c1 >= k) if side == 1 else (x0 == (C + q - 1) // q * q - W and c1 == W and c0 >= k)
         for g, r, c in pl["src"]:
             assert not (g == b_ and y0 - k <= r - row0 < y1 + k and x0 <= c < x0 + W), "a source inside a run's window"
         for g, r, c in pl["probe"]:
@@ -153,9 +153,9 @@ def test_wavefront_takes_large_grids_and_both_dtypes(lib):
     pl = plan(lib, 0, 65536, 65536, 8, rows=(8192, 16384), halo=8)
     assert pl["n_wave_band"] >= 2 * (65536 // 112) and pl["n_edge"] == 0, "a middle slab without sources is all wavefront"
     pl = plan(lib, 1, 8192, 8192, 8)
-    assert pl["n_wave"] > 1000 and pl["CW"] == 96 and pl["ring"] == 0
+    assert pl["n_wave"] > 1000 and pl["CW"] == 96 and pl["ring"] == 1 and pl["n_edge"] < 300, pl["n_edge"]
     t = pl["tasks"]
-    assert set(np.unique(t[:, 5] - t[:, 4])) == {48}
+    assert set(np.unique((t[:, 5] - t[:, 4])[t[:, 6] == 0])) == {48}
     pl = plan(lib, 1, 8192, 8192, 8, wavefront=0)
     assert pl["n_wave"] == 0 and pl["n_tma"] == 0 and pl["n_edge"] == pl["tiles_y"] * pl["tiles_x"]
     pl = plan(lib, 0, 1024, 1024, 8)  # small grid: persistent TMA tiles
