@@ -1,4 +1,4 @@
-"""k sweep of the tile kernels on one GPU (k = 0: library default).  usage: [KS=8] [SIZES=4096,16384] [FDTD2D_FAST_CFG=n] python profiles/quick_bench.py"""
+"""k sweep on one GPU (k = 0: library default).  usage: [KS=8] [SIZES=4096,16384] [FDTD2D_WAVEFRONT=0] python profiles/quick_bench.py"""
 import os, sys, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fdtd2d_b200 as fd, torch
