@@ -816,3 +816,70 @@ def test_staged_wavefront_equals_one_warp_kernels_large(fd):
     for o in outs[1:]:
         for a, b in zip(outs[0], o):
             assert_bits(a, b, "staged 12 levels vs 8 levels")
+
+
+# --------------------------------------------------------------------------------------------
+# non-blocking copies: two jobs in flight from one host thread (what bench.py's e2e does)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shared_stream", [False, True])
+def test_async_copies_pipeline_two_handles_from_one_thread(fd, shared_stream):
+    """Upload (materials + state), step, download with the *_async entry points on pinned arrays, two handles alternating so
+    that one job's copies overlap the other's kernels; every job must give what the blocking calls give.  With a shared
+    compute stream (how sharded jobs run) the handles must still only wait for their OWN work."""
+    import torch
+
+    R, C, n = 1500, 2100, 160
+    rng = np.random.default_rng(13)
+    eps, mu, Ez, Hx, Hy = _random_problem(rng, R, C, "float32")
+    mu[...] = np.float32(4 * np.pi * 1e-7)
+
+    def pin(a):
+        t = torch.from_numpy(a.copy()).pin_memory()
+        return t.numpy()
+
+    peps, pmu, pEz, pHx, pHy = (pin(a) for a in (eps, mu, Ez, Hx, Hy))
+    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as ref:
+        ref.set_point_source(R // 2, C // 2, n, FC)
+        ref.set_probes([(R // 2, C // 2 + 16), (R // 4, C // 4)], n)
+        ref.set_materials(eps, mu)
+        ref.set_state(Ez, Hx, Hy)
+        ref.step(n, 0)
+        want_Ez, want_tr = ref.read_Ez(), ref.read_probes(0, n)
+    sims = [fd.Simulation(R, C, np.float32, dt=DT, dx=DX) for _ in range(2)]
+    stream = torch.cuda.Stream()
+    outs = [pin(np.zeros((R, C), np.float32)) for _ in sims]
+    try:
+        for sim in sims:
+            if shared_stream:
+                sim.set_stream(stream.cuda_stream)
+            sim.set_point_source(R // 2, C // 2, n, FC)
+            sim.set_probes([(R // 2, C // 2 + 16), (R // 4, C // 4)], n)
+
+        def issue(w):
+            sims[w].step_index = 0
+            sims[w].set_materials_async(peps, pmu)
+            sims[w].set_state_async(pEz, pHx, pHy)
+            sims[w].step(n, 0)
+            sims[w].read_Ez_async(outs[w])
+
+        queued, done = [], 0
+        for j in range(6):
+            if len(queued) == 2:
+                w = queued.pop(0)
+                sims[w].synchronize()
+                assert_bits(outs[w], want_Ez, f"job {done} (handle {w})")
+                assert_bits(sims[w].read_probes(0, n), want_tr, f"probes of job {done}")
+                outs[w][...] = 0
+                done += 1
+            issue(j % 2)
+            queued.append(j % 2)
+        for w in queued:
+            sims[w].synchronize()
+            assert_bits(outs[w], want_Ez, f"job {done} (handle {w})")
+            done += 1
+        assert done == 6
+        with pytest.raises(ValueError):
+            sims[0].set_state_async(Ez.astype(np.float64), pHx, pHy)  # the caller's buffer is taken as it is: wrong dtype is refused
+    finally:
+        for sim in sims:
+            sim.close()

@@ -100,3 +100,29 @@ def test_slab_exchange_matches_single_domain(tmp_path, world):
         assert np.array_equal(g["Ez"], Ez[b:e]), f"Ez rows of rank {r}"
         assert np.array_equal(g["Hx"], Hx[b:e]), f"Hx rows of rank {r}"
         assert np.array_equal(g["Hy"], Hy[b:min(e, R - 1)]), f"Hy rows of rank {r}"
+
+
+def _blob_worker(rank, world, port, out_dir):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import fdtd2d_b200 as fd
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = bytes([rank]) * 640  # stands in for fdtd2d_peer_export's blob
+    got = fd.exchange_peer_blobs(mine, rank, world)
+    np.save(os.path.join(out_dir, f"blob{rank}.npy"), np.array([got.get(0, b"\xff")[0], got.get(1, b"\xff")[0], len(got)]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_blobs_reach_the_right_neighbours(tmp_path, world):
+    """The one collective of the peer-link set-up (SlabSimulation, exchange='p2p'): every rank's blob is all-gathered and
+    each rank keeps the blobs of the slab above (side 0) and below (side 1) -- checked over gloo, no GPU."""
+    mp.spawn(_blob_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        top, bottom, n = np.load(os.path.join(str(tmp_path), f"blob{r}.npy"))
+        assert top == (r - 1 if r > 0 else 255) and bottom == (r + 1 if r < world - 1 else 255)
+        assert n == (r > 0) + (r < world - 1)
