@@ -1191,12 +1191,14 @@ template <typename T> static int launch_hybrid_t(fdtd2d_sim* s, int k, int part)
     PassParams<T> p;
     fill_params(s, pl.tp, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC, &p, &pl);
     const int e_off = part == 2 ? pl.n_edge_band : 0, w_off = part == 2 ? pl.n_wave_band : 0;
-    const int n_edge = part == 1 ? pl.n_edge_band : pl.n_edge - e_off;
-    const int n_wave = part == 1 ? pl.n_wave_band : pl.n_wave - w_off;
-    const int n_fast = part == 1 ? 0 : pl.n_fast;
+    int n_edge = part == 1 ? pl.n_edge_band : pl.n_edge - e_off;
+    int n_wave = part == 1 ? pl.n_wave_band : pl.n_wave - w_off;
+    int n_fast = part == 1 ? 0 : pl.n_fast;
+    if (s->opt.measure_skip & 1) n_edge = 0;  // (timing of the parts of a pass; the results are wrong)
+    if (s->opt.measure_skip & 2) n_wave = n_fast = 0;
     if (peer_mode(s) && part != 2)  // band tasks done in this pass: counted from zero
         CUDA_TRY(cudaMemsetAsync(s->d_slab_flags + FLAG_CNT_TOP, 0, 2 * sizeof(unsigned), s->stream));
-    const bool both = n_edge > 0 && (n_wave > 0 || n_fast > 0);
+    const bool both = n_edge > 0 && (n_wave > 0 || n_fast > 0) && !(s->opt.measure_skip & 4);
     cudaStream_t estream = s->stream;
     if (both) {
         if (!s->side_stream) {
@@ -1847,9 +1849,17 @@ int fdtd2d_zero_state(fdtd2d_sim* s) {
     REQUIRE(s, "handle is null");
     USE_DEVICE(s);
     if (int rc = begin_work(s)) return rc;
+    if (peer_mode(s)) {  // the neighbours' last ghost rows must have landed before they are cleared
+        if (int rc = wait_own_work(s)) return rc;
+        if (int rc = peer_settle(s)) return rc;
+    }
     const size_t bytes = s->grid_elems * s->esize * (size_t)s->batch;
+    // With peer links only the current set is cleared: the other set's ghost rows belong to the neighbours, whose first
+    // pass after their own zero_state may already be storing into them (every pass overwrites all owned rows of its
+    // output set, so stale values there are never read).
     for (int h = 0; h < 2; ++h)
-        for (int f = 0; f < 3; ++f) CUDA_TRY(cudaMemsetAsync(s->field[h][f], 0, bytes, s->stream));
+        if (!peer_mode(s) || h == s->cur)
+            for (int f = 0; f < 3; ++f) CUDA_TRY(cudaMemsetAsync(s->field[h][f], 0, bytes, s->stream));
     s->step = 0;
     return mark_work(s);
 }
@@ -2200,7 +2210,8 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
                 if (pl.d_wave) k = 12;
             }
         } else {
-            // fp64: 8 levels where the wavefront kernel takes the grid, 4 steps per pass on the tile kernel otherwise
+            // fp64: 8 levels where the wavefront kernel takes the grid or where the k = 8 tiles fit one wave of CTAs (small
+            // grids are bound by launch and barrier latency: 200^2 runs 275k steps/s at k = 8, 217k at k = 4); otherwise 4
             k = s->opt.f64_k > 0 ? std::min(s->opt.f64_k, FDTD2D_MAX_K) : 8;
             if (s->opt.f64_k <= 0) {
                 if (s->variant == 1) {
@@ -2209,7 +2220,7 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
                     PassPlan& pl = s->hybrid[8];
                     if (!pl.valid)
                         if (int rc = classify_tiles(s, 8, &pl)) return rc;
-                    if (!pl.d_wave) k = 4;
+                    if (!pl.d_wave && pl.n_edge > sm_count(s)) k = 4;
                 }
             }
         }

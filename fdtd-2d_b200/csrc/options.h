@@ -29,6 +29,8 @@ struct Options {
     int stage = 0;             // k = 12 passes on the staged wavefront (three warps of 4 levels each, strip_stage.cuh) instead of
                                // the one-warp 12-level instance; 4 / 5 = groups per CTA
     int debug = 0;             // print launch geometry to stderr
+    int measure_skip = 0;      // MEASUREMENT AID, results are wrong: 1 = passes launch no edge tiles, 2 = no runs / plain tiles,
+                               // 4 = edge tiles on the main stream (no overlap with the runs)
 };
 
 struct OptionKey {
@@ -54,6 +56,7 @@ inline const OptionKey* option_keys(int* n) {
         {"fuse", &Options::fuse},
         {"stage", &Options::stage},
         {"debug", &Options::debug},
+        {"measure_skip", &Options::measure_skip},
     };
     *n = (int)(sizeof(keys) / sizeof(keys[0]));
     return keys;

@@ -201,6 +201,10 @@ class SlabSimulation:
         first (the neighbours' kernels store into this slab's ghost rows): call barrier() between runs."""
         self.sim.set_state(Ez, Hx, Hy)
 
+    def zero_state(self):
+        """grid_init (main.py:79-85) for this slab, on the device; the step index returns to 0."""
+        self.sim.zero_state()
+
     def set_point_source(self, row, col, nsteps, fc=30e9, kind="ricker"):
         self.sim.set_point_source(row, col, nsteps, fc, kind)
 

@@ -586,6 +586,89 @@ def test_default_path_at_bench_size_vs_oracle(fd, oracle, engine):
     _window_check(c_oracle, (Ez0, Hx0, Hy0), (Ez, Hx, Hy), ce, ch, mur[0], n, windows, m, "default path")
 
 
+class _DeviceView:
+    """numpy-style window access to a field the library holds in HBM (fdtd2d_device_field), for grids whose state does
+    not fit the host: rows x pitch elements, wrapped through __cuda_array_interface__."""
+
+    def __init__(self, sim, field):
+        import torch
+
+        self.__cuda_array_interface__ = {"shape": (sim.local_rows, sim.pitch), "typestr": np.dtype(sim.dtype).str,
+                                         "data": (sim.device_field(field), False), "version": 3}
+        self.t = torch.as_tensor(self, device=f"cuda:{sim.device}")
+
+    def get(self, r0, r1, c0, c1):
+        return self.t[r0:r1, c0:c1].cpu().numpy()
+
+    def put(self, r0, c0, a):
+        import torch
+
+        self.t[r0:r0 + a.shape[0], c0:c0 + a.shape[1]] = torch.from_numpy(a).to(self.t.device)
+
+
+@pytest.mark.parametrize("R,C", [(16384, 16384), (65536, 65536)], ids=["cfg3_16384sq", "cfg4_65536sq"])
+def test_baseline_sizes_on_one_gpu_vs_oracle_windows(fd, oracle, engine, R, C):
+    """BASELINE configs[2] and configs[3] at their FULL sizes on one GPU (65536^2: 137 GB of HBM, element offsets past
+    2^31), default options, 24 steps = 3 passes.  The state is zero except for random patches written straight into HBM
+    around eight windows -- the four corners, the four edges away from the corners (top / bottom ring tiles, left / right
+    ring strips), two interior spots far into the index range -- and each window is compared with the C oracle run on
+    its patch (cut sides lie n + 8 cells outside the window; true edges of the grid stay edges)."""
+    import torch
+
+    if engine == "tiled":
+        pytest.skip("one kernel choice is enough at this size")
+    need = (8 * R * C * 4) * 1.05
+    if torch.cuda.get_device_properties(0).total_memory < need:
+        pytest.skip(f"needs {need / 2**30:.0f} GiB of HBM")
+    c_oracle, npo = oracle
+    n, m = 24, 32
+    rng = np.random.default_rng(R)
+    windows = [(0, 0, 48, 48), (0, C - 48, 48, 48), (R - 48, 0, 48, 48), (R - 48, C - 48, 48, 48),
+               (0, C // 2 + 1000, 56, 96), (R - 56, C // 3, 56, 96), (R // 2 + 777, 0, 64, 40), (R // 3, C - 40, 64, 40),
+               (R - 5000, C - 7000, 64, 96), (R // 2 - 20, C // 2 - 30, 64, 64)]
+    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
+        sim.set_materials_random(seed=2026, span=9.0)
+        sim.set_point_source(R // 2, C // 2, 40, FC)
+        sim.zero_state()
+        sim.synchronize()
+        views = [_DeviceView(sim, f) for f in range(5)]
+        patches = []
+        for (r0, c0, h, w) in windows:
+            a, b_, c_, d = max(0, r0 - m), min(R, r0 + h + m), max(0, c0 - m), min(C, c0 + w + m)
+            Ez0 = (1e-3 * rng.standard_normal((b_ - a, d - c_))).astype(np.float32)
+            Hx0 = (1e-6 * rng.standard_normal((b_ - a, d - c_ - 1))).astype(np.float32)
+            Hy0 = (1e-6 * rng.standard_normal((b_ - a - 1, d - c_))).astype(np.float32)
+            views[0].put(a, c_, Ez0), views[1].put(a, c_, Hx0), views[2].put(a, c_, Hy0)
+            patches.append((a, b_, c_, d, Ez0, Hx0, Hy0, views[3].get(a, b_, c_, d), views[4].get(a, b_, c_, d)))
+        torch.cuda.synchronize()
+        info = sim.plan_info(8)
+        assert info["wave_runs"] > 1000 and info["ring_strips"] == 1, info
+        sim.step(n, 0)
+        assert sim.pass_count == 3
+        sim.synchronize()
+        out = [_DeviceView(sim, f) for f in range(3)]  # (the current set has changed)
+        u00 = np.float32(sim_hash(fd, 2026, 0, 0, 0))
+        eps00 = np.float32(8.85418e-12) * (np.float32(1) + np.float32(9.0) * u00)
+        cc = 1 / np.sqrt(np.float32(4 * np.pi * 1e-7) * eps00)
+        coef = np.float32((cc * DT - DX) / (cc * DT + DX))
+        amp = npo.source_table("ricker", n, DT, FC)
+        for (r0, c0, h, w), (a, b_, c_, d, Ez0, Hx0, Hy0, ce, ch) in zip(windows, patches):
+            src = [(R // 2 - a, C // 2 - c_)] if a <= R // 2 < b_ and c_ <= C // 2 < d else []
+            c_oracle.run(Ez0, Hx0, Hy0, ce, ch, coef, n, amp if src else None, src, [])
+            ro, co = r0 - a, c0 - c_
+            assert_bits(out[0].get(r0, r0 + h, c0, c0 + w), Ez0[ro:ro + h, co:co + w], f"Ez window at {(r0, c0)}")
+            wx, hy = min(w, C - 1 - c0), min(h, R - 1 - r0)
+            assert_bits(out[1].get(r0, r0 + h, c0, c0 + wx), Hx0[ro:ro + h, co:co + wx], f"Hx window at {(r0, c0)}")
+            assert_bits(out[2].get(r0, r0 + hy, c0, c0 + w), Hy0[ro:ro + hy, co:co + w], f"Hy window at {(r0, c0)}")
+            assert np.count_nonzero(Ez0[ro:ro + h, co:co + w]) > h * w // 2
+
+
+def sim_hash(fd, seed, grid, row, col):
+    from fdtd2d_b200 import _lib
+
+    return _lib.lib().fdtd2d_hash_uniform(seed, grid, row, col)
+
+
 def test_fp64_wavefront_large_vs_oracle_windows(fd, oracle, engine):
     """4096 x 4096 fp64 with the default choice (8 levels on 64-column strips): windows against the C oracle, and the
     whole state against the tile kernel (wavefront option off)."""

@@ -81,6 +81,34 @@ def test_slabs_match_single_domain_and_oracle(world, k, dtype, exchange):
     assert np.array_equal(total, otrace)
 
 
+def test_slabs_zero_state_restarts_a_job(exchange):
+    """A second job on the same slab handles (zero_state = grid_init on the device, the source restarted) must equal a
+    fresh single-domain run: with peer links only the current field set is cleared, the ghost rows of the other one
+    belong to the neighbours (bench.py's e2e restarts its slab jobs this way)."""
+    import fdtd2d_b200 as fd
+
+    R, C, n = 1500, 1100, 41
+    with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
+        sim.set_materials_random(5, 9.0)
+        sim.set_sources([(0, R // 3, C // 2, 0), (0, 2 * R // 3 + 1, 40, 0)], (1e-2 * np.ones((1, n))))
+        sim.step(n, 8)
+        ref = sim.state()
+    grp = fd.InProcessSlabs(R, C, np.float32, dt=DT, dx=DX, world=3, devices=_devices(), halo=8, exchange=exchange)
+    try:
+        for s in grp.slabs:
+            s.set_materials_random(5, 9.0)
+            s.set_sources([(0, R // 3, C // 2, 0), (0, 2 * R // 3 + 1, 40, 0)], (1e-2 * np.ones((1, n))))
+        for job in range(3):  # 41 steps at k = 8 = 6 passes: the field sets swap roles from job to job
+            for s in grp.slabs:
+                s.zero_state()
+            grp.step(n, 8)
+            got = grp.gather()
+            for a, b in zip(got, ref):
+                assert np.array_equal(a, b), f"job {job}"
+    finally:
+        grp.close()
+
+
 def test_large_slabs_vs_single_domain_fast_path(exchange, plain_tile_kernel):
     """4 slabs of a 4096 x 3000 fp32 grid (wavefront runs incl. the band runs, or TMA tiles) == single domain, k = 8,
     with a remainder pass (44 = 5 x 8 + 4)."""
