@@ -145,6 +145,11 @@ struct fdtd2d_sim {
     int ch_uniform = -1;  // dt/(mu*dx) the same in every cell? (-1 = not checked since the maps last changed)
     double ch_value = 0.0;
     int* d_flag = nullptr;
+    // fdtd2d_set_materials_async runs the permeability check right behind the coefficient kernels on the copy stream and
+    // parks the answer in pinned host memory: {flag, value bits}
+    unsigned long long* h_check = nullptr;
+    cudaEvent_t ev_check = nullptr;
+    bool check_pending = false;
     int resident_ok = -1;  // cluster-resident kernel usable for this handle? (-1 = not decided yet)
     int resident_cluster = 0, resident_rpc = 0, resident_edge = 0, resident_cfg = 0;  // CTAs per grid, rows per middle / first CTA, kResCfgs index
     unsigned char* d_gray = nullptr;  // snapshot background (Rl x C per grid)
@@ -155,6 +160,7 @@ struct fdtd2d_sim {
     unsigned* d_slab_flags = nullptr;
     PeerLink peer[2];
     unsigned pass_seq = 0;
+    unsigned settled_seq = 0;  // the newest state whose ghost rows are known to have arrived (peer_settle)
     long long fused_pairs = 0, fused_checked = 0;  // fused double passes launched / covered by the last look at the error flag
     // fdtd2d_*_async: copies run on a stream of their own, ordered against this handle's stepping work by two events
     cudaStream_t copy_stream = nullptr;
@@ -468,8 +474,44 @@ template <typename T> __global__ void uniform_check_kernel(const T* a, int rows,
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(differs, 1);
 }
 
+// The check queued on `st`, the answer copied to the handle's pinned words; ev_check marks its arrival.
+static int enqueue_ch_check(fdtd2d_sim* s, cudaStream_t st) {
+    if (!s->d_flag) CUDA_TRY(cudaMalloc(&s->d_flag, sizeof(int)));
+    if (!s->h_check) CUDA_TRY(cudaHostAlloc(&s->h_check, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    if (!s->ev_check) CUDA_TRY(cudaEventCreateWithFlags(&s->ev_check, cudaEventDisableTiming));
+    CUDA_TRY(cudaMemsetAsync(s->d_flag, 0, sizeof(int), st));
+    const int blocks = sm_count(s) * 8;
+    if (s->dtype == FDTD2D_F32)
+        uniform_check_kernel<float><<<blocks, 256, 0, st>>>((const float*)s->ch, s->batch * s->Rl, s->C, (int)s->pitch, s->d_flag);
+    else
+        uniform_check_kernel<double><<<blocks, 256, 0, st>>>((const double*)s->ch, s->batch * s->Rl, s->C, (int)s->pitch, s->d_flag);
+    CUDA_TRY(cudaGetLastError());
+    s->h_check[0] = 1, s->h_check[1] = 0;
+    CUDA_TRY(cudaMemcpyAsync(&s->h_check[0], s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&s->h_check[1], s->ch, s->esize, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(s->ev_check, st));
+    s->launches += 1;
+    return 0;
+}
+
 static int check_ch_uniform(fdtd2d_sim* s) {
     if (s->ch_uniform >= 0) return 0;
+    if (s->check_pending) {  // queued with the maps (fdtd2d_set_materials_async): usually long done, and no other handle's work
+        CUDA_TRY(cudaEventSynchronize(s->ev_check));  // on a shared stream stands between the host and the answer
+        s->check_pending = false;
+        const bool differs = (int)(s->h_check[0] & 0xffffffffu) != 0;
+        if (s->dtype == FDTD2D_F32) {
+            float v;
+            memcpy(&v, &s->h_check[1], sizeof v);
+            s->ch_value = v;
+        } else {
+            double v;
+            memcpy(&v, &s->h_check[1], sizeof v);
+            s->ch_value = v;
+        }
+        s->ch_uniform = (differs || !s->opt.uniform_ch) ? 0 : 1;
+        return 0;
+    }
     if (!s->d_flag) CUDA_TRY(cudaMalloc(&s->d_flag, sizeof(int)));
     CUDA_TRY(cudaMemsetAsync(s->d_flag, 0, sizeof(int), s->stream));
     // the batch grids are back to back: rows = batch * Rl
@@ -1501,7 +1543,10 @@ static int peer_settle(fdtd2d_sim* s) {
                                      f[FLAG_ERR] == 1 ? "top" : "bottom");
         const bool top_ok = !s->peer[0].attached || (int)(f[FLAG_IN_TOP] - s->pass_seq) >= 0;
         const bool bot_ok = !s->peer[1].attached || (int)(f[FLAG_IN_BOT] - s->pass_seq) >= 0;
-        if (top_ok && bot_ok) return 0;
+        if (top_ok && bot_ok) {
+            s->settled_seq = s->pass_seq;
+            return 0;
+        }
         if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20))
             return fail(FDTD2D_ESTATE, "halo rows of state %u have not arrived after 20 s (flags %u / %u)", s->pass_seq, f[FLAG_IN_TOP], f[FLAG_IN_BOT]);
         std::this_thread::sleep_for(std::chrono::microseconds(50));
@@ -1679,6 +1724,8 @@ int fdtd2d_destroy(fdtd2d_sim* s) {
     cudaFree(s->d_lut);
     cudaFree(s->d_canvas);
     cudaFree(s->d_flag);
+    if (s->h_check) cudaFreeHost(s->h_check);
+    if (s->ev_check) cudaEventDestroy(s->ev_check);
     cudaFree(s->d_slab_flags);
     free_plans(s);
     if (s->side_stream) cudaStreamDestroy(s->side_stream);
@@ -1849,7 +1896,9 @@ int fdtd2d_zero_state(fdtd2d_sim* s) {
     REQUIRE(s, "handle is null");
     USE_DEVICE(s);
     if (int rc = begin_work(s)) return rc;
-    if (peer_mode(s)) {  // the neighbours' last ghost rows must have landed before they are cleared
+    if (peer_mode(s) && s->settled_seq != s->pass_seq) {
+        // the neighbours' last ghost rows must have landed before they are cleared (nothing to wait for when the handle
+        // was synchronised after its last step: a job pipeline that re-uses the handle then queues this without blocking)
         if (int rc = wait_own_work(s)) return rc;
         if (int rc = peer_settle(s)) return rc;
     }
@@ -1870,6 +1919,7 @@ int fdtd2d_zero_state(fdtd2d_sim* s) {
 static void materials_changed(fdtd2d_sim* s) {
     s->coeffs_set = true;
     s->ch_uniform = -1;
+    s->check_pending = false;
 }
 
 int fdtd2d_set_mur_coef(fdtd2d_sim* s, const void* mur_coef) {
@@ -1893,7 +1943,7 @@ int fdtd2d_set_coeffs(fdtd2d_sim* s, const void* ce, const void* ch, const void*
     return 0;
 }
 
-static int finish_materials(fdtd2d_sim* s, double dt, double dx, bool wait);
+static int finish_materials(fdtd2d_sim* s, double dt, double dx, bool wait, bool on_copy_stream = false);
 
 int fdtd2d_set_materials(fdtd2d_sim* s, const void* eps, const void* mu, double dt, double dx) {
     REQUIRE(s && eps && mu, "null argument");
@@ -1911,8 +1961,7 @@ int fdtd2d_set_materials_async(fdtd2d_sim* s, const void* eps, const void* mu, d
     if (int rc = copy_fork(s)) return rc;
     if (int rc = transfer_field(s, s->ce, const_cast<void*>(eps), s->Rl, s->C, true, s->copy_stream)) return rc;
     if (int rc = transfer_field(s, s->ch, const_cast<void*>(mu), s->Rl, s->C, true, s->copy_stream)) return rc;
-    if (int rc = copy_join(s)) return rc;
-    return finish_materials(s, dt, dx, false);
+    return finish_materials(s, dt, dx, false, true);
 }
 
 double fdtd2d_hash_uniform(uint64_t seed, uint32_t grid, uint32_t row, uint32_t col) {
@@ -1943,29 +1992,39 @@ int fdtd2d_set_materials_random(fdtd2d_sim* s, uint64_t seed, double span, doubl
 
 // eps/mu are staged in ce/ch: form the Mur coefficient(s) and the coefficient maps in place (device-side tail of
 // every fdtd2d_set_materials* entry point)
-static int finish_materials(fdtd2d_sim* s, double dt, double dx, bool wait) {
-    if (int rc = begin_work(s)) return rc;  // (an asynchronous upload of eps / mu may still be in flight)
+// on_copy_stream: the asynchronous form -- the kernels follow the uploads on the copy stream (the handle's next stepping
+// work waits for them through ev_copy), so that on a compute stream shared with other handles nothing of this job queues
+// behind their kernels; the permeability check rides along.
+static int finish_materials(fdtd2d_sim* s, double dt, double dx, bool wait, bool on_copy_stream) {
+    if (!on_copy_stream)
+        if (int rc = begin_work(s)) return rc;  // (an asynchronous upload of eps / mu may still be in flight)
+    cudaStream_t st = on_copy_stream ? s->copy_stream : s->stream;
     const long long n = (long long)s->grid_elems * s->batch;
     const int blocks = (int)std::min<long long>((n + 255) / 256, sm_count(s) * 16);
     const bool has_corner = s->row0 == 0;
     if (s->dtype == FDTD2D_F32) {
         if (has_corner)
-            mur_from_materials_kernel<float><<<(s->batch + 127) / 128, 128, 0, s->stream>>>(
+            mur_from_materials_kernel<float><<<(s->batch + 127) / 128, 128, 0, st>>>(
                 (const float*)s->ce, (const float*)s->ch, (long long)s->grid_elems, s->batch, (float)dt, (float)dx,
                 (float*)s->mur);
-        coeff_from_materials_kernel<float><<<blocks, 256, 0, s->stream>>>((float*)s->ce, (float*)s->ch, n, (float)dt,
+        coeff_from_materials_kernel<float><<<blocks, 256, 0, st>>>((float*)s->ce, (float*)s->ch, n, (float)dt,
                                                                          (float)dx);
     } else {
         if (has_corner)
-            mur_from_materials_kernel<double><<<(s->batch + 127) / 128, 128, 0, s->stream>>>(
+            mur_from_materials_kernel<double><<<(s->batch + 127) / 128, 128, 0, st>>>(
                 (const double*)s->ce, (const double*)s->ch, (long long)s->grid_elems, s->batch, dt, dx, (double*)s->mur);
-        coeff_from_materials_kernel<double><<<blocks, 256, 0, s->stream>>>((double*)s->ce, (double*)s->ch, n, dt, dx);
+        coeff_from_materials_kernel<double><<<blocks, 256, 0, st>>>((double*)s->ce, (double*)s->ch, n, dt, dx);
     }
     CUDA_TRY(cudaGetLastError());
-    if (wait) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (wait) CUDA_TRY(cudaStreamSynchronize(st));
     s->launches += has_corner ? 2 : 1;
     materials_changed(s);
     if (has_corner) s->mur_set = true;
+    if (on_copy_stream) {
+        if (int rc = enqueue_ch_check(s, st)) return rc;
+        s->check_pending = true;
+        return copy_join(s);
+    }
     return mark_work(s);
 }
 
