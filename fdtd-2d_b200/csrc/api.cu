@@ -86,7 +86,7 @@ struct PassPlan {
     WaveTask* d_wave = nullptr;
     bool wave_ring = false;           // the list holds runs of the strips with the left / right Mur ring
     int band_expected[2] = {0, 0};    // band tasks (runs + edge tiles) next to the top / bottom neighbour
-    int* d_ticket = nullptr;          // next run to hand out (reset before every launch)
+    int* d_ticket = nullptr;          // next run to hand out (zero between launches: the last draw of a launch resets it)
     // fused double pass (strip_wave.cuh): the runs of two consecutive passes in one ticket order; the phase-1 pieces next to
     // edge tiles wait for a second, short launch
     int n_fused = 0, n_deferred = 0, fuse_nblk = 0;
@@ -591,7 +591,6 @@ static bool wave_has_k(const fdtd2d_sim* s, int k) {
 static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k, bool ring) {
     if (int rc = check_ch_uniform(s)) return rc;
     const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, sm_count(s));
-    CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int), s->stream));
     const bool uch = s->ch_uniform == 1;  // uniform permeability: the map is not read at all (28 instead of 32 B per cell and pass)
     const bool slab = s->has_top_nb || s->has_bot_nb;
     if (k == 12) {  // (runs for k = 12 are only built when the permeability is uniform)
@@ -620,7 +619,6 @@ static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask
 static int launch_wave_fused(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, bool ring) {
     if (int rc = check_ch_uniform(s)) return rc;
     const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, sm_count(s));
-    CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int), s->stream));
     const bool uch = s->ch_uniform == 1;
     if (uch) return ring ? launch_wave_x2_t<8, true, WAVE_P, true, 2>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_x2_t<8, true, WAVE_P, false, 2>(s, p, tasks, n_tasks, ticket, grid);
     return ring ? launch_wave_x2_t<8, false, WAVE_P, true, 2>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_x2_t<8, false, WAVE_P, false, 2>(s, p, tasks, n_tasks, ticket, grid);
@@ -635,7 +633,6 @@ template <int K, bool RING> static int launch_wave_f64_k(fdtd2d_sim* s, const Pa
 static int launch_wave(fdtd2d_sim* s, const PassParams<double>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k, bool ring) {
     if (int rc = check_ch_uniform(s)) return rc;
     const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, sm_count(s));
-    CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(int), s->stream));
     switch (k) {
         case 4: return launch_wave_f64_k<4, false>(s, p, tasks, n_tasks, ticket, grid);  // (ring strips are built for k = 8 only)
         case 8: return ring ? launch_wave_f64_k<8, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_f64_k<8, false>(s, p, tasks, n_tasks, ticket, grid);
@@ -1179,6 +1176,7 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
     pl->n_fast = (int)L.fast.size();
     if (pl->n_wave) {
         CUDA_TRY(cudaMalloc(&pl->d_ticket, sizeof(int)));
+        CUDA_TRY(cudaMemsetAsync(pl->d_ticket, 0, sizeof(int), s->stream));  // (the kernels put it back to zero themselves)
         CUDA_TRY(cudaMalloc(&pl->d_wave, sizeof(WaveTask) * L.tasks.size()));
         // on the handle's own stream: a plain cudaMemcpy goes through the legacy default stream, which a non-blocking
         // stream does not wait for -- with another handle keeping the GPU busy the kernel could read the list before it
@@ -1238,8 +1236,6 @@ template <typename T> static int launch_hybrid_t(fdtd2d_sim* s, int k, int part)
     int n_fast = part == 1 ? 0 : pl.n_fast;
     if (s->opt.measure_skip & 1) n_edge = 0;  // (timing of the parts of a pass; the results are wrong)
     if (s->opt.measure_skip & 2) n_wave = n_fast = 0;
-    if (peer_mode(s) && part != 2)  // band tasks done in this pass: counted from zero
-        CUDA_TRY(cudaMemsetAsync(s->d_slab_flags + FLAG_CNT_TOP, 0, 2 * sizeof(unsigned), s->stream));
     const bool both = n_edge > 0 && (n_wave > 0 || n_fast > 0) && !(s->opt.measure_skip & 4);
     cudaStream_t estream = s->stream;
     if (both) {

@@ -156,8 +156,9 @@ template <typename T> __device__ __forceinline__ void band_wait(const PassParams
 template <typename T> __device__ __forceinline__ void band_done(const PassParams<T>& p, int side) {
     if (!(side ? p.peer_out[1][0] : p.peer_out[0][0])) return;
     __threadfence_system();  // cumulative: covers the stores of the threads this one has synchronised with
-    const unsigned done = atomicAdd(p.flags + FLAG_CNT_TOP + side, 1u) + 1u;
-    if (done == (unsigned)(side ? p.band_expected[1] : p.band_expected[0])) {
+    // (atomicInc wraps to zero at the last task: the counter is ready for the next pass without a memset)
+    const unsigned last = (unsigned)(side ? p.band_expected[1] : p.band_expected[0]) - 1u;
+    if (atomicInc(p.flags + FLAG_CNT_TOP + side, last) == last) {
         __threadfence_system();
         st_release_sys(side ? p.peer_flag[1] : p.peer_flag[0], p.seq + 1u);
     }

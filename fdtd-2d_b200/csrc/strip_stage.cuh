@@ -248,7 +248,10 @@ __global__ void __launch_bounds__(NG * STAGE_S * 32, 1) strip_stage_kernel(const
         }
         group_sync(g);
         const int ti = *gtask;
-        if (ti >= n_tasks) break;
+        if (ti >= n_tasks) {  // (the last ticket drawn by the launch resets the counter, as in strip_wave.cuh)
+            if (t == 0 && l == 0 && ti == n_tasks + (int)gridDim.x * NG - 1) atomicExch(ticket, 0);
+            break;
+        }
         const WaveTask tk = tasks[ti];
         const bool lr = RING && tk.side != 0;
         if (t == 0) {

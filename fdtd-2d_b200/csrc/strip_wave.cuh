@@ -261,7 +261,12 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_kernel(const PassP
         int t = 0;
         if (l == 0) t = atomicAdd(ticket, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n_tasks) break;
+        if (t >= n_tasks) {
+            // every warp of the launch draws exactly one ticket past the end: the last of those puts the counter back to
+            // zero for the next launch (no memset per pass -- a memset can queue behind a host copy on a copy engine)
+            if (l == 0 && t == n_tasks + (int)gridDim.x * WAVE_NW - 1) atomicExch(ticket, 0);
+            break;
+        }
         const WaveTask tk = tasks[t];
         if (RING && tk.side != 0) {
             if (SLAB && tk.band)
@@ -548,7 +553,12 @@ __global__ void __launch_bounds__(WAVE_NW * 32, 1) strip_wave_x2_kernel(const Pa
         int t = 0;
         if (l == 0) t = atomicAdd(ticket, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n_tasks) break;
+        if (t >= n_tasks) {
+            // every warp of the launch draws exactly one ticket past the end: the last of those puts the counter back to
+            // zero for the next launch (no memset per pass -- a memset can queue behind a host copy on a copy engine)
+            if (l == 0 && t == n_tasks + (int)gridDim.x * WAVE_NW - 1) atomicExch(ticket, 0);
+            break;
+        }
         const WaveTask tk = tasks[t];
         if (FLAVOUR == 2) {
             if (RING && tk.side != 0) {
