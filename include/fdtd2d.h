@@ -80,8 +80,10 @@ int fdtd2d_sync(fdtd2d_sim* s);
  * plans.  Keys: "wavefront" (1), "wave_min_tiles" (-1 = automatic), "ring_min_tiles" (-1), "ring_strips" (1),
  * "wave_run_rows" (640), "auto_k12" (0), "uniform_ch" (1), "resident" (1), "resident_cfg" (0), "resident_cluster" (0),
  * "resident_trim" (-1), "tma_pair" (0), "f64_k" (0 = automatic), "fuse" (0; 1 = two k = 8 passes per launch, the second fed from L2: an
- * experiment that is bit-exact but slower on B200; -1 = on for large grids), "debug" (0).  Every setting is covered by the parity
- * tests: options change which kernel runs, never a result bit. */
+ * experiment that is bit-exact but slower on B200; -1 = on for large grids), "stage" (0; 4 / 5 = k = 12 passes on the staged
+ * wavefront, the other experiment), "debug" (0).  Every setting is covered by the parity tests: options change which kernel
+ * runs, never a result bit -- with ONE exception, "measure_skip" (0), a timing aid that leaves parts of a pass out (1 = no
+ * edge tiles, 2 = no runs / plain tiles, 4 = edge tiles not overlapped with the runs): fields are wrong while it is set. */
 int fdtd2d_set_option(fdtd2d_sim* s, const char* key, int value);
 int fdtd2d_get_option(const fdtd2d_sim* s, const char* key, int* value);
 
@@ -94,6 +96,10 @@ int fdtd2d_geometry(const fdtd2d_sim* s, int* local_rows, int* cols, int* row0, 
  * Ez[Rl][C], Hx[Rl][C-1], Hy[Rl or Rl-1][C] (Rl-1 only when the slab holds the global last row). */
 int fdtd2d_upload_state(fdtd2d_sim* s, const void* Ez, const void* Hx, const void* Hy);
 int fdtd2d_download_state(fdtd2d_sim* s, void* Ez, void* Hx, void* Hy);
+/* grid_init (main.py:79-85) on the device: all three fields zero, step index 0.  Queued on the handle's stream (never
+ * blocks a handle that was synchronised after its last step); on a slab with peer links it first waits, if need be, until
+ * the neighbours' last ghost rows have arrived, and clears the current field set only (the other set's ghost rows are the
+ * neighbours' to write). */
 int fdtd2d_zero_state(fdtd2d_sim* s);
 /* Non-blocking forms for PINNED host arrays: the copy is ordered after the stepping work issued so far and before the
  * stepping work issued afterwards, on the handle's own copy stream, and the call returns at once -- one host thread
@@ -109,7 +115,9 @@ int fdtd2d_set_coeffs(fdtd2d_sim* s, const void* ce, const void* ch, const void*
 /* eps/mu maps ((R, C) each, run dtype, batch-major) -> device forms ce = dt/(eps*dx), ch = dt/(mu*dx)
  * and the Mur coefficient from cell (0,0) with the reference's operation order, bit-identically. */
 int fdtd2d_set_materials(fdtd2d_sim* s, const void* eps, const void* mu, double dt, double dx);
-/* fdtd2d_set_materials without blocking the host (pinned eps / mu, see fdtd2d_upload_state_async). */
+/* fdtd2d_set_materials without blocking the host (pinned eps / mu, see fdtd2d_upload_state_async).  The upload, the
+ * coefficient kernels and the uniform-permeability check all run on the handle's copy stream (its next stepping work
+ * waits for them), so on a compute stream shared with other handles nothing of this call queues behind their kernels. */
 int fdtd2d_set_materials_async(fdtd2d_sim* s, const void* eps, const void* mu, double dt, double dx);
 /* Mur coefficient(s) only (one scalar per grid, run dtype).  Needed by slab handles that do not hold
  * global cell (0,0): fdtd2d_set_materials leaves their coefficient unset. */
