@@ -613,19 +613,23 @@ def run_e2e(args, wl, fd, torch, dist, rank, world, local_rank, grows, cols, inn
     one out, so the bench keeps TWO jobs in flight from ONE host thread with the library's non-blocking copies
     (fdtd2d_set_materials_async / _upload_state_async / _download_state_async): two handles (two slab groups when the
     grid is sharded), each with its own copy stream, so the copies of one job overlap the stepping kernels of the
-    other.  Sharded jobs share one compute stream, so every rank runs the kernels of the two jobs in the same order (a
-    kernel that waits for a neighbour rank's flag can then never wait for a kernel queued behind another waiting kernel).
+    other.  The jobs share one compute stream (set_stream): job after job on the device, and on slabs the same kernel order
+    on every rank (a kernel that waits for a neighbour rank's flag can then never wait for a kernel queued behind another
+    waiting kernel).
     Every job still uploads all its inputs and downloads its results inside the timed region; the figure is jobs
     finished per wall-clock second, pipeline fill and drain included."""
     batch = wl.get("batch", 0)
     inflight = 2
     if os.environ.get("BENCH_E2E_INFLIGHT"):
         inflight = max(1, int(os.environ["BENCH_E2E_INFLIGHT"]))
-    steps = max(4, min(args.steps, 8))
+    steps = max(4, min(args.steps, 16))
     sims = [make_sim(fd, wl, grows, cols, rank, world, local_rank, k, args.exchange) for _ in range(inflight)]
-    if world > 1 and not batch:
+    if not batch:
+        # One compute stream for the jobs in flight: their stepping kernels run job after job instead of pass by pass in
+        # turn, so a job is finished -- and its download and the next upload under way -- while the next one computes;
+        # on slabs it also gives every rank the same kernel order.
         for sm in sims:
-            sm.set_stream(torch.cuda.current_stream().cuda_stream)  # one compute stream: the same kernel order on every rank
+            sm.set_stream(torch.cuda.current_stream().cuda_stream)
     sim = sims[0]
     raw = [sm.sim for sm in sims]  # the Simulation under the slab / batch wrapper
     lr, hyr = sim.local_rows, sim.hy_rows

@@ -14,8 +14,7 @@ inflight, jobs, up = int(os.environ.get("INFLIGHT", 2)), int(os.environ.get("JOB
 wl = {"rows": R, "cols": C}
 sims = [bench.make_sim(fd, wl, grows, C, rank, world, lr_, k, "p2p") for _ in range(inflight)]
 cs = torch.cuda.current_stream()
-if world > 1:
-    for sm in sims: sm.set_stream(cs.cuda_stream)
+for sm in sims: sm.set_stream(cs.cuda_stream)
 raw = [sm.sim for sm in sims]
 lr, hyr = sims[0].local_rows, sims[0].hy_rows
 pin = lambda shape: torch.zeros(shape, dtype=torch.float32, pin_memory=True).numpy()
@@ -36,7 +35,7 @@ def issue(w, j):
     if up: r.set_state_async(*st)
     else: r.zero_state()
     stamp(" state queued", j)
-    strm = cs if world > 1 else torch.cuda.ExternalStream(r.cuda_stream)
+    strm = cs
     e0 = torch.cuda.Event(enable_timing=True); e0.record(strm)
     sm.step(inner, k); stamp(" step queued", j)
     e1 = torch.cuda.Event(enable_timing=True); e1.record(strm)
