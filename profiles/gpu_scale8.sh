@@ -4,7 +4,7 @@
 N=${1:-8}
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/scale_$N.json 2> gpurun_out/scale_$N.err; echo "p2p rc=$?"; tail -3 gpurun_out/scale_$N.err
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps ${STEPS:-5} --warmup ${WARMUP:-3} > gpurun_out/scale_$N.json 2> gpurun_out/scale_$N.err; echo "p2p rc=$?"; tail -3 gpurun_out/scale_$N.err
 [ "${2:-nccl}" = nccl ] && timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --steps 5 --warmup 3 --exchange nccl --no-extras --no-e2e > gpurun_out/scale_${N}_nccl.json 2> gpurun_out/scale_${N}_nccl.err; echo "nccl rc=$?"
 python - <<PY
 import json
