@@ -22,6 +22,7 @@
 #include "tile_tma.cuh"
 #include "tile_generic.cuh"
 #include "grid_resident.cuh"
+#include "grid_resident_x2.cuh"
 #include "strip_wave.cuh"
 #include "strip_stage.cuh"
 #include "grid_small.cuh"
@@ -1353,7 +1354,8 @@ static int launch_fused_pair(fdtd2d_sim* s) {
 struct ResCfg {
     int MR, NW;
 };
-static const ResCfg kResCfgs[] = {{3, 16}, {4, 12}, {2, 16}, {4, 8}, {3, 12}};
+static const ResCfg kResCfgs[] = {{3, 16}, {4, 12}, {2, 16}, {4, 8}, {3, 12}, {RX_MR, RX_NW}};
+constexpr int RES_CFG_X2 = 5;  // the packed kernel of grid_resident_x2.cuh (6 rows per thread x 8 warps)
 constexpr int N_RES_CFG = sizeof(kResCfgs) / sizeof(kResCfgs[0]);
 
 static int resident_cfg(const fdtd2d_sim* s) {
@@ -1377,6 +1379,35 @@ static bool resident_eligible(fdtd2d_sim* s) {
         if (v > RES_MAX_SLOTS) return false;
     int n = (s->Rg + band - 1) / band;
     if (s->opt.resident_cluster >= n && s->opt.resident_cluster <= 8) n = s->opt.resident_cluster;  // tuning knob: more, thinner bands per grid
+    if (rcfg == RES_CFG_X2) {
+        // Bands of the packed kernel: first | (n-2) x rpc | last with rpc and last multiples of 6 (the six bottom ring rows are
+        // ONE warp's rows; the six top ring rows always are) and the first band whatever is left (6..48).  One band holds both
+        // rings only when it has twelve rows or more and a multiple of six.
+        if (n == 1 && (s->Rg % mr != 0 || s->Rg < 2 * mr)) n = 2;
+        int rpc = 0, edge = 0, last = 0;
+        if (n == 1) {
+            rpc = edge = last = s->Rg;
+        } else {
+            bool ok = false;
+            for (int r6 = mr * ((s->Rg + mr * n - 1) / (mr * n)); r6 <= band && !ok; r6 += mr) {
+                const int rem = s->Rg - (n - 2) * r6;  // rows of the first and the last band together
+                if (rem < 2 * mr) break;
+                const int la_min = std::max(mr, (rem - band + mr - 1) / mr * mr), la_max = std::min(band, (rem - mr) / mr * mr);
+                if (la_min > la_max) continue;
+                rpc = r6;
+                last = std::min(std::max(rem / 2 / mr * mr, la_min), la_max);
+                edge = rem - last;
+                ok = true;
+            }
+            if (!ok) return false;
+        }
+        s->resident_cfg = rcfg;
+        s->resident_cluster = n;
+        s->resident_rpc = rpc;
+        s->resident_edge = edge;
+        s->resident_ok = 1;
+        return true;
+    }
     // The first and last CTA of a cluster also run the top / bottom boundary pass: give them `trim` rows fewer
     // than the middle ones when the grid leaves room (rows: edge | (n-2) x rpc | what is left, at most edge).
     int trim = 4 * mr;
@@ -1443,7 +1474,53 @@ template <int MR, int NW> static int launch_resident_t(fdtd2d_sim* s, int n_step
     return 0;
 }
 
+// the packed kernel (grid_resident_x2.cuh): uniform dt/(mu*dx) as an argument, or the map
+template <bool UCH> static int launch_resident_x2_t(fdtd2d_sim* s, int n_steps) {
+    static bool done_[MAX_DEVICES] = {};
+    bool& done = done_[s->device % MAX_DEVICES];
+    const size_t smem = resident_x2_smem_floats() * sizeof(float);
+    if (!done) {
+        CUDA_TRY(cudaFuncSetAttribute(grid_resident_x2_kernel<UCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        done = true;
+    }
+    TilePlan tp;
+    tp.k = n_steps;
+    tp.CH = s->resident_rpc;
+    tp.CW = s->resident_edge;
+    PassParams<float> p;
+    fill_params(s, tp, FDTD2D_PHASE_H | FDTD2D_PHASE_E | FDTD2D_PHASE_SRC, &p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(s->batch * s->resident_cluster));
+    cfg.blockDim = dim3(RX_NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)s->resident_cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (s->opt.debug) {
+        int nc = -1;
+        cudaOccupancyMaxActiveClusters(&nc, grid_resident_x2_kernel<UCH>, &cfg);
+        fprintf(stderr, "[fdtd2d] resident x2: %d grids x cluster %d (%d | %d rows per CTA), uniform ch %d, %zu B smem, max active clusters %d\n",
+                s->batch, s->resident_cluster, s->resident_edge, s->resident_rpc, (int)UCH, smem, nc);
+    }
+    const float chu = (float)s->ch_value;
+    const unsigned long long negzero = 0x8000000080000000ull;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_resident_x2_kernel<UCH>, p, chu, negzero));
+    s->launches += 1;
+    s->passes += 1;
+    s->cur ^= 1;
+    return 0;
+}
+
 static int launch_resident(fdtd2d_sim* s, int n_steps) {
+    if (s->resident_cfg == RES_CFG_X2) {
+        if (int rc = check_ch_uniform(s)) return rc;
+        return s->ch_uniform == 1 ? launch_resident_x2_t<true>(s, n_steps) : launch_resident_x2_t<false>(s, n_steps);
+    }
     switch (s->resident_cfg) {
         case 1: return launch_resident_t<4, 12>(s, n_steps);
         case 2: return launch_resident_t<2, 16>(s, n_steps);
@@ -2266,7 +2343,8 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
             }
         } else {
             // fp64: 8 levels where the wavefront kernel takes the grid or where the k = 8 tiles fit one wave of CTAs (small
-            // grids are bound by launch and barrier latency: 200^2 runs 275k steps/s at k = 8, 217k at k = 4); otherwise 4
+            // grids are bound by launch and barrier latency: 200^2 runs 275k steps/s at k = 8, 217k at k = 4 -- and 12 steps per
+            // launch where even those tiles fit one wave); otherwise 4
             k = s->opt.f64_k > 0 ? std::min(s->opt.f64_k, FDTD2D_MAX_K) : 8;
             if (s->opt.f64_k <= 0) {
                 if (s->variant == 1) {
@@ -2275,7 +2353,16 @@ int fdtd2d_step(fdtd2d_sim* s, int n_steps, int k_temporal) {
                     PassPlan& pl = s->hybrid[8];
                     if (!pl.valid)
                         if (int rc = classify_tiles(s, 8, &pl)) return rc;
-                    if (!pl.d_wave && pl.n_edge > sm_count(s)) k = 4;
+                    if (!pl.d_wave) {
+                        if (pl.n_edge > sm_count(s)) {
+                            k = 4;
+                        } else if (!slab && n_steps >= FDTD2D_MAX_K) {  // still one wave of CTAs at 12 steps per launch? (200^2: 307k steps/s)
+                            PassPlan& p12 = s->hybrid[FDTD2D_MAX_K];
+                            if (!p12.valid)
+                                if (int rc = classify_tiles(s, FDTD2D_MAX_K, &p12)) return rc;
+                            if (!p12.d_wave && p12.n_edge <= sm_count(s)) k = FDTD2D_MAX_K;
+                        }
+                    }
                 }
             }
         }

@@ -40,6 +40,10 @@
 #include "tile_edge.cuh"
 #include "tile_tma.cuh"
 
+#ifndef FDTD2D_RES_DIAG
+#define FDTD2D_RES_DIAG 0  // MEASUREMENT AID (wrong results): 1 = no top / bottom pass, 2 = no ring work at all
+#endif
+
 namespace fdtd2d {
 
 constexpr int RES_TW = 256;         // columns per CTA (two 128-column halves per warp row)
@@ -278,6 +282,7 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
     float* const s2R = F + keep(s2r);
     // registers -> S0 / S1 frames (delta = 0 / DELTA)
     auto park = [&](int delta) {
+        if (FDTD2D_RES_DIAG >= 2) return;
 #pragma unroll
         for (int r = 0; r < MR; ++r) {
             if (z0) store4(zp0 + delta + r * ZW, e[r][0]);
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
     const uint32_t dn_rEz = map_to_rank(smem_u32(rEz), dn_rank), dn_barA = map_to_rank(smem_u32(&barA[0]), dn_rank);
     const bool edge_dn = (w == wl) && has_below;  // my last row needs the Ez row of the CTA below
     const bool edge_up = (w == 0) && has_above;   // my first row needs the Hx row of the CTA above
-    const bool cta_tb = isTop || isBot;
+    const bool cta_tb = FDTD2D_RES_DIAG >= 1 ? false : (isTop || isBot);
     const bool warp_on = li0 < nrows;  // warps past the end of the band only help with the top / bottom pass
     {  // rows nobody publishes are still read as a neighbour row by the last active warp: keep them finite
         const float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -484,12 +489,12 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
             // ---- S2: Mur left/right (main.py:33-41) of my warp's own rows, one lane per ring cell; all cells are
             // read before any is written (the reference's k order reads column k+1 before overwriting it) ------
             float vl = 0.0f, vr = 0.0f;
-            if (s2act) {
+            if (s2act && FDTD2D_RES_DIAG < 2) {
                 vl = add_rn(s2L[1 - DELTA], mul_rn(coef, sub_rn(s2L[1], s2L[-DELTA])));
                 vr = add_rn(s2R[-1 - DELTA], mul_rn(coef, sub_rn(s2R[-1], s2R[-DELTA])));
             }
             __syncwarp();
-            if (s2act) *s2L = vl, *s2R = vr;
+            if (s2act && FDTD2D_RES_DIAG < 2) *s2L = vl, *s2R = vr;
         }
         RES_STAMP(5)
         // ---- top / bottom rows: S3, S4 in one pass over their frames (all threads of the CTA) ----------------
@@ -512,7 +517,7 @@ __global__ void __launch_bounds__(NW * 32, 1) grid_resident_kernel(const PassPar
             __syncwarp();
         RES_STAMP(7)
         // ---- finished ring -> registers ---------------------------------------------------------------------
-        if (warp_on) {
+        if (warp_on && FDTD2D_RES_DIAG < 2) {
 #pragma unroll
             for (int r = 0; r < MR; ++r) {
                 if (z0) load4(zp0 + DELTA + r * ZW, e[r][0]);

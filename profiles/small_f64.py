@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import fdtd2d_b200 as fd
 for R in (200, 1000):
-    for k in (4, 6, 8):
+    for k in (8, 9, 10, 11, 12):
         with fd.Simulation(R, R, np.float64, dt=5e-14, dx=1e-4) as sim:
             sim.set_stream(torch.cuda.current_stream().cuda_stream)
             eps, mu = fd.material_init(None, R, R)

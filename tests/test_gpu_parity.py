@@ -78,7 +78,7 @@ def test_update_functions_vs_reference_golden(fd, golden_dir, dtype, shape):
 # the reference demo (fdtd.py defaults), every k
 # --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
-@pytest.mark.parametrize("k", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 4, 8, 12])  # 0: the library's choice (fp32: cluster-resident; fp64: 12 steps per launch)
 def test_demo200_vs_reference_golden(fd, golden_dir, dtype, k):
     g = np.load(os.path.join(golden_dir, f"demo200_vacuum_{dtype}.npz"))
     eps, mu = fd.material_init(None, 200, 200)

@@ -48,19 +48,28 @@ def _problem(rng, R, C, scale=1e-3):
 SHAPES = [(16, 16), (17, 33), (48, 256), (49, 255), (64, 256), (65, 255), (100, 128), (128, 129), (129, 131), (130, 136),
           (200, 200), (256, 256), (255, 140), (260, 64), (300, 250), (384, 256), (383, 17), (37, 53), (96, 130), (72, 100)]
 # (kernel shape, grid shape): shape 0 = 3 rows per thread x 16 warps (48-row bands, the default), 1 = 4 x 12 (48 rows),
-# 2 = 2 x 16 (32 rows), 3 = 4 x 8 (32 rows), 4 = 3 x 12 (36 rows); a cluster has at most 8 bands
+# 2 = 2 x 16 (32 rows), 3 = 4 x 8 (32 rows), 4 = 3 x 12 (36 rows); a cluster has at most 8 bands;
+# 5 = the packed kernel of grid_resident_x2.cuh (6 x 8, 48 rows: first band of any size, the others multiples of six)
 SMALL = [(256, 256), (33, 40), (250, 141), (100, 128), (17, 33), (200, 200)]
-CASES = [(0, s) for s in SHAPES] + [(1, s) for s in SHAPES[::2]] + [(c, s) for c in (2, 3, 4) for s in SMALL]
+X2_MORE = [(18, 40), (24, 64), (30, 31), (47, 47), (54, 250), (97, 256), (101, 19), (144, 144), (250, 141), (33, 40)]
+CASES = ([(0, s) for s in SHAPES] + [(1, s) for s in SHAPES[::2]] + [(c, s) for c in (2, 3, 4) for s in SMALL]
+         + [(5, s) for s in SHAPES + X2_MORE])
 
 
-@pytest.mark.parametrize("rcfg,shape", CASES)
+# (the packed kernel takes dt/(mu*dx) as a kernel argument when it is uniform: both forms)
+CASES = [(c, s, False) for c, s in CASES] + [(5, s, True) for s in SHAPES[::2] + X2_MORE[::2]]
+
+
+@pytest.mark.parametrize("rcfg,shape,uniform_mu", CASES)
 @pytest.mark.parametrize("nsteps", [1, 2, 37])
-def test_resident_vs_oracle(fd, oracle, rcfg, shape, nsteps, monkeypatch):
+def test_resident_vs_oracle(fd, oracle, rcfg, shape, uniform_mu, nsteps, monkeypatch):
     c_oracle, npo = oracle
     R, C = shape
     monkeypatch.setenv("FDTD2D_RESIDENT_CFG", str(rcfg))
     rng = np.random.default_rng(R * 1009 + C * 13 + nsteps)
     eps, mu, Ez, Hx, Hy = _problem(rng, R, C)
+    if uniform_mu:
+        mu[:] = mu[0, 0]
     ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(np.float32))
     # sources in the interior, inside every ring frame and on the corner cells
     cells = [(R // 2, C // 2), (R // 2, C // 2 + 1), (7, 9), (R - 3, C - 2), (0, 0), (R - 1, 0), (3, C - 1), (R // 3, 2),
@@ -79,7 +88,8 @@ def test_resident_vs_oracle(fd, oracle, rcfg, shape, nsteps, monkeypatch):
         sim.set_probes(probes, nsteps)
         before = sim.launch_count
         sim.step(nsteps)
-        assert sim.launch_count == before + 1  # the whole run is one launch
+        # the whole run is one launch (the packed kernel asks once whether dt/(mu*dx) is uniform: one small kernel more)
+        assert sim.launch_count == before + (2 if rcfg == 5 else 1)
         gEz, gHx, gHy = sim.state()
         gtrace = sim.read_probes()
     what = f"{R}x{C} n={nsteps}"
@@ -89,11 +99,13 @@ def test_resident_vs_oracle(fd, oracle, rcfg, shape, nsteps, monkeypatch):
     assert_bits(gHy, oHy, "Hy " + what)
 
 
-def test_resident_batched_dataset_like(fd, oracle):
+@pytest.mark.parametrize("rcfg", [0, 5])
+def test_resident_batched_dataset_like(fd, oracle, rcfg, monkeypatch):
     """Many independent 256 x 256 grids in one launch (BASELINE configs[4]): per-grid binary media, point and
     line sources with per-grid waveforms, probes; a sample of the grids is checked against the oracle and
     every grid against the tiled path."""
     c_oracle, npo = oracle
+    monkeypatch.setenv("FDTD2D_RESIDENT_CFG", str(rcfg))
     B, R, C, nsteps = 40, 256, 256, 120
     rng = np.random.default_rng(8)
     eps = np.where(rng.random((B, R, C)) > 0.5, 5.0, 1.0).astype(np.float32) * np.float32(8.85418e-12)
@@ -135,8 +147,10 @@ def test_resident_batched_dataset_like(fd, oracle):
         assert_bits(gtrace[:, B + b], otr[:, 1], f"probe B grid {b}")
 
 
-def test_resident_demo_golden_and_pieces(fd, golden_dir):
+@pytest.mark.parametrize("rcfg", [0, 5])
+def test_resident_demo_golden_and_pieces(fd, golden_dir, rcfg, monkeypatch):
     """The reference demo (fdtd.py defaults, fp32) in one launch and in pieces, against the reference's output."""
+    monkeypatch.setenv("FDTD2D_RESIDENT_CFG", str(rcfg))
     g = np.load(os.path.join(golden_dir, "demo200_vacuum_float32.npz"))
     eps, mu = fd.material_init(None, 200, 200)
     for plan in ([1000], [1, 2, 333, 64, 600]):
@@ -155,8 +169,9 @@ def test_resident_demo_golden_and_pieces(fd, golden_dir):
         assert_bits(Hy, g["Hy"], "Hy")
 
 
+@pytest.mark.parametrize("rcfg", [0, 5])
 @pytest.mark.parametrize("cluster", [3, 4, 5, 7, 8])
-def test_resident_cluster_size_knob(fd, oracle, cluster, monkeypatch):
+def test_resident_cluster_size_knob(fd, oracle, cluster, rcfg, monkeypatch):
     """More, thinner bands per grid (FDTD2D_RESIDENT_CLUSTER) must not change a bit."""
     c_oracle, npo = oracle
     R, C, nsteps = 120, 200, 33
@@ -167,6 +182,7 @@ def test_resident_cluster_size_knob(fd, oracle, cluster, monkeypatch):
     oEz, oHx, oHy = Ez.copy(), Hx.copy(), Hy.copy()
     otrace = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, nsteps, amp, [(60, 100)], [(61, 100), (0, 0)])
     monkeypatch.setenv("FDTD2D_RESIDENT_CLUSTER", str(cluster))
+    monkeypatch.setenv("FDTD2D_RESIDENT_CFG", str(rcfg))
     with fd.Simulation(R, C, np.float32, dt=DT, dx=DX) as sim:
         sim.set_kernel_variant(4)
         sim.set_coefficients(ce, ch, coef)
