@@ -1355,7 +1355,7 @@ struct ResCfg {
     int MR, NW;
 };
 static const ResCfg kResCfgs[] = {{3, 16}, {4, 12}, {2, 16}, {4, 8}, {3, 12}, {RX_MR, RX_NW}};
-constexpr int RES_CFG_X2 = 5;  // the packed kernel of grid_resident_x2.cuh (6 rows per thread x 8 warps)
+constexpr int RES_CFG_X2 = 5;  // the packed kernel of grid_resident_x2.cuh (6 rows x 4 columns per thread, 8 row blocks x 2 column halves)
 constexpr int N_RES_CFG = sizeof(kResCfgs) / sizeof(kResCfgs[0]);
 
 static int resident_cfg(const fdtd2d_sim* s) {
@@ -1368,7 +1368,10 @@ static bool resident_eligible(fdtd2d_sim* s) {
     if (s->resident_ok >= 0) return s->resident_ok != 0;
     s->resident_ok = 0;
     if (s->dtype != FDTD2D_F32 || s->has_top_nb || s->has_bot_nb) return false;
-    const int rcfg = resident_cfg(s), mr = kResCfgs[rcfg].MR, band = mr * kResCfgs[rcfg].NW;
+    int rcfg = resident_cfg(s);
+    if (rcfg == RES_CFG_X2 && s->C > RX_HW && (((s->C - 6) >> 2) << 2) < RX_HW) rcfg = 0;  // right ring astride the two column halves
+    if (rcfg == RES_CFG_X2 && s->Rg > 8 * RX_TH) rcfg = 0;
+    const int mr = kResCfgs[rcfg].MR, band = rcfg == RES_CFG_X2 ? RX_TH : mr * kResCfgs[rcfg].NW;
     if (s->C < 16 || s->C > RES_TW || s->Rg < 16 || s->Rg > 8 * band) return false;
     if (!s->opt.resident) return false;
     // every source / probe cell may need a 4-cell slot in its CTA's slot frame
@@ -1475,12 +1478,12 @@ template <int MR, int NW> static int launch_resident_t(fdtd2d_sim* s, int n_step
 }
 
 // the packed kernel (grid_resident_x2.cuh): uniform dt/(mu*dx) as an argument, or the map
-template <bool UCH> static int launch_resident_x2_t(fdtd2d_sim* s, int n_steps) {
+template <bool UCH, int RL> static int launch_resident_x2_t(fdtd2d_sim* s, int n_steps) {
     static bool done_[MAX_DEVICES] = {};
     bool& done = done_[s->device % MAX_DEVICES];
     const size_t smem = resident_x2_smem_floats() * sizeof(float);
     if (!done) {
-        CUDA_TRY(cudaFuncSetAttribute(grid_resident_x2_kernel<UCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(grid_resident_x2_kernel<UCH, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         done = true;
     }
     TilePlan tp;
@@ -1503,13 +1506,13 @@ template <bool UCH> static int launch_resident_x2_t(fdtd2d_sim* s, int n_steps) 
     cfg.numAttrs = 1;
     if (s->opt.debug) {
         int nc = -1;
-        cudaOccupancyMaxActiveClusters(&nc, grid_resident_x2_kernel<UCH>, &cfg);
+        cudaOccupancyMaxActiveClusters(&nc, grid_resident_x2_kernel<UCH, RL>, &cfg);
         fprintf(stderr, "[fdtd2d] resident x2: %d grids x cluster %d (%d | %d rows per CTA), uniform ch %d, %zu B smem, max active clusters %d\n",
                 s->batch, s->resident_cluster, s->resident_edge, s->resident_rpc, (int)UCH, smem, nc);
     }
     const float chu = (float)s->ch_value;
     const unsigned long long negzero = 0x8000000080000000ull;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_resident_x2_kernel<UCH>, p, chu, negzero));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_resident_x2_kernel<UCH, RL>, p, chu, negzero));
     s->launches += 1;
     s->passes += 1;
     s->cur ^= 1;
@@ -1519,7 +1522,17 @@ template <bool UCH> static int launch_resident_x2_t(fdtd2d_sim* s, int n_steps) 
 static int launch_resident(fdtd2d_sim* s, int n_steps) {
     if (s->resident_cfg == RES_CFG_X2) {
         if (int rc = check_ch_uniform(s)) return rc;
-        return s->ch_uniform == 1 ? launch_resident_x2_t<true>(s, n_steps) : launch_resident_x2_t<false>(s, n_steps);
+        // the row inside a row block at which the first band ends is a template parameter (see the kernel)
+        const int rl = s->resident_cluster > 1 ? (s->resident_edge - 1) % RX_MR : RX_MR - 1;
+        const bool uch = s->ch_uniform == 1;
+        switch (rl) {
+            case 0: return uch ? launch_resident_x2_t<true, 0>(s, n_steps) : launch_resident_x2_t<false, 0>(s, n_steps);
+            case 1: return uch ? launch_resident_x2_t<true, 1>(s, n_steps) : launch_resident_x2_t<false, 1>(s, n_steps);
+            case 2: return uch ? launch_resident_x2_t<true, 2>(s, n_steps) : launch_resident_x2_t<false, 2>(s, n_steps);
+            case 3: return uch ? launch_resident_x2_t<true, 3>(s, n_steps) : launch_resident_x2_t<false, 3>(s, n_steps);
+            case 4: return uch ? launch_resident_x2_t<true, 4>(s, n_steps) : launch_resident_x2_t<false, 4>(s, n_steps);
+            default: return uch ? launch_resident_x2_t<true, 5>(s, n_steps) : launch_resident_x2_t<false, 5>(s, n_steps);
+        }
     }
     switch (s->resident_cfg) {
         case 1: return launch_resident_t<4, 12>(s, n_steps);

@@ -8,7 +8,7 @@ if os.environ.get("LIB"):
     L.LIB_PATH = os.path.abspath(os.environ["LIB"])
 B, R, C, n = int(os.environ.get("B", 1)), 256, 256, 1000
 x2 = os.environ.get("FDTD2D_RESIDENT_CFG", "0") == "5"
-NW = 8 if x2 else 16
+NW = 16
 with fd.Simulation(R, C, np.float32, dt=5e-14, dx=1e-3, batch=B) as sim:
     sim.set_kernel_variant(4)
     sim.set_materials_random(1, 4.0)
