@@ -1348,9 +1348,11 @@ static int launch_fused_pair(fdtd2d_sim* s) {
 }
 
 // ---- cluster-resident path (grid_resident.cuh) ---------------------------------------------------
-// Shapes of the cluster-resident kernel: MR rows per thread x NW warps -> a CTA holds MR*NW rows x 256 columns.
-// 3 x 16 is the measured best on B200 for 256^2 grids (profiles/); the others are kept selectable for tuning
-// (FDTD2D_RESIDENT_CFG) and are covered by the parity tests.
+// Shapes of the cluster-resident kernels.  0..4: grid_resident.cuh, MR rows per thread x NW warps -> a CTA holds MR*NW rows x
+// 256 columns (3 x 16 was the best of them on B200 for 256^2 grids); 5 (the default): the packed kernel of
+// grid_resident_x2.cuh, 6 rows x 4 columns per thread, 8 row blocks x 2 column halves -- 686 against 649 Gcell/s on
+// BASELINE configs[4], 563k against 435k steps/s on one 200^2 grid.  All are selectable (option resident_cfg) and covered
+// by the parity tests; grids the packed kernel does not take (right ring astride column 128, more than 384 rows) use 0.
 struct ResCfg {
     int MR, NW;
 };

@@ -277,7 +277,6 @@ __global__ void __launch_bounds__(RX_NW * 32, 1) grid_resident_x2_kernel(const P
     const bool cact = tbmode != 0 && l < RING * RING;
     const bool cl_on = cact && wc == 0, cr_on = cact && wc == wcR;
     const int cd = l / RING, cj = l % RING;
-    auto cfr = [&](int d) { return (tbmode == 1 ? d : MR - 1 - d) * ZW; };
     float* const cF = F + oLR + li0 * ZW;  // S0 frame of my first row
 
     auto park = [&](int delta) {
@@ -341,32 +340,28 @@ __global__ void __launch_bounds__(RX_NW * 32, 1) grid_resident_x2_kernel(const P
         t[0] = add2(e[r][0], mul2(curl0, c[0], negzero));
         t[1] = add2(e[r][1], mul2(curl1, c[1], negzero));
     };
-    // Ez update of the warps that hold the top (TOP) or bottom ring rows: the rows are walked towards the edge (top:
-    // r = 5..0, bottom: r = 0..5), so that when row r has its interior update S1[r] the row nearer the edge, rn, still holds
-    // Ez_prev; main.py:43-51 for row rn is S0[r] + coef * (S1[r] - S0[rn]) (on the ring columns S2 instead of S1: those cells
-    // are corner cells and are overwritten through the frame).  S1 of the ring groups is parked on the way (S2 and the
-    // corners need it).
+    // Ez update of the warps that hold the top (TOP) or bottom ring rows.  main.py:43-51 for row r (r = depth from the edge,
+    // 0..4) is S0[r+1] + coef * (S1[r+1] - S0[r]): the rows are walked AWAY from the edge with the interior update of the next
+    // row formed one row ahead (T), so row r's result goes straight into its registers while row r + 1 still holds Ez_prev.
+    // (On the ring columns the reference uses S2 instead of S1: those cells are corner cells and are overwritten through the
+    // frame.)  S1 of the ring groups is parked on the way (S2 and the corners need it); the edge row itself has no
+    // interior update (its S1 is never read).
     auto e_rows_tb = [&](auto top_c) {
         constexpr bool TOP = decltype(top_c)::value;
-        u64 pend[2] = {0, 0};
+        u64 t[2];
 #pragma unroll
-        for (int i = 0; i < MR; ++i) {
-            const int r = TOP ? MR - 1 - i : i;  // the row whose interior update is formed
-            const int rn = TOP ? r - 1 : r + 1;  // the row nearer the edge
-            u64 t[2], t3[2] = {0, 0};
-            if (r == 0)
-                e_row(r, hxa, t);
+        for (int d = 0; d + 1 < MR; ++d) {
+            const int r = TOP ? d : MR - 1 - d;          // the row that gets its final value
+            const int rx = TOP ? d + 1 : MR - 2 - d;     // the next row from the edge: its interior update is formed now
+            if (rx == 0)
+                e_row(rx, hxa, t);
             else
-                e_row(r, hx[r > 0 ? r - 1 : 0], t);
-            if (zg) store22(zp + DELTA + r * ZW, t);
-            if (i < MR - 1) {
-                const int rc = rn < 0 ? 0 : (rn >= MR ? MR - 1 : rn);
-                t3[0] = add2(e[r][0], mul2(coef2, sub2(t[0], e[rc][0]), negzero));
-                t3[1] = add2(e[r][1], mul2(coef2, sub2(t[1], e[rc][1]), negzero));
-            }
-            e[r][0] = i == 0 ? t[0] : pend[0], e[r][1] = i == 0 ? t[1] : pend[1];
-            pend[0] = t3[0], pend[1] = t3[1];
+                e_row(rx, hx[rx > 0 ? rx - 1 : 0], t);
+            if (zg) store22(zp + DELTA + rx * ZW, t);
+            e[r][0] = add2(e[rx][0], mul2(coef2, sub2(t[0], e[r][0]), negzero));
+            e[r][1] = add2(e[rx][1], mul2(coef2, sub2(t[1], e[r][1]), negzero));
         }
+        e[TOP ? MR - 1 : 0][0] = t[0], e[TOP ? MR - 1 : 0][1] = t[1];  // the sixth row: interior update only
     };
     cluster_sync_all();  // every CTA's barriers are initialised before anyone signals them
 
@@ -390,6 +385,24 @@ __global__ void __launch_bounds__(RX_NW * 32, 1) grid_resident_x2_kernel(const P
         const int tb = GEN ? tbmode : (int)((ROLE >> 3) & 3u);
         const int hr = GEN ? hrows : (ghost ? RL + 1 : (tb == 2 ? MR - 1 : MR));  // rows whose H is updated
         const bool uprow = GEN ? has_up_row : tb != 1;                            // there is a row above my rows
+        // the corner lanes' frame offsets (from cF) and index tests do not change from step to step: side 0 = left, 1 = right;
+        // value A = after-S3 value of (depth d, column next to mine towards the middle), value B = of (depth d + 1, my column)
+        int cA0[2] = {0, 0}, cA1[2] = {0, 0}, cB0[2] = {0, 0}, cB1[2] = {0, 0}, cW[2] = {0, 0};
+        bool cAs3[2] = {false, false}, cBs3[2] = {false, false}, con[2] = {false, false};
+        if (tb) {
+            auto fro = [&](int d) { return (tb == 1 ? d : MR - 1 - d) * ZW; };
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+                const int gmine = sd == 0 ? cj : C - 1 - cj, gnext = sd == 0 ? cj + 1 : C - 2 - cj;
+                const int fmine = sd == 0 ? cj : LW + gmine - cR0, fnext = sd == 0 ? cj + 1 : LW + gnext - cR0;
+                con[sd] = sd == 0 ? cl_on : cr_on;
+                cA0[sd] = fro(cd) + fnext, cA1[sd] = fro(cd + 1) + fnext;                      // rows d, d + 1 in the next column
+                cB0[sd] = fro(cd + 1) + fmine, cB1[sd] = fro(cd + 2 < MR ? cd + 2 : MR - 1) + fmine;  // rows d + 1, d + 2 in my column
+                cAs3[sd] = gnext >= 1 && gnext <= C - 2;                                      // (d <= 4 always)
+                cBs3[sd] = cd + 1 <= 4 && gmine >= 1 && gmine <= C - 2;
+                cW[sd] = DELTA + fro(cd) + fmine;
+            }
+        }
 #pragma unroll 1
         for (int s = 0; s < n_steps; ++s) {
             const int par = s & 1;
@@ -467,22 +480,25 @@ __global__ void __launch_bounds__(RX_NW * 32, 1) grid_resident_x2_kernel(const P
                 park(DELTA);
             }
             RX_STAMP(4)
-            // ---- source / probe cells outside the frames go through their slot ---------------------------------
+            // ---- source / probe cells outside the frames: the source add in registers (fdtd.py:34: float64 sum, then cast),
+            // the result also goes to the cell's slot, where the probes are sampled.  (Fetching the amplitudes a step ahead
+            // with cp.async was measured: slower -- sixteen steps share a cache line.)
             if (spmask) {
+                const long long step = p.step0 + s;
 #pragma unroll
                 for (int r = 0; r < MR; ++r)
                     if (spmask >> r & 1u) {
                         const int sl = slot_tbl[(li0 + r) * (TW / 4) + (cg >> 2)];
-                        float* f = F + oSlot + sl * 4;
-                        store22(f, e[r]);
-                        const long long step = p.step0 + s;
-                        if (step < p.amp_steps)
-                            for (int q = 0; q < 4; ++q) {  // source add (fdtd.py:34): float64 sum, then cast.  (Fetching the
-                                // amplitudes a step ahead with cp.async was measured: slower -- sixteen steps share a cache line.)
-                                const int wv = slotW[sl * 4 + q];
-                                if (wv >= 0) f[q] = add_source(f[q], p.amp[(long long)wv * p.amp_steps + step]);
-                            }
-                        load22(f, e[r]);
+                        if (step < p.amp_steps) {
+                            const int4 wv = *reinterpret_cast<const int4*>(slotW + sl * 4);
+                            float v[4] = {lo2(e[r][0]), hi2(e[r][0]), lo2(e[r][1]), hi2(e[r][1])};
+                            if (wv.x >= 0) v[0] = add_source(v[0], p.amp[(long long)wv.x * p.amp_steps + step]);
+                            if (wv.y >= 0) v[1] = add_source(v[1], p.amp[(long long)wv.y * p.amp_steps + step]);
+                            if (wv.z >= 0) v[2] = add_source(v[2], p.amp[(long long)wv.z * p.amp_steps + step]);
+                            if (wv.w >= 0) v[3] = add_source(v[3], p.amp[(long long)wv.w * p.amp_steps + step]);
+                            e[r][0] = pack2(v[0], v[1]), e[r][1] = pack2(v[2], v[3]);
+                        }
+                        store22(F + oSlot + sl * 4, e[r]);
                     }
             }
             __syncwarp();
@@ -500,18 +516,15 @@ __global__ void __launch_bounds__(RX_NW * 32, 1) grid_resident_x2_kernel(const P
             if (tb) {
                 // ---- corners: Jacobi over values after S3 (every read is of a not-yet-processed cell) --------------
                 __syncwarp();
-                if (cact) {
-                    // value after main.py:43-51 of the frame cell (depth d, frame column fc = global column gc)
-                    auto S3v = [&](int d, int fc, int gc) -> float {
-                        const float s2 = cF[DELTA + cfr(d) + fc];
-                        if (d <= 4 && gc >= 1 && gc <= C - 2)
-                            return add_rn(cF[cfr(d + 1) + fc], mul_rn(coef, sub_rn(cF[DELTA + cfr(d + 1) + fc], cF[cfr(d) + fc])));
-                        return s2;
-                    };
-                    const int gr = C - 1 - cj, fr = LW + gr - cR0;
-                    if (cl_on) vl = mul_rn(add_rn(S3v(cd, cj + 1, cj + 1), S3v(cd + 1, cj, cj)), 0.5f);  // == sum / 2 exactly
-                    if (cr_on) vr = mul_rn(add_rn(S3v(cd, fr - 1, gr - 1), S3v(cd + 1, fr, gr)), 0.5f);
-                }
+                float cv[2] = {0.0f, 0.0f};
+#pragma unroll
+                for (int sd = 0; sd < 2; ++sd)
+                    if (con[sd]) {
+                        // value after main.py:43-51 of a frame cell: S0[d+1] + coef * (S2[d+1] - S0[d]) where that applies, else S2
+                        const float a = cAs3[sd] ? add_rn(cF[cA1[sd]], mul_rn(coef, sub_rn(cF[DELTA + cA1[sd]], cF[cA0[sd]]))) : cF[DELTA + cA0[sd]];
+                        const float bq = cBs3[sd] ? add_rn(cF[cB1[sd]], mul_rn(coef, sub_rn(cF[DELTA + cB1[sd]], cF[cB0[sd]]))) : cF[DELTA + cB0[sd]];
+                        cv[sd] = mul_rn(add_rn(a, bq), 0.5f);  // == sum / 2 exactly
+                    }
                 __syncwarp();
                 // the rows S3 finished in registers -> frame (columns of the ring groups that are not corner cells)
                 if (zg) {
@@ -520,8 +533,8 @@ __global__ void __launch_bounds__(RX_NW * 32, 1) grid_resident_x2_kernel(const P
                         if (tb == 1 ? r < MR - 1 : r > 0) store22(zp + DELTA + r * ZW, e[r]);
                 }
                 __syncwarp();
-                if (cl_on) cF[DELTA + cfr(cd) + cj] = vl;
-                if (cr_on) cF[DELTA + cfr(cd) + LW + (C - 1 - cj) - cR0] = vr;
+                if (con[0]) cF[cW[0]] = cv[0];
+                if (con[1]) cF[cW[1]] = cv[1];
             }
             RX_STAMP(6)
             if (n_rsrc) {  // sources inside a ring frame are added once the frame is finished (by the cells' own warp)

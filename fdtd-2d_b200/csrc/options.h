@@ -19,7 +19,7 @@ struct Options {
     int auto_k12 = 0;          // k_temporal = 0 picks the 12-level wavefront when it exists (uniform permeability)
     int uniform_ch = 1;        // pass dt/(mu*dx) as a scalar when the map is uniform
     int resident = 1;          // cluster-resident kernel for small fp32 grids
-    int resident_cfg = 0;      // its shape (index into kResCfgs)
+    int resident_cfg = 5;      // its shape (index into kResCfgs): 5 = the packed kernel (grid_resident_x2.cuh; grids it does not take fall to 0)
     int resident_cluster = 0;  // CTAs per grid (0: as few as fit)
     int resident_trim = -1;    // rows the first / last CTA of a cluster hold fewer than the others (-1: 4 x rows per thread)
     int tma_pair = 0;          // pairwise mbarriers instead of CTA barriers in the TMA tile kernel
