@@ -73,6 +73,7 @@ _SIGNATURES = {
     "fdtd2d_launch_count": ([_vp, ctypes.POINTER(_i64)], _i),
     "fdtd2d_pass_count": ([_vp, ctypes.POINTER(_i64)], _i),
     "fdtd2d_plan_wave_runs": ([_i, _vp, _vp, _i, _i, _i, _vp, _vp], _i),
+    "fdtd2d_plan_resident": ([_i, _i, _i, _i, _vp], _i),
     "fdtd2d_halo_block": ([_vp, _i, _i, _pp, _pp, ctypes.POINTER(_sz)], _i),
     "fdtd2d_halo_block_next": ([_vp, _i, _i, _pp, _pp, ctypes.POINTER(_sz)], _i),
     "fdtd2d_peer_export": ([_vp, _vp], _i),

@@ -2464,6 +2464,17 @@ int fdtd2d_plan_wave_runs(int n_stretches, const int32_t* rows, const uint8_t* r
     return 0;
 }
 
+int fdtd2d_plan_resident(int rows, int cols, int cfg, int cluster, int32_t* out) {
+    REQUIRE(out && rows > 0 && cols > 0, "bad argument");
+    fdtd2d_sim s;  // geometry only: no device resources are created or touched
+    s.dtype = FDTD2D_F32, s.batch = 1, s.Rg = rows, s.C = cols, s.row_begin = 0, s.row_end = rows;
+    s.opt = Options();
+    s.opt.resident_cfg = cfg, s.opt.resident_cluster = cluster;
+    out[0] = out[1] = out[2] = out[3] = -1;
+    if (resident_eligible(&s)) out[0] = s.resident_cfg, out[1] = s.resident_cluster, out[2] = s.resident_edge, out[3] = s.resident_rpc;
+    return 0;
+}
+
 int fdtd2d_plan_host(const int32_t* geom, int n_src, const int32_t* src, int n_probe, const int32_t* probe, int32_t* plan,
                      int32_t* tile_kind, int cap_tiles, int32_t* tasks, int cap_tasks) {
     REQUIRE(geom && plan && (n_src == 0 || src) && (n_probe == 0 || probe) && n_src >= 0 && n_probe >= 0, "bad argument");

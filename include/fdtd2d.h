@@ -208,6 +208,10 @@ int fdtd2d_pass_count(const fdtd2d_sim* s, int64_t* passes);
  * (nearly equal) runs of stretch i, *run_rows the plain run length chosen.  No reference counterpart. */
 int fdtd2d_plan_wave_runs(int n_stretches, const int32_t* rows, const uint8_t* ring, int warps, int cap_rows, int k,
                           int32_t* parts, int32_t* run_rows);
+/* Host-only: how the cluster-resident kernels would split a whole fp32 grid of rows x cols (cfg: option resident_cfg,
+ * cluster: option resident_cluster, 0 = as few CTAs as fit).  out[4] = kernel shape used (5 = the packed kernel), CTAs per
+ * grid, rows of the first band, rows of the other bands (the last band takes what is left); all -1: not eligible. */
+int fdtd2d_plan_resident(int rows, int cols, int cfg, int cluster, int32_t* out);
 /* Host-only: the whole plan of a k-step pass for a geometry, without a handle or a GPU (the CPU tests check that every
  * owned cell is produced exactly once, for whole grids and slabs, fp32 and fp64).  geom[15] = dtype, batch, global rows,
  * cols, row_begin, row_end, halo, k, SM count, kernel variant, wave_min_tiles, ring_min_tiles, wavefront, ring_strips,

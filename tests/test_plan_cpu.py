@@ -230,3 +230,45 @@ def test_fused_automatic_mode_takes_only_large_grids(lib):
     assert len(plan_fused(lib, 16384, 16384, fuse=-1)[0]) > 2000
     assert len(plan_fused(lib, 4096, 4096, fuse=-1)[0]) == 0
     assert len(plan_fused(lib, 16384, 16384, fuse=0)[0]) == 0
+
+
+# ---- the band split of the cluster-resident kernels (fdtd2d_plan_resident: host arithmetic only) ----------------------
+def resident_plan(lib, R, C, cfg=5, cluster=0):
+    out = np.zeros(4, np.int32)
+    rc = lib.fdtd2d_plan_resident(R, C, cfg, cluster, out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0, lib.fdtd2d_last_error()
+    return tuple(int(v) for v in out)
+
+
+def test_resident_bands_of_the_packed_kernel(lib):
+    """grid_resident_x2.cuh relies on: at most 8 bands of at most 48 rows; every band but the first a multiple of six rows
+    (the six bottom ring rows are ONE row block's rows), the last one at least six; the first band 6..48 rows (the six top
+    ring rows are its first block); a band that holds both rings has twelve rows or more; grids whose right ring straddles
+    column 128 and grids of more than 384 rows go to the round-1 kernel (shape 0) or are not resident at all."""
+    for C in (16, 100, 128, 129, 133, 134, 200, 256):
+        straddle = C > 128 and ((C - 6) // 4) * 4 < 128
+        for R in range(16, 420):
+            shape, n, first, rpc = resident_plan(lib, R, C)
+            if R > 384:
+                assert shape == -1, (R, C)
+                continue
+            assert shape == (0 if straddle else 5), (R, C, shape)
+            if shape != 5:
+                continue
+            assert 1 <= n <= 8 and n == max(-(-R // 48), 2 if (R % 6 or R < 12) and R <= 48 else 1), (R, C, n)
+            if n == 1:
+                assert first == R and R % 6 == 0 and R >= 12
+                continue
+            last = R - first - (n - 2) * rpc
+            assert 6 <= first <= 48 and rpc % 6 == 0 and 6 <= rpc <= 48, (R, C, n, first, rpc)
+            assert last % 6 == 0 and 6 <= last <= 48, (R, C, n, first, rpc, last)
+    # the cluster-size knob: more, thinner bands keep the same invariants (or the grid is not resident)
+    for R in (96, 120, 200, 256):
+        for n_req in range(2, 9):
+            shape, n, first, rpc = resident_plan(lib, R, 200, cluster=n_req)
+            if shape != 5:
+                continue
+            last = R - first - (n - 2) * rpc
+            assert n >= n_req or n == -(-R // 48)
+            assert 6 <= first <= 48 and rpc % 6 == 0 and last % 6 == 0 and 6 <= last <= 48, (R, n_req, n, first, rpc, last)
+    assert resident_plan(lib, 64, 300) == (-1, -1, -1, -1) and resident_plan(lib, 12, 64) == (-1, -1, -1, -1)
