@@ -1394,15 +1394,21 @@ static bool resident_eligible(fdtd2d_sim* s) {
             rpc = edge = last = s->Rg;
         } else {
             bool ok = false;
-            for (int r6 = mr * ((s->Rg + mr * n - 1) / (mr * n)); r6 <= band && !ok; r6 += mr) {
+            // Warps w, w + 4, ... share a scheduler, i.e. row blocks 0 and 4: the two SLOW row blocks of a CTA -- the first
+            // (ring rows or the CTA above) and the last (ring rows or the CTA below) -- must not be blocks 0 and 4
+            // (measured on cfg5: 685 against 712 Gcell/s), so a band of 5 blocks is avoided where the grid leaves the choice.
+            auto clash = [&](int rows) { return (rows + mr - 1) / mr == 5; };
+            int best = 1 << 30;
+            for (int r6 = mr * ((s->Rg + mr * n - 1) / (mr * n)); r6 <= band; r6 += mr) {
                 const int rem = s->Rg - (n - 2) * r6;  // rows of the first and the last band together
                 if (rem < 2 * mr) break;
                 const int la_min = std::max(mr, (rem - band + mr - 1) / mr * mr), la_max = std::min(band, (rem - mr) / mr * mr);
-                if (la_min > la_max) continue;
-                rpc = r6;
-                last = std::min(std::max(rem / 2 / mr * mr, la_min), la_max);
-                edge = rem - last;
-                ok = true;
+                for (int la = la_min; la <= la_max; la += mr) {
+                    // cost: clashes first, then thick middle bands, then a first and a last band of different size
+                    int cost = 10000 * ((n > 2 && clash(r6) ? n - 2 : 0) + (clash(la) ? 1 : 0) + (clash(rem - la) ? 1 : 0)) + 100 * (r6 / mr) + std::abs(2 * la - rem);
+                    if (s->opt.resident_trim > 0) cost = std::abs(la - s->opt.resident_trim / mr * mr) + 100 * (r6 / mr);  // tuning knob: rows of the last band
+                    if (cost < best) best = cost, rpc = r6, last = la, edge = rem - la, ok = true;
+                }
             }
             if (!ok) return false;
         }
