@@ -1399,18 +1399,30 @@ static bool resident_eligible(fdtd2d_sim* s) {
             // (measured on cfg5: 685 against 712 Gcell/s), so a band of 5 blocks is avoided where the grid leaves the choice.
             auto clash = [&](int rows) { return (rows + mr - 1) / mr == 5; };
             int best = 1 << 30;
-            for (int r6 = mr * ((s->Rg + mr * n - 1) / (mr * n)); r6 <= band; r6 += mr) {
+            const int r6_lo = n > 2 ? std::max(mr, (s->Rg - 2 * band + (n - 2) * mr - 1) / ((n - 2) * mr) * mr) : mr;  // (the first and the last band hold at most 2 x 48 rows)
+            for (int r6 = r6_lo; r6 <= band; r6 += mr) {
                 const int rem = s->Rg - (n - 2) * r6;  // rows of the first and the last band together
                 if (rem < 2 * mr) break;
                 const int la_min = std::max(mr, (rem - band + mr - 1) / mr * mr), la_max = std::min(band, (rem - mr) / mr * mr);
-                for (int la = la_min; la <= la_max; la += mr) {
+                for (int la = la_min; la <= std::min(la_max, n > 2 ? r6 : la_max); la += mr) {  // (the kernel caps every band but the first at rpc rows)
                     // cost: clashes first, then thick middle bands, then a first and a last band of different size
-                    int cost = 10000 * ((n > 2 && clash(r6) ? n - 2 : 0) + (clash(la) ? 1 : 0) + (clash(rem - la) ? 1 : 0)) + 100 * (r6 / mr) + std::abs(2 * la - rem);
-                    if (s->opt.resident_trim > 0) cost = std::abs(la - s->opt.resident_trim / mr * mr) + 100 * (r6 / mr);  // tuning knob: rows of the last band
+                    // cost: clashes first; then a first / last CTA that is not full -- they hold the ring warps, the slowest of the
+                    // cluster, and the fewer other warps share their SM the better (256 rows as 46 | 42 x 4 | 42: 694 Gcell/s, as
+                    // 40 | 48 x 4 | 24: 712); then thin middle bands (200 rows as 38 | 42 x 3 | 36: 505 Gcell/s over 148 grids, as
+                    // 32 | 48 x 3 | 24: 481); then a first and a last band of similar size
+                    const int fi = rem - la, thick = std::max(fi, la), thin = std::min(fi, la);
+                    auto blocks = [&](int rows) { return (rows + mr - 1) / mr; };
+                    int cost = 10000 * ((n > 2 && clash(r6) ? n - 2 : 0) + (clash(la) ? 1 : 0) + (clash(fi) ? 1 : 0)) +
+                               300 * (std::max(0, blocks(fi) - 7) + std::max(0, blocks(la) - 7)) + (n > 2 ? 100 * blocks(r6) : 0) + (thick - thin);
+                    // tuning knobs: rows of the last band (resident_trim) and of the middle bands (resident_rows)
+                    if (s->opt.resident_trim > 0 || s->opt.resident_rows > 0)
+                        cost = (s->opt.resident_trim > 0 ? 100 * std::abs(la - s->opt.resident_trim / mr * mr) : 0) +
+                               (s->opt.resident_rows > 0 ? 100 * std::abs(r6 - s->opt.resident_rows / mr * mr) : 0) + (thick - thin);
                     if (cost < best) best = cost, rpc = r6, last = la, edge = rem - la, ok = true;
                 }
             }
             if (!ok) return false;
+            if (n == 2) rpc = last;
         }
         s->resident_cfg = rcfg;
         s->resident_cluster = n;

@@ -21,7 +21,9 @@ struct Options {
     int resident = 1;          // cluster-resident kernel for small fp32 grids
     int resident_cfg = 5;      // its shape (index into kResCfgs): 5 = the packed kernel (grid_resident_x2.cuh; grids it does not take fall to 0)
     int resident_cluster = 0;  // CTAs per grid (0: as few as fit)
-    int resident_trim = -1;    // rows the first / last CTA of a cluster hold fewer than the others (-1: 4 x rows per thread)
+    int resident_trim = -1;    // rows the first / last CTA of a cluster hold fewer than the others (-1: 4 x rows per thread);
+                               // packed kernel: rows of the last band (<= 0: automatic)
+    int resident_rows = 0;     // packed kernel: rows of the middle bands (0: automatic)
     int tma_pair = 0;          // pairwise mbarriers instead of CTA barriers in the TMA tile kernel
     int f64_k = 0;             // default k_temporal of fp64 handles (0: 8 on the wavefront, else 4)
     int fuse = 0;              // EXPERIMENT, off: two k = 8 passes per launch, the second reading the first's output from L2
@@ -51,6 +53,7 @@ inline const OptionKey* option_keys(int* n) {
         {"resident_cfg", &Options::resident_cfg},
         {"resident_cluster", &Options::resident_cluster},
         {"resident_trim", &Options::resident_trim},
+        {"resident_rows", &Options::resident_rows},
         {"tma_pair", &Options::tma_pair},
         {"f64_k", &Options::f64_k},
         {"fuse", &Options::fuse},

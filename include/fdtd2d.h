@@ -79,7 +79,7 @@ int fdtd2d_sync(fdtd2d_sim* s);
  * (upper case), read once at that moment.  fdtd2d_set_option changes one option of this handle and drops its cached
  * plans.  Keys: "wavefront" (1), "wave_min_tiles" (-1 = automatic), "ring_min_tiles" (-1), "ring_strips" (1),
  * "wave_run_rows" (640), "auto_k12" (0), "uniform_ch" (1), "resident" (1), "resident_cfg" (5), "resident_cluster" (0),
- * "resident_trim" (-1), "tma_pair" (0), "f64_k" (0 = automatic), "fuse" (0; 1 = two k = 8 passes per launch, the second fed from L2: an
+ * "resident_trim" (-1), "resident_rows" (0), "tma_pair" (0), "f64_k" (0 = automatic), "fuse" (0; 1 = two k = 8 passes per launch, the second fed from L2: an
  * experiment that is bit-exact but slower on B200; -1 = on for large grids), "stage" (0; 4 / 5 = k = 12 passes on the staged
  * wavefront, the other experiment), "debug" (0).  Every setting is covered by the parity tests: options change which kernel
  * runs, never a result bit -- with ONE exception, "measure_skip" (0), a timing aid that leaves parts of a pass out (1 = no

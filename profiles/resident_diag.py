@@ -15,6 +15,7 @@ for cfg in [int(x) for x in os.environ.get("CFGS", "0").split(",")]:
         sim.set_option("resident_cfg", cfg)
         sim.set_option("resident_trim", trim)
         if os.environ.get("CLUSTER"): sim.set_option("resident_cluster", int(os.environ["CLUSTER"]))
+        if os.environ.get("ROWS"): sim.set_option("resident_rows", int(os.environ["ROWS"]))
         sim.set_materials_random(1, 4.0)
         amp = fd.source_table("ricker", 4000, DT, 20e9)
         sim.set_sources([(b, R // 2, C // 2, 0) for b in range(B)], amp[None, :])
