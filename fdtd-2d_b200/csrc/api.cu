@@ -23,6 +23,12 @@
 #include "tile_generic.cuh"
 #include "grid_resident.cuh"
 #include "grid_resident_x2.cuh"
+namespace fdtd2d {
+// resident_x2.cu (a translation unit of its own: the build compiles the two side by side) holds the twelve instantiations of
+// the packed cluster-resident kernel and this launcher; api.cu never names the kernel template.
+cudaError_t resident_x2_launch(bool uch, int rl, const cudaLaunchConfig_t* cfg, const PassParams<float>& p, float ch_uniform, bool set_smem_attr,
+                               size_t smem, int* max_active_clusters);
+}  // namespace fdtd2d
 #include "strip_wave.cuh"
 #include "strip_stage.cuh"
 #include "grid_small.cuh"
@@ -1498,14 +1504,10 @@ template <int MR, int NW> static int launch_resident_t(fdtd2d_sim* s, int n_step
 }
 
 // the packed kernel (grid_resident_x2.cuh): uniform dt/(mu*dx) as an argument, or the map
-template <bool UCH, int RL> static int launch_resident_x2_t(fdtd2d_sim* s, int n_steps) {
-    static bool done_[MAX_DEVICES] = {};
-    bool& done = done_[s->device % MAX_DEVICES];
+static int launch_resident_x2(fdtd2d_sim* s, int n_steps, bool uch, int rl) {
+    static bool done_[2][RX_MR][MAX_DEVICES] = {};
+    bool& done = done_[uch ? 1 : 0][rl][s->device % MAX_DEVICES];
     const size_t smem = resident_x2_smem_floats() * sizeof(float);
-    if (!done) {
-        CUDA_TRY(cudaFuncSetAttribute(grid_resident_x2_kernel<UCH, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        done = true;
-    }
     TilePlan tp;
     tp.k = n_steps;
     tp.CH = s->resident_rpc;
@@ -1524,15 +1526,12 @@ template <bool UCH, int RL> static int launch_resident_x2_t(fdtd2d_sim* s, int n
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (s->opt.debug) {
-        int nc = -1;
-        cudaOccupancyMaxActiveClusters(&nc, grid_resident_x2_kernel<UCH, RL>, &cfg);
+    int nc = -1;
+    CUDA_TRY(resident_x2_launch(uch, rl, &cfg, p, (float)s->ch_value, !done, smem, s->opt.debug ? &nc : nullptr));
+    done = true;
+    if (s->opt.debug)
         fprintf(stderr, "[fdtd2d] resident x2: %d grids x cluster %d (%d | %d rows per CTA), uniform ch %d, %zu B smem, max active clusters %d\n",
-                s->batch, s->resident_cluster, s->resident_edge, s->resident_rpc, (int)UCH, smem, nc);
-    }
-    const float chu = (float)s->ch_value;
-    const unsigned long long negzero = 0x8000000080000000ull;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, grid_resident_x2_kernel<UCH, RL>, p, chu, negzero));
+                s->batch, s->resident_cluster, s->resident_edge, s->resident_rpc, (int)uch, smem, nc);
     s->launches += 1;
     s->passes += 1;
     s->cur ^= 1;
@@ -1544,15 +1543,7 @@ static int launch_resident(fdtd2d_sim* s, int n_steps) {
         if (int rc = check_ch_uniform(s)) return rc;
         // the row inside a row block at which the first band ends is a template parameter (see the kernel)
         const int rl = s->resident_cluster > 1 ? (s->resident_edge - 1) % RX_MR : RX_MR - 1;
-        const bool uch = s->ch_uniform == 1;
-        switch (rl) {
-            case 0: return uch ? launch_resident_x2_t<true, 0>(s, n_steps) : launch_resident_x2_t<false, 0>(s, n_steps);
-            case 1: return uch ? launch_resident_x2_t<true, 1>(s, n_steps) : launch_resident_x2_t<false, 1>(s, n_steps);
-            case 2: return uch ? launch_resident_x2_t<true, 2>(s, n_steps) : launch_resident_x2_t<false, 2>(s, n_steps);
-            case 3: return uch ? launch_resident_x2_t<true, 3>(s, n_steps) : launch_resident_x2_t<false, 3>(s, n_steps);
-            case 4: return uch ? launch_resident_x2_t<true, 4>(s, n_steps) : launch_resident_x2_t<false, 4>(s, n_steps);
-            default: return uch ? launch_resident_x2_t<true, 5>(s, n_steps) : launch_resident_x2_t<false, 5>(s, n_steps);
-        }
+        return launch_resident_x2(s, n_steps, s->ch_uniform == 1, rl);
     }
     switch (s->resident_cfg) {
         case 1: return launch_resident_t<4, 12>(s, n_steps);
