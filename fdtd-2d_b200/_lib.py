@@ -11,7 +11,7 @@ F32, F64 = 0, 1
 PHASE_H, PHASE_E, PHASE_SRC = 1, 2, 4
 MAX_K = 12
 PEER_BLOB_BYTES = 640
-PLAN_INFO_WORDS = 12
+PLAN_INFO_WORDS = 13
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -74,6 +74,7 @@ _SIGNATURES = {
     "fdtd2d_pass_count": ([_vp, ctypes.POINTER(_i64)], _i),
     "fdtd2d_plan_wave_runs": ([_i, _vp, _vp, _i, _i, _i, _vp, _vp], _i),
     "fdtd2d_plan_resident": ([_i, _i, _i, _i, _vp], _i),
+    "fdtd2d_plan_edge_reserve": ([_i64, _i64, _i, _i], _i),
     "fdtd2d_halo_block": ([_vp, _i, _i, _pp, _pp, ctypes.POINTER(_sz)], _i),
     "fdtd2d_halo_block_next": ([_vp, _i, _i, _pp, _pp, ctypes.POINTER(_sz)], _i),
     "fdtd2d_peer_export": ([_vp, _vp], _i),

@@ -94,6 +94,7 @@ struct PassPlan {
     bool wave_ring = false;           // the list holds runs of the strips with the left / right Mur ring
     int band_expected[2] = {0, 0};    // band tasks (runs + edge tiles) next to the top / bottom neighbour
     int* d_ticket = nullptr;          // next run to hand out (zero between launches: the last draw of a launch resets it)
+    int reserve_sms = 0;              // SMs the wavefront kernel leaves to the edge tiles (its runs are cut for the others)
     // fused double pass (strip_wave.cuh): the runs of two consecutive passes in one ticket order; the phase-1 pieces next to
     // edge tiles wait for a second, short launch
     int n_fused = 0, n_deferred = 0, fuse_nblk = 0;
@@ -595,9 +596,10 @@ static bool wave_has_k(const fdtd2d_sim* s, int k) {
     return k == 8 || (k == 12 && !s->has_top_nb && !s->has_bot_nb);  // (12 levels: whole grids with uniform permeability)
 }
 
-static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k, bool ring) {
+// max_ctas > 0: the kernel takes at most that many SMs (the rest are left to the edge tiles of the pass)
+static int launch_wave(fdtd2d_sim* s, const PassParams<float>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k, bool ring, int max_ctas = 0) {
     if (int rc = check_ch_uniform(s)) return rc;
-    const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, sm_count(s));
+    const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, max_ctas > 0 ? std::min(max_ctas, sm_count(s)) : sm_count(s));
     const bool uch = s->ch_uniform == 1;  // uniform permeability: the map is not read at all (28 instead of 32 B per cell and pass)
     const bool slab = s->has_top_nb || s->has_bot_nb;
     if (k == 12) {  // (runs for k = 12 are only built when the permeability is uniform)
@@ -637,9 +639,9 @@ template <int K, bool RING> static int launch_wave_f64_k(fdtd2d_sim* s, const Pa
     return slab ? launch_wave_f64_t<K, false, true, RING>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_f64_t<K, false, false, RING>(s, p, tasks, n_tasks, ticket, grid);
 }
 
-static int launch_wave(fdtd2d_sim* s, const PassParams<double>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k, bool ring) {
+static int launch_wave(fdtd2d_sim* s, const PassParams<double>& p, const WaveTask* tasks, int n_tasks, int* ticket, int k, bool ring, int max_ctas = 0) {
     if (int rc = check_ch_uniform(s)) return rc;
-    const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, sm_count(s));
+    const int grid = std::min((n_tasks + WAVE_NW - 1) / WAVE_NW, max_ctas > 0 ? std::min(max_ctas, sm_count(s)) : sm_count(s));
     switch (k) {
         case 4: return launch_wave_f64_k<4, false>(s, p, tasks, n_tasks, ticket, grid);  // (ring strips are built for k = 8 only)
         case 8: return ring ? launch_wave_f64_k<8, true>(s, p, tasks, n_tasks, ticket, grid) : launch_wave_f64_k<8, false>(s, p, tasks, n_tasks, ticket, grid);
@@ -769,13 +771,19 @@ static void free_plans(fdtd2d_sim* s) {
 // shortest plain run length L (>= 4k rows: a run spends 2k rows warming up) for which the stretches fall into at most
 // m x `warps` runs, m = the smallest count of runs per warp that keeps a run under ~cap_rows rows; parts[i] runs of
 // (nearly) equal height then cover stretch i.
+// ring_cost > 0: a ring-strip row costs ring_cost percent of a plain row and a run's 2k warm-up rows are counted too, so a
+// ring run of r rows takes as long as a plain run of L rows when (r + 2k) * ring_cost = (L + 2k) * 100.
 static int plan_wave_runs(const std::vector<int>& rows, const std::vector<unsigned char>& ring, long long warps, long long cap_rows, int k,
-                          std::vector<int>* parts) {
+                          std::vector<int>* parts, int ring_cost = 0) {
     long long total = 0;
     int longest = 1;
     for (size_t i = 0; i < rows.size(); ++i) total += (ring[i] ? 2LL : 1LL) * rows[i], longest = std::max(longest, rows[i]);
     const long long m = std::max<long long>(1, (total + warps * cap_rows - 1) / (warps * cap_rows));
-    auto run_len = [&](size_t i, int len) { return ring[i] ? std::max(4 * k, len / 2) : len; };
+    auto run_len = [&](size_t i, int len) {
+        if (!ring[i]) return len;
+        if (ring_cost <= 0) return std::max(4 * k, len / 2);
+        return std::max(4 * k, (int)((long long)(len + 2 * k) * 100 / ring_cost) - 2 * k);
+    };
     auto count_runs = [&](int len) {
         long long c = 0;
         for (size_t i = 0; i < rows.size(); ++i) c += (rows[i] + run_len(i, len) - 1) / run_len(i, len);
@@ -789,6 +797,32 @@ static int plan_wave_runs(const std::vector<int>& rows, const std::vector<unsign
     parts->resize(rows.size());
     for (size_t i = 0; i < rows.size(); ++i) (*parts)[i] = (rows[i] + run_len(i, lo) - 1) / run_len(i, lo);
     return lo;
+}
+
+// How many SMs the wavefront kernel of a pass should leave to the pass's edge tiles (host arithmetic only; exported as
+// fdtd2d_plan_edge_reserve for the CPU tests).  An edge tile is one CTA that fills an SM (512 threads, the whole register file
+// next to a wavefront CTA's 8 x 32 x 232 registers), so an SM holds either.  Launched first, the edge tiles of a mid-size
+// grid take half the SMs for their ~23 us and the wavefront CTAs of those SMs -- with one run per warp -- start that much
+// later: 4096^2 fp32 measured 112 us per pass = 22.7 (edge tiles) + 89 (a plain run), with a work-conserving floor of 101.
+// Instead the wavefront goes first on sms - r SMs, its runs cut for that many warps, and the edge tiles cycle through the r
+// SMs left: r minimises max(edge rounds x tile time, rows per warp).  Units: rows of one wavefront warp (0.60 us at 4096^2);
+// an edge tile takes ~38 of them (22.7 us; both scale with k).  Below 5 % of the pass (large grids: the runs are DRAM-bound
+// and the edge tiles hide behind them as it is) and above 25 % (small grids, where the wavefront is the minor part and the
+// constants above were not measured) nothing is reserved.  wave_rows: rows of all stretches, ring strips weighted.
+static int plan_edge_reserve(long long n_edge, long long wave_rows, int sms, int k) {
+    constexpr long long EDGE_ROWS = 38;
+    if (n_edge <= 0 || wave_rows <= 0 || sms < 8) return 0;
+    const long long edge_work = n_edge * EDGE_ROWS * WAVE_NW;  // in rows of one warp, like wave_rows
+    if (edge_work * 20 < edge_work + wave_rows || edge_work * 4 > edge_work + wave_rows) return 0;  // (5 % .. 25 % of the pass)
+    int best = 0;
+    long long best_t = -1;
+    for (int r = 1; r <= sms / 2; ++r) {
+        const long long w = (long long)(sms - r) * WAVE_NW;
+        const long long t_edge = (n_edge + r - 1) / r * EDGE_ROWS, t_wave = (wave_rows + w - 1) / w + 2 * k;
+        const long long t = std::max(t_edge, t_wave);
+        if (best_t < 0 || t < best_t) best_t = t, best = r;
+    }
+    return best;
 }
 
 // Classify the tile grid of a k-step pass and build its task lists (cached per k until sources, probes, materials or
@@ -809,6 +843,7 @@ struct PlanLists {
     int n_wave_band = 0;
     bool wave_ring = false;
     int band_expected[2] = {0, 0};
+    int reserve_sms = 0;              // SMs left to the edge tiles (plan_edge_reserve)
     std::vector<WaveTask> fused, deferred;  // fused double pass: stage-1 ticket order (both phases), stage-2 phase-1 pieces
     int fuse_nblk = 0;
 };
@@ -822,7 +857,7 @@ static int plan_pass(const fdtd2d_sim* s, int k, PlanLists* pl) {
     // fp64 strips are 64 columns wide (two columns per lane): a tile column is cut into two strips
     const int hxw = (int)round_up((size_t)k, 2), strip_core_max = 64 - 2 * hxw;
     TilePlan& tp = pl->tp;
-    pl->wave_ring = false, pl->n_wave_band = 0, pl->n_edge_band = 0;
+    pl->wave_ring = false, pl->n_wave_band = 0, pl->n_edge_band = 0, pl->reserve_sms = 0;
     if (int rc = plan_tiles(s, k, TH, &tp, 4, (f64 && wave_k) ? 2 * strip_core_max : 0)) return rc;
     const int per_grid = tp.tiles_y * tp.tiles_x;
     const long long n_tiles = (long long)s->batch * per_grid;
@@ -1030,7 +1065,22 @@ static int plan_pass(const fdtd2d_sim* s, int k, PlanLists* pl) {
         std::vector<int> seg_rows(segs.size()), parts;
         std::vector<unsigned char> seg_ring(segs.size());
         for (size_t i = 0; i < segs.size(); ++i) seg_rows[i] = segs[i].y1 - segs[i].y0, seg_ring[i] = segs[i].side != 0;
-        plan_wave_runs(seg_rows, seg_ring, warps, std::max(1, s->opt.wave_run_rows), k, &parts);
+        // whole grids: leave some SMs to the edge tiles and cut the runs for the rest (plan_edge_reserve)
+        int reserve = 0;
+        const long long n_edge_all = (long long)edge_band.size() + (long long)edge_rest.size();
+        if (!slab && band_tasks.empty() && s->opt.edge_reserve != 0 && n_edge_all > 0) {
+            if (s->opt.edge_reserve > 0) {
+                reserve = std::min(s->opt.edge_reserve, std::max(1, s->sm_count) / 2);
+            } else {
+                long long wave_rows = 0;
+                for (size_t i = 0; i < segs.size(); ++i) wave_rows += seg_ring[i] ? (long long)seg_rows[i] * 208 / 100 : seg_rows[i];
+                reserve = plan_edge_reserve(n_edge_all, wave_rows, std::max(1, s->sm_count), k);
+            }
+        }
+        pl->reserve_sms = reserve;
+        const int ring_cost = s->opt.ring_cost > 0 ? s->opt.ring_cost : (reserve > 0 ? 208 : 0);
+        const long long run_warps = (long long)(std::max(1, s->sm_count) - reserve) * WAVE_NW;
+        plan_wave_runs(seg_rows, seg_ring, run_warps, std::max(1, s->opt.wave_run_rows), k, &parts, ring_cost);
         for (size_t i = 0; i < segs.size(); ++i) {
             const WaveTask& g = segs[i];
             const int rows = seg_rows[i];
@@ -1177,6 +1227,7 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
     if (int rc = plan_pass(s, k, &L)) return rc;
     pl->tp = L.tp;
     pl->wave_ring = L.wave_ring;
+    pl->reserve_sms = L.reserve_sms;
     pl->band_expected[0] = L.band_expected[0], pl->band_expected[1] = L.band_expected[1];
     pl->n_wave = (int)L.tasks.size(), pl->n_wave_band = L.n_wave_band;
     pl->n_edge = (int)L.edge.size(), pl->n_edge_band = L.n_edge_band;
@@ -1212,9 +1263,9 @@ static int classify_tiles(fdtd2d_sim* s, int k, PassPlan* pl) {
     CUDA_TRY(cudaStreamSynchronize(s->stream));  // the host vectors die here
     const TilePlan& tp = pl->tp;
     if (s->opt.debug)
-        fprintf(stderr, "[fdtd2d] plan k=%d: tiles %d x %d (core %d x %d), edge %d (band %d), tma %d, wave runs %d (band %d, ring %d), band tasks %d | %d, fused %d + deferred %d\n", k,
+        fprintf(stderr, "[fdtd2d] plan k=%d: tiles %d x %d (core %d x %d), edge %d (band %d), tma %d, wave runs %d (band %d, ring %d), band tasks %d | %d, fused %d + deferred %d, SMs left to the edge tiles %d\n", k,
                 tp.tiles_y, tp.tiles_x, tp.CH, tp.CW, pl->n_edge, pl->n_edge_band, pl->n_fast, pl->n_wave, pl->n_wave_band, (int)pl->wave_ring,
-                pl->band_expected[0], pl->band_expected[1], pl->n_fused, pl->n_deferred);
+                pl->band_expected[0], pl->band_expected[1], pl->n_fused, pl->n_deferred, pl->reserve_sms);
     pl->valid = true;
     return 0;
 }
@@ -1255,7 +1306,10 @@ template <typename T> static int launch_hybrid_t(fdtd2d_sim* s, int k, int part)
         CUDA_TRY(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
         estream = s->side_stream;
     }
-    if (n_edge) {
+    // With SMs reserved for them (plan_edge_reserve) the edge tiles go out AFTER the wavefront kernel, which takes only its
+    // share of the SMs: the edge CTAs then cycle through the SMs that are left instead of holding up half the wavefront CTAs.
+    const bool wave_first = both && part == 0 && pl.reserve_sms > 0 && n_wave > 0;
+    auto launch_edges = [&]() -> int {
         p.tile_list = pl.d_edge + e_off;
         int rc;
         if (s->variant == 3) {  // debugging aid: shared-memory generic kernel for the edge tiles (fp32)
@@ -1268,14 +1322,21 @@ template <typename T> static int launch_hybrid_t(fdtd2d_sim* s, int k, int part)
         } else {
             rc = launch_edge(s->device, p, n_edge, estream);
         }
+        p.tile_list = nullptr;
         if (rc) return rc;
         s->launches += 1;
-    }
+        return 0;
+    };
+    if (n_edge && !wave_first)
+        if (int rc = launch_edges()) return rc;
     p.tile_list = nullptr;
     if (n_wave) {
-        if (int rc = launch_wave(s, p, pl.d_wave + w_off, n_wave, pl.d_ticket, k, pl.wave_ring)) return rc;
+        const int max_ctas = wave_first ? sm_count(s) - pl.reserve_sms : 0;
+        if (int rc = launch_wave(s, p, pl.d_wave + w_off, n_wave, pl.d_ticket, k, pl.wave_ring, max_ctas)) return rc;
         s->launches += 1;
     }
+    if (n_edge && wave_first)
+        if (int rc = launch_edges()) return rc;
     if (n_fast) {
         if constexpr (std::is_same<T, float>::value) {
             p.tile_list = pl.d_fast;
@@ -2473,6 +2534,11 @@ int fdtd2d_plan_wave_runs(int n_stretches, const int32_t* rows, const uint8_t* r
     return 0;
 }
 
+int fdtd2d_plan_edge_reserve(int64_t n_edge, int64_t wave_rows, int sm_count, int k) {
+    if (k < 1 || k > FDTD2D_MAX_K) return 0;
+    return plan_edge_reserve(n_edge, wave_rows, sm_count, k);
+}
+
 int fdtd2d_plan_resident(int rows, int cols, int cfg, int cluster, int32_t* out) {
     REQUIRE(out && rows > 0 && cols > 0, "bad argument");
     fdtd2d_sim s;  // geometry only: no device resources are created or touched
@@ -2559,7 +2625,8 @@ int fdtd2d_plan_info(fdtd2d_sim* s, int k, int32_t* info, int n_info) {
     if (!pl.valid)
         if (int rc = classify_tiles(s, k, &pl)) return rc;
     const int32_t v[FDTD2D_PLAN_INFO_WORDS] = {pl.tp.tiles_y, pl.tp.tiles_x, pl.tp.CH, pl.tp.CW, pl.n_edge, pl.n_edge_band, pl.n_fast,
-                                              pl.n_wave, pl.n_wave_band, pl.wave_ring ? 1 : 0, pl.band_expected[0], pl.band_expected[1]};
+                                              pl.n_wave, pl.n_wave_band, pl.wave_ring ? 1 : 0, pl.band_expected[0], pl.band_expected[1],
+                                              pl.reserve_sms};
     for (int i = 0; i < n_info && i < FDTD2D_PLAN_INFO_WORDS; ++i) info[i] = v[i];
     return 0;
 }

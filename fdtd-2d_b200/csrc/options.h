@@ -16,6 +16,11 @@ struct Options {
     int ring_min_tiles = -1;   // ... from which the left / right Mur ring rides along the wavefront; -1: 2 per warp
     int ring_strips = 1;       // left / right ring strips on the wavefront at all
     int wave_run_rows = 640;   // cap on the rows of one wavefront run
+    int edge_reserve = -1;     // whole grids: SMs the wavefront kernel leaves to the edge tiles of its pass (the runs are cut for the
+                               // other SMs and launched first); 0 none (edge tiles first, wavefront on every SM), -1: automatic --
+                               // reserve when the edge tiles are >= 5 % of the pass (mid-size grids such as 4096^2)
+    int ring_cost = 0;         // cost of a ring-strip row in percent of a plain row when runs are balanced, warm-up rows included;
+                               // 0: 208 with reserved SMs, else the older rule (ring runs half as long as plain runs)
     int auto_k12 = 0;          // k_temporal = 0 picks the 12-level wavefront when it exists (uniform permeability)
     int uniform_ch = 1;        // pass dt/(mu*dx) as a scalar when the map is uniform
     int resident = 1;          // cluster-resident kernel for small fp32 grids
@@ -47,6 +52,8 @@ inline const OptionKey* option_keys(int* n) {
         {"ring_min_tiles", &Options::ring_min_tiles},
         {"ring_strips", &Options::ring_strips},
         {"wave_run_rows", &Options::wave_run_rows},
+        {"edge_reserve", &Options::edge_reserve},
+        {"ring_cost", &Options::ring_cost},
         {"auto_k12", &Options::auto_k12},
         {"uniform_ch", &Options::uniform_ch},
         {"resident", &Options::resident},

@@ -144,7 +144,7 @@ class Simulation:
         a = (ctypes.c_int32 * _lib.PLAN_INFO_WORDS)()
         check(lib().fdtd2d_plan_info(self._h, k, a, _lib.PLAN_INFO_WORDS))
         names = ("tiles_y", "tiles_x", "core_rows", "core_cols", "edge_tiles", "edge_band_tiles", "tma_tiles", "wave_runs",
-                 "wave_band_runs", "ring_strips", "band_tasks_top", "band_tasks_bottom")
+                 "wave_band_runs", "ring_strips", "band_tasks_top", "band_tasks_bottom", "reserve_sms")
         return dict(zip(names, (int(v) for v in a)))
 
     # ---- state ------------------------------------------------------------------------------

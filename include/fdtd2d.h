@@ -78,7 +78,9 @@ int fdtd2d_sync(fdtd2d_sim* s);
 /* A handle copies its options when it is created; the defaults come from the environment variables FDTD2D_<KEY>
  * (upper case), read once at that moment.  fdtd2d_set_option changes one option of this handle and drops its cached
  * plans.  Keys: "wavefront" (1), "wave_min_tiles" (-1 = automatic), "ring_min_tiles" (-1), "ring_strips" (1),
- * "wave_run_rows" (640), "auto_k12" (0), "uniform_ch" (1), "resident" (1), "resident_cfg" (5), "resident_cluster" (0),
+ * "wave_run_rows" (640), "edge_reserve" (-1 = automatic: whole grids whose edge tiles are >= 5 % of a pass leave some SMs to
+ * them and launch the wavefront first; 0 = never, n = that many SMs), "ring_cost" (0 = automatic; percent of a plain row that
+ * a ring-strip row costs when runs are balanced), "auto_k12" (0), "uniform_ch" (1), "resident" (1), "resident_cfg" (5), "resident_cluster" (0),
  * "resident_trim" (-1), "resident_rows" (0), "tma_pair" (0), "f64_k" (0 = automatic), "fuse" (0; 1 = two k = 8 passes per launch, the second fed from L2: an
  * experiment that is bit-exact but slower on B200; -1 = on for large grids), "stage" (0; 4 / 5 = k = 12 passes on the staged
  * wavefront, the other experiment), "debug" (0).  Every setting is covered by the parity tests: options change which kernel
@@ -208,6 +210,10 @@ int fdtd2d_pass_count(const fdtd2d_sim* s, int64_t* passes);
  * (nearly equal) runs of stretch i, *run_rows the plain run length chosen.  No reference counterpart. */
 int fdtd2d_plan_wave_runs(int n_stretches, const int32_t* rows, const uint8_t* ring, int warps, int cap_rows, int k,
                           int32_t* parts, int32_t* run_rows);
+/* Host-only: how many SMs the wavefront kernel of a k-step pass leaves to the pass's `n_edge` edge tiles when its stretches
+ * hold `wave_rows` rows (ring-strip rows weighted by their cost); 0 = none (edge tiles below 5 % of the pass).  No
+ * reference counterpart. */
+int fdtd2d_plan_edge_reserve(int64_t n_edge, int64_t wave_rows, int sm_count, int k);
 /* Host-only: how the cluster-resident kernels would split a whole fp32 grid of rows x cols (cfg: option resident_cfg,
  * cluster: option resident_cluster, 0 = as few CTAs as fit).  out[4] = kernel shape used (5 = the packed kernel), CTAs per
  * grid, rows of the first band, rows of the other bands (the last band takes what is left); all -1: not eligible. */
@@ -229,10 +235,11 @@ int fdtd2d_plan_host(const int32_t* geom, int n_src, const int32_t* src, int n_p
  * and last tile column read. */
 int fdtd2d_plan_host_fused(const int32_t* geom, int fuse, int n_src, const int32_t* src, int n_probe, const int32_t* probe, int32_t* counts,
                            int32_t* fused, int cap_fused, int32_t* deferred, int cap_deferred);
-/* What a k-step pass of this handle consists of (builds and caches the plan; needs the materials): info[0..11] =
+/* What a k-step pass of this handle consists of (builds and caches the plan; needs the materials): info[0..12] =
  * tile rows, tile columns, core rows, core columns, edge tiles, of which band tiles, TMA tiles, wavefront runs, of
- * which band runs, ring strips present, band tasks next to the top / bottom neighbour. */
-#define FDTD2D_PLAN_INFO_WORDS 12
+ * which band runs, ring strips present, band tasks next to the top / bottom neighbour, SMs the wavefront kernel leaves
+ * to the edge tiles. */
+#define FDTD2D_PLAN_INFO_WORDS 13
 int fdtd2d_plan_info(fdtd2d_sim* s, int k, int32_t* info, int n_info);
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 int fdtd2d_launch_count(const fdtd2d_sim* s, int64_t* launches);

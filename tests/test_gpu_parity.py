@@ -782,6 +782,43 @@ def test_options_are_per_handle_and_change_only_the_kernel(fd, monkeypatch):
         assert_bits(x, y, "wavefront option on vs off")
 
 
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("reserve,ring_cost", [(0, 0), (20, 0), (60, 208), (-1, 240)])
+def test_edge_tiles_on_reserved_sms_vs_oracle(fd, oracle, dtype, reserve, ring_cost):
+    """Option edge_reserve: the wavefront kernel goes out first on fewer SMs, its runs cut for those, and the edge tiles follow
+    on the side stream; ring_cost changes the length of the ring-strip runs.  Scheduling only -- the bits are the oracle's."""
+    c_oracle, npo = oracle
+    R, C, nsteps = 700, 1500, 24
+    rng = np.random.default_rng(R * 11 + C + reserve)
+    eps, mu, Ez, Hx, Hy = _random_problem(rng, R, C, dtype)
+    mu[...] = np.dtype(dtype).type(4 * np.pi * 1e-7)
+    ce, ch, coef = c_oracle.coefficients(eps, mu, DT, DX, np.dtype(dtype))
+    cells = [(R // 2, C // 2), (7, 9)]
+    amp = npo.source_table("ricker", nsteps, DT, FC) + 0.125
+    probes = [(R // 2, C // 2 + 3), (0, 0), (R - 1, C - 1), (R // 4, C // 3)]
+    oEz, oHx, oHy = Ez.copy(), Hx.copy(), Hy.copy()
+    otrace = c_oracle.run(oEz, oHx, oHy, ce, ch, coef, nsteps, amp, cells, probes, omp=True)
+    with fd.Simulation(R, C, np.dtype(dtype), dt=DT, dx=DX) as sim:
+        sim.set_kernel_variant(2)
+        for key, v in (("wave_min_tiles", 0), ("ring_min_tiles", 0), ("edge_reserve", reserve), ("ring_cost", ring_cost)):
+            sim.set_option(key, v)
+        sim.set_coefficients(ce, ch, coef)
+        sim.set_state(Ez, Hx, Hy)
+        sim.set_sources([(0, r, c, 0) for r, c in cells], amp[None, :])
+        sim.set_probes(probes, nsteps)
+        sim.step(nsteps, 8)
+        info = sim.plan_info(8)
+        assert info["wave_runs"] > 0 and info["edge_tiles"] > 0 and info["ring_strips"] == 1
+        if reserve >= 0:
+            assert info["reserve_sms"] == reserve
+        gEz, gHx, gHy = sim.state()
+        gtrace = sim.read_probes()
+    assert_bits(gtrace, otrace, "probe trace")
+    assert_bits(gEz, oEz, "Ez")
+    assert_bits(gHx, oHx, "Hx")
+    assert_bits(gHy, oHy, "Hy")
+
+
 # --------------------------------------------------------------------------------------------
 # the fused double pass: two k = 8 passes per launch, the second one reading the first one's rows from L2
 # --------------------------------------------------------------------------------------------

@@ -274,3 +274,35 @@ def test_resident_bands_of_the_packed_kernel(lib):
             assert n >= n_req or n == -(-R // 48)
             assert 6 <= first <= 48 and rpc % 6 == 0 and last % 6 == 0 and 6 <= last <= min(48, rpc), (R, n_req, n, first, rpc, last)
     assert resident_plan(lib, 64, 300) == (-1, -1, -1, -1) and resident_plan(lib, 12, 64) == (-1, -1, -1, -1)
+
+
+def test_edge_reserve_model(lib):
+    """fdtd2d_plan_edge_reserve: SMs the wavefront kernel leaves to the edge tiles.  4096^2 fp32 (81 edge tiles next to
+    ~158 k weighted rows): the smallest share that gets the tiles through in four rounds; nothing below 5 % of the pass
+    (16384^2) or above 25 % (small grids); never more than half the SMs."""
+    f = lib.fdtd2d_plan_edge_reserve
+    assert f(81, 158_000, SM, 8) == 21  # ceil(81 / 21) = 4 rounds of 38 row-times < (158000 / (127 * 8) + 16)
+    assert f(301, 2_430_000, SM, 8) == 0 and f(177, 72_000, SM, 8) == 0 and f(0, 100_000, SM, 8) == 0
+    for n_edge, rows in ((60, 150_000), (109, 330_000), (149, 620_000), (40, 50_000)):
+        r = f(n_edge, rows, SM, 8)
+        assert 0 < r <= SM // 2
+        # the edge rounds fit under the wavefront's own time on the remaining SMs (or it is the best compromise)
+        t_edge, t_wave = -(-n_edge // r) * 38, -(-rows // ((SM - r) * 8)) + 16
+        best = min(max(-(-n_edge // q) * 38, -(-rows // ((SM - q) * 8)) + 16) for q in range(1, SM // 2 + 1))
+        assert max(t_edge, t_wave) == best
+
+
+def test_reserved_sms_shorten_nothing_but_the_run_count(lib):
+    """4096^2 fp32 with the bench's source and probes: the automatic reserve is on (edge tiles ~12 % of the pass), the runs fit
+    the warps of the remaining SMs one each, ring runs are balanced against plain runs with their warm-up rows counted, and
+    the coverage invariants hold as for every other plan."""
+    R = 4096
+    probes = [(0, R // 2, R // 2 + 5)] + [(0, R // 8 * i + 3, R // 8 * i + 7) for i in range(1, 8)]
+    pl = plan(lib, 0, R, R, 8, src=[(0, R // 2, R // 2)], probe=probes)
+    check(pl)
+    t = pl["tasks"]
+    rows, ring = t[:, 3] - t[:, 2], t[:, 6] != 0
+    weighted = int(rows[~ring].sum() + (rows[ring].astype(np.int64) * 208 // 100).sum())
+    r = lib.fdtd2d_plan_edge_reserve(pl["n_edge"], weighted, SM, 8)
+    assert r > 0 and len(t) <= (SM - r) * 8
+    assert ring.any() and abs((rows[ring].mean() + 16) * 2.08 - (rows[~ring].mean() + 16)) < 0.1 * (rows[~ring].mean() + 16)
