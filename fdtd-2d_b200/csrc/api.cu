@@ -806,14 +806,16 @@ static int plan_wave_runs(const std::vector<int>& rows, const std::vector<unsign
 // later: 4096^2 fp32 measured 112 us per pass = 22.7 (edge tiles) + 89 (a plain run), with a work-conserving floor of 101.
 // Instead the wavefront goes first on sms - r SMs, its runs cut for that many warps, and the edge tiles cycle through the r
 // SMs left: r minimises max(edge rounds x tile time, rows per warp).  Units: rows of one wavefront warp (0.60 us at 4096^2);
-// an edge tile takes ~38 of them (22.7 us; both scale with k).  Below 5 % of the pass (large grids: the runs are DRAM-bound
-// and the edge tiles hide behind them as it is) and above 25 % (small grids, where the wavefront is the minor part and the
-// constants above were not measured) nothing is reserved.  wave_rows: rows of all stretches, ring strips weighted.
+// an edge tile takes ~38 of them (22.7 us; both scale with k).  Measured (profiles/r2_reserve_ab.txt, bit-equal fields):
+// 4096^2 113.2 -> 108.2 us per pass (21 SMs), 8192^2 fp32 364 -> 351 (11), 16384^2 1317 -> 1295 (6), 8192^2 fp64 749 -> 739
+// (6).  Below 2 % of the pass (65536^2: a reserved SM costs the DRAM-bound runs more than its edge tiles' 0.9 %) and above
+// 25 % (small grids, where the wavefront is the minor part and the constants above were not measured) nothing is
+// reserved.  wave_rows: rows of all stretches, ring strips weighted.
 static int plan_edge_reserve(long long n_edge, long long wave_rows, int sms, int k) {
     constexpr long long EDGE_ROWS = 38;
     if (n_edge <= 0 || wave_rows <= 0 || sms < 8) return 0;
     const long long edge_work = n_edge * EDGE_ROWS * WAVE_NW;  // in rows of one warp, like wave_rows
-    if (edge_work * 20 < edge_work + wave_rows || edge_work * 4 > edge_work + wave_rows) return 0;  // (5 % .. 25 % of the pass)
+    if (edge_work * 50 < edge_work + wave_rows || edge_work * 4 > edge_work + wave_rows) return 0;  // (2 % .. 25 % of the pass)
     int best = 0;
     long long best_t = -1;
     for (int r = 1; r <= sms / 2; ++r) {
@@ -1066,7 +1068,7 @@ static int plan_pass(const fdtd2d_sim* s, int k, PlanLists* pl) {
         std::vector<unsigned char> seg_ring(segs.size());
         for (size_t i = 0; i < segs.size(); ++i) seg_rows[i] = segs[i].y1 - segs[i].y0, seg_ring[i] = segs[i].side != 0;
         // whole grids: leave some SMs to the edge tiles and cut the runs for the rest (plan_edge_reserve)
-        int reserve = 0;
+        int reserve = 0, auto_ring_cost = 208;
         const long long n_edge_all = (long long)edge_band.size() + (long long)edge_rest.size();
         if (!slab && band_tasks.empty() && s->opt.edge_reserve != 0 && n_edge_all > 0) {
             if (s->opt.edge_reserve > 0) {
@@ -1075,10 +1077,13 @@ static int plan_pass(const fdtd2d_sim* s, int k, PlanLists* pl) {
                 long long wave_rows = 0;
                 for (size_t i = 0; i < segs.size(); ++i) wave_rows += seg_ring[i] ? (long long)seg_rows[i] * 208 / 100 : seg_rows[i];
                 reserve = plan_edge_reserve(n_edge_all, wave_rows, std::max(1, s->sm_count), k);
+                // one run per warp (mid-size grids, edge tiles >= 5 % of the pass): the ring runs end the kernel, and 220
+                // measured better than 208 there (4096^2: 108.2 against 109.5 us per pass)
+                if (n_edge_all * 38 * WAVE_NW * 20 >= n_edge_all * 38 * WAVE_NW + wave_rows) auto_ring_cost = 220;
             }
         }
         pl->reserve_sms = reserve;
-        const int ring_cost = s->opt.ring_cost > 0 ? s->opt.ring_cost : (reserve > 0 ? 208 : 0);
+        const int ring_cost = s->opt.ring_cost > 0 ? s->opt.ring_cost : (reserve > 0 ? auto_ring_cost : 0);
         const long long run_warps = (long long)(std::max(1, s->sm_count) - reserve) * WAVE_NW;
         plan_wave_runs(seg_rows, seg_ring, run_warps, std::max(1, s->opt.wave_run_rows), k, &parts, ring_cost);
         for (size_t i = 0; i < segs.size(); ++i) {

@@ -18,9 +18,9 @@ struct Options {
     int wave_run_rows = 640;   // cap on the rows of one wavefront run
     int edge_reserve = -1;     // whole grids: SMs the wavefront kernel leaves to the edge tiles of its pass (the runs are cut for the
                                // other SMs and launched first); 0 none (edge tiles first, wavefront on every SM), -1: automatic --
-                               // reserve when the edge tiles are >= 5 % of the pass (mid-size grids such as 4096^2)
+                               // when the edge tiles are 2 .. 25 % of the pass (4096^2: 21 SMs, 16384^2: 6)
     int ring_cost = 0;         // cost of a ring-strip row in percent of a plain row when runs are balanced, warm-up rows included;
-                               // 0: 208 with reserved SMs, else the older rule (ring runs half as long as plain runs)
+                               // 0: 208 / 220 with reserved SMs, else the older rule (ring runs half as long as plain runs)
     int auto_k12 = 0;          // k_temporal = 0 picks the 12-level wavefront when it exists (uniform permeability)
     int uniform_ch = 1;        // pass dt/(mu*dx) as a scalar when the map is uniform
     int resident = 1;          // cluster-resident kernel for small fp32 grids

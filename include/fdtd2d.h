@@ -78,7 +78,7 @@ int fdtd2d_sync(fdtd2d_sim* s);
 /* A handle copies its options when it is created; the defaults come from the environment variables FDTD2D_<KEY>
  * (upper case), read once at that moment.  fdtd2d_set_option changes one option of this handle and drops its cached
  * plans.  Keys: "wavefront" (1), "wave_min_tiles" (-1 = automatic), "ring_min_tiles" (-1), "ring_strips" (1),
- * "wave_run_rows" (640), "edge_reserve" (-1 = automatic: whole grids whose edge tiles are >= 5 % of a pass leave some SMs to
+ * "wave_run_rows" (640), "edge_reserve" (-1 = automatic: whole grids whose edge tiles are 2 .. 25 % of a pass leave some SMs to
  * them and launch the wavefront first; 0 = never, n = that many SMs), "ring_cost" (0 = automatic; percent of a plain row that
  * a ring-strip row costs when runs are balanced), "auto_k12" (0), "uniform_ch" (1), "resident" (1), "resident_cfg" (5), "resident_cluster" (0),
  * "resident_trim" (-1), "resident_rows" (0), "tma_pair" (0), "f64_k" (0 = automatic), "fuse" (0; 1 = two k = 8 passes per launch, the second fed from L2: an
@@ -211,7 +211,7 @@ int fdtd2d_pass_count(const fdtd2d_sim* s, int64_t* passes);
 int fdtd2d_plan_wave_runs(int n_stretches, const int32_t* rows, const uint8_t* ring, int warps, int cap_rows, int k,
                           int32_t* parts, int32_t* run_rows);
 /* Host-only: how many SMs the wavefront kernel of a k-step pass leaves to the pass's `n_edge` edge tiles when its stretches
- * hold `wave_rows` rows (ring-strip rows weighted by their cost); 0 = none (edge tiles below 5 % of the pass).  No
+ * hold `wave_rows` rows (ring-strip rows weighted by their cost); 0 = none (edge tiles below 2 % or above 25 % of the pass).  No
  * reference counterpart. */
 int fdtd2d_plan_edge_reserve(int64_t n_edge, int64_t wave_rows, int sm_count, int k);
 /* Host-only: how the cluster-resident kernels would split a whole fp32 grid of rows x cols (cfg: option resident_cfg,
